@@ -1,0 +1,213 @@
+// C ABI (include/exaspim_b200.h) over exa::Engine.  Nothing throws across this boundary:
+// every entry point converts Status / C++ exceptions into a negative code and a message
+// retrievable with exa_last_error().
+#include <new>
+#include <string>
+
+#include "../../include/exaspim_b200.h"
+#include "engine.h"
+
+struct exa_engine {
+  exa::Engine impl;
+  exa_engine(int device, int precision) : impl(device, precision) {}
+};
+
+namespace {
+
+thread_local std::string g_create_error;
+
+int code_for(const std::string& msg) {
+  if (msg.find("cuda") != std::string::npos || msg.find("CUDA") != std::string::npos)
+    return EXA_ERR_CUDA;
+  if (msg.find("not finalised") != std::string::npos || msg.find("not set") != std::string::npos ||
+      msg.find("no slab job") != std::string::npos)
+    return EXA_ERR_STATE;
+  return EXA_ERR_INVALID;
+}
+
+template <typename F>
+int guarded(exa_engine* e, F&& f) {
+  if (!e) return EXA_ERR_INVALID;
+  try {
+    exa::Status s = f();
+    if (s.ok) return EXA_OK;
+    e->impl.last_error = s.msg;
+    return code_for(s.msg);
+  } catch (const std::exception& ex) {
+    e->impl.last_error = std::string("exception: ") + ex.what();
+    return EXA_ERR_INVALID;
+  } catch (...) {
+    e->impl.last_error = "unknown exception";
+    return EXA_ERR_INVALID;
+  }
+}
+
+template <typename F>
+int guarded_static(F&& f) {
+  try {
+    exa::Status s = f();
+    if (s.ok) return EXA_OK;
+    g_create_error = s.msg;
+    return code_for(s.msg);
+  } catch (const std::exception& ex) {
+    g_create_error = std::string("exception: ") + ex.what();
+    return EXA_ERR_INVALID;
+  } catch (...) {
+    g_create_error = "unknown exception";
+    return EXA_ERR_INVALID;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* exa_version(void) { return "exaspim_b200 0.1 (sm_100a)"; }
+
+int exa_create(int device, int precision, exa_engine** out) {
+  if (!out) return EXA_ERR_INVALID;
+  *out = nullptr;
+  exa_engine* e = new (std::nothrow) exa_engine(device, precision);
+  if (!e) {
+    g_create_error = "out of host memory";
+    return EXA_ERR_INVALID;
+  }
+  exa::Status s;
+  try {
+    s = e->impl.init();
+  } catch (...) {
+    s = exa::Status::Err("exception during init");
+  }
+  if (!s.ok) {
+    g_create_error = s.msg;
+    delete e;
+    return code_for(s.msg);
+  }
+  *out = e;
+  return EXA_OK;
+}
+
+int exa_destroy(exa_engine* e) {
+  if (!e) return EXA_ERR_INVALID;
+  delete e;
+  return EXA_OK;
+}
+
+const char* exa_last_error(const exa_engine* e) {
+  return e ? e->impl.last_error.c_str() : g_create_error.c_str();
+}
+
+int exa_load_weight(exa_engine* e, const char* name, const void* data, const int64_t* shape,
+                    int ndim, int dtype) {
+  return guarded(e, [&] {
+    EXA_CHECK(name != nullptr, "load_weight: null name");
+    EXA_CHECK(ndim == 0 || shape != nullptr, "load_weight: null shape");
+    return e->impl.load_weight(name, data, shape, ndim, dtype);
+  });
+}
+
+int exa_finalize_weights(exa_engine* e) {
+  return guarded(e, [&] { return e->impl.finalize_weights(); });
+}
+
+int exa_out_channels(const exa_engine* e) { return e ? e->impl.out_channels() : EXA_ERR_INVALID; }
+
+int exa_forward(exa_engine* e, const float* x, float* logits, int batch, const int32_t patch[3],
+                void* stream) {
+  return guarded(e, [&] {
+    EXA_CHECK(patch != nullptr, "forward: null patch");
+    return e->impl.forward(x, logits, batch, patch, (cudaStream_t)stream);
+  });
+}
+
+int exa_predict(exa_engine* e, const uint16_t* vol, int D, int H, int W,
+                const exa_predict_params* p, float* out) {
+  return guarded(e, [&] {
+    EXA_CHECK(p != nullptr, "predict: null params");
+    return e->impl.predict_host(vol, D, H, W, *p, out);
+  });
+}
+
+int exa_predict_device(exa_engine* e, const uint16_t* vol_dev, int D, int H, int W,
+                       const exa_predict_params* p, float* out_dev, void* stream) {
+  return guarded(e, [&] {
+    EXA_CHECK(p != nullptr, "predict: null params");
+    return e->impl.predict_device(vol_dev, D, H, W, *p, out_dev, (cudaStream_t)stream);
+  });
+}
+
+int exa_plan_slab(int D, int H, int W, const exa_predict_params* p, int row_begin, int row_end,
+                  exa_slab_plan* plan) {
+  return guarded_static([&] {
+    EXA_CHECK(p && plan, "plan_slab: null argument");
+    exa::Plan pl;
+    EXA_TRY(exa::make_plan(D, H, W, *p, &pl));
+    return exa::plan_slab(pl, row_begin, row_end, plan);
+  });
+}
+
+int exa_histogram(exa_engine* e, const uint16_t* vol_dev, int64_t n, int clip, uint64_t* hist_dev,
+                  void* stream) {
+  return guarded(e, [&] {
+    return e->impl.histogram(vol_dev, n, clip, hist_dev, (cudaStream_t)stream);
+  });
+}
+
+int exa_percentiles_from_hist(const uint64_t* hist, int nbins, double q_lo, double q_hi,
+                              double* mn, double* mx) {
+  return guarded_static([&] { return exa::percentiles_from_hist(hist, nbins, q_lo, q_hi, mn, mx); });
+}
+
+int exa_set_normalization(exa_engine* e, double mn, double mx, int clip) {
+  return guarded(e, [&] { return e->impl.set_normalization(mn, mx, clip); });
+}
+
+int exa_slab_run(exa_engine* e, const uint16_t* slab_dev, int D, int H, int W,
+                 const exa_predict_params* p, int row_begin, int row_end, void* stream) {
+  return guarded(e, [&] {
+    EXA_CHECK(p != nullptr, "slab_run: null params");
+    return e->impl.slab_run(slab_dev, D, H, W, *p, row_begin, row_end, (cudaStream_t)stream);
+  });
+}
+
+int exa_slab_partial(exa_engine* e, float* halo_dev, void* stream) {
+  return guarded(e, [&] { return e->impl.slab_partial(halo_dev, (cudaStream_t)stream); });
+}
+
+int exa_slab_stitch(exa_engine* e, const float* seed_dev, float* out_dev, void* stream) {
+  return guarded(e, [&] { return e->impl.slab_stitch(seed_dev, out_dev, (cudaStream_t)stream); });
+}
+
+int exa_count_patches(int D, int H, int W, const int32_t patch[3], const int32_t overlap[3]) {
+  if (!patch || !overlap) return EXA_ERR_INVALID;
+  const int dims[3] = {D, H, W};
+  long long n = 1;
+  for (int i = 0; i < 3; ++i) {
+    if (patch[i] <= 0 || overlap[i] < 0 || overlap[i] >= patch[i]) return EXA_ERR_INVALID;
+    n *= (long long)exa::axis_starts(dims[i], patch[i], overlap[i]).size();
+  }
+  return n > 0x7fffffffLL ? EXA_ERR_INVALID : (int)n;
+}
+
+int exa_patch_starts(int D, int H, int W, const int32_t patch[3], const int32_t overlap[3],
+                     int32_t* starts, int capacity) {
+  const int n = exa_count_patches(D, H, W, patch, overlap);
+  if (n < 0) return n;
+  if (!starts || capacity < n) return EXA_ERR_INVALID;
+  const std::vector<int> sz = exa::axis_starts(D, patch[0], overlap[0]);
+  const std::vector<int> sy = exa::axis_starts(H, patch[1], overlap[1]);
+  const std::vector<int> sx = exa::axis_starts(W, patch[2], overlap[2]);
+  size_t i = 0;
+  for (int z : sz)
+    for (int y : sy)
+      for (int x : sx) {
+        starts[i++] = z;
+        starts[i++] = y;
+        starts[i++] = x;
+      }
+  return n;
+}
+
+int64_t exa_launch_count(const exa_engine* e) { return e ? e->impl.launches : -1; }
+
+}  // extern "C"

@@ -1,0 +1,750 @@
+// Engine implementation: weight folding/packing, workspace layout, the layer schedule of
+// reference unet3d.py:77-105 and the volume driver of reference inference.py:29-126.
+#include "engine.h"
+
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+namespace exa {
+
+// ---------------------------------------------------------------------------
+// pure host helpers
+// ---------------------------------------------------------------------------
+// range(0, dim - patch + stride, stride)                       (inference.py:389-393)
+std::vector<int> axis_starts(int dim, int patch, int overlap) {
+  std::vector<int> out;
+  const int stride = patch - overlap;
+  if (stride <= 0) return out;
+  for (int s = 0; s < dim - patch + stride; s += stride) out.push_back(s);
+  return out;
+}
+
+static Status check_params(const exa_predict_params& p) {
+  for (int i = 0; i < 3; ++i) {
+    EXA_CHECK(p.patch[i] > 0 && p.patch[i] % 16 == 0,
+              "patch_shape entries must be positive multiples of 16 (unet3d.py:281-288)");
+    EXA_CHECK(p.overlap[i] >= 0 && p.overlap[i] < p.patch[i], "overlap must be in [0, patch)");
+    EXA_CHECK(p.patch[i] - 2 * p.trim > 0, "trim too large for patch_shape");
+  }
+  EXA_CHECK(p.trim >= 0, "trim must be >= 0");
+  EXA_CHECK(p.brightness_clip >= 0 && p.brightness_clip <= 65535,
+            "brightness_clip must be in [0, 65535]");
+  EXA_CHECK(p.pct_lo >= 0 && p.pct_lo <= 100 && p.pct_hi >= 0 && p.pct_hi <= 100,
+            "percentiles must be in [0, 100]");
+  return Status::OK();
+}
+
+Status make_plan(int D, int H, int W, const exa_predict_params& p, Plan* plan) {
+  EXA_TRY(check_params(p));
+  EXA_CHECK(D > 0 && H > 0 && W > 0, "volume dims must be positive");
+  plan->D = D;
+  plan->H = H;
+  plan->W = W;
+  const int dims[3] = {D, H, W};
+  AxisGeom* g[3] = {&plan->az, &plan->ay, &plan->ax};
+  for (int i = 0; i < 3; ++i) {
+    g[i]->dim = dims[i];
+    g[i]->patch = p.patch[i];
+    g[i]->stride = p.patch[i] - p.overlap[i];
+    g[i]->trim = p.trim;
+    g[i]->n = (int)axis_starts(dims[i], p.patch[i], p.overlap[i]).size();
+  }
+  plan->n_patches = plan->az.n * plan->ay.n * plan->ax.n;
+  return Status::OK();
+}
+
+Status plan_slab(const Plan& plan, int row_begin, int row_end, exa_slab_plan* out) {
+  const AxisGeom& z = plan.az;
+  EXA_CHECK(row_begin >= 0 && row_begin <= row_end && row_end <= z.n, "row range out of bounds");
+  const int keep = z.patch - 2 * z.trim;
+  memset(out, 0, sizeof(*out));
+  out->nz = z.n;
+  out->ny = plan.ay.n;
+  out->nx = plan.ax.n;
+  out->n_patches = plan.n_patches;
+  if (row_begin == row_end) return Status::OK();  // empty slab: all ranges empty
+  // a plane may be covered by at most two consecutive z rows, otherwise more than the
+  // neighbouring slab would have to contribute partial sums
+  EXA_CHECK(keep <= 2 * z.stride || (row_begin == 0 && row_end == z.n),
+            "slab sharding needs patch - 2*trim <= 2*(patch - overlap) along z");
+  out->in_z0 = z.stride * row_begin;
+  out->in_z1 = std::min(z.stride * (row_end - 1) + z.patch, z.dim);
+  out->out_z0 = row_begin == 0 ? 0 : z.stride * row_begin + z.trim;
+  out->out_z1 = row_end == z.n ? z.dim : std::min(z.stride * row_end + z.trim, z.dim);
+  if (row_end < z.n) {
+    out->halo_z0 = std::min(z.stride * row_end + z.trim, z.dim);
+    out->halo_z1 = std::max(out->halo_z0, std::min(z.stride * (row_end - 1) + z.trim + keep, z.dim));
+  }
+  if (row_begin > 0) {
+    out->seed_z0 = std::min(z.stride * row_begin + z.trim, z.dim);
+    out->seed_z1 =
+        std::max(out->seed_z0, std::min(z.stride * (row_begin - 1) + z.trim + keep, z.dim));
+  }
+  return Status::OK();
+}
+
+// np.percentile(a, q) with the default method="linear" on the sorted multiset described by
+// `hist` (img_util.py:526).  Mirrors numpy's arithmetic step by step so that the float64
+// results are bit-identical: virtual index n*q + (alpha + q*(1-alpha-beta)) - 1 with
+// alpha = beta = 1, gamma = index - floor(index), and numpy's two-sided lerp.
+static double percentile_linear(const uint64_t* hist, int nbins, uint64_t n, double pct) {
+  const double q = pct / 100.0;
+  const double alpha = 1.0, beta = 1.0;
+  double vidx = (double)n * q + (alpha + q * (1.0 - alpha - beta)) - 1.0;
+  double prev = floor(vidx);
+  double gamma = vidx - prev;
+  int64_t i0 = (int64_t)prev;
+  int64_t i1 = i0 + 1;
+  const int64_t last = (int64_t)n - 1;
+  if (i0 < 0) i0 = 0;  // numpy clips / wraps indexes that fall outside [0, n-1]
+  if (i0 > last) i0 = last;
+  if (i1 < 0) i1 = 0;
+  if (i1 > last) i1 = last;
+  // order statistics i0, i1 from the histogram
+  double a = 0, b = 0;
+  uint64_t cum = 0;
+  bool got_a = false, got_b = false;
+  for (int v = 0; v < nbins && !(got_a && got_b); ++v) {
+    cum += hist[v];
+    if (!got_a && (uint64_t)i0 < cum) {
+      a = (double)v;
+      got_a = true;
+    }
+    if (!got_b && (uint64_t)i1 < cum) {
+      b = (double)v;
+      got_b = true;
+    }
+  }
+  const double diff = b - a;
+  double r = a + diff * gamma;
+  if (gamma >= 0.5) r = b - diff * (1.0 - gamma);
+  return r;
+}
+
+Status percentiles_from_hist(const uint64_t* hist, int nbins, double q_lo, double q_hi, double* mn,
+                             double* mx) {
+  EXA_CHECK(hist && nbins > 0 && mn && mx, "percentiles_from_hist: bad arguments");
+  uint64_t n = 0;
+  for (int i = 0; i < nbins; ++i) n += hist[i];
+  EXA_CHECK(n > 0, "percentiles_from_hist: empty histogram");
+  *mn = percentile_linear(hist, nbins, n, q_lo);
+  *mx = percentile_linear(hist, nbins, n, q_hi);
+  return Status::OK();
+}
+
+// ---------------------------------------------------------------------------
+// Engine: lifetime
+// ---------------------------------------------------------------------------
+static void free_dev(void* p) {
+  if (p) cudaFree(p);
+}
+
+Engine::~Engine() {
+  cudaSetDevice(device_);
+  for (auto& L : layers_) {
+    free_dev(L.w_bf16);
+    free_dev(L.w_f32);
+    free_dev(L.bias);
+  }
+  free_dev(head_w_);
+  free_dev(head_b_);
+  free_dev(ws_);
+  free_dev(lut_);
+  free_dev(probs_);
+  free_dev(starts_dev_);
+  free_dev(hist_dev_);
+}
+
+Status Engine::init() {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    return Status::Err(std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                       "); this library has no CPU fallback");
+  }
+  EXA_CHECK(device_ >= 0 && device_ < count, "device index out of range");
+  EXA_CHECK(precision_ == EXA_PRECISION_BF16 || precision_ == EXA_PRECISION_FP32,
+            "unknown precision");
+  EXA_CUDA(cudaSetDevice(device_));
+  cudaDeviceProp prop;
+  EXA_CUDA(cudaGetDeviceProperties(&prop, device_));
+  EXA_CHECK(prop.major == 10, "this library is built for sm_100a (B200) only; found sm_" +
+                                  std::to_string(prop.major) + std::to_string(prop.minor));
+  num_sms_ = prop.multiProcessorCount;
+  return Status::OK();
+}
+
+// ---------------------------------------------------------------------------
+// Engine: weights (replaces UNet3D.load_state_dict, inference.py:420-421)
+// ---------------------------------------------------------------------------
+Status Engine::load_weight(const char* name, const void* data, const int64_t* shape, int ndim,
+                           int dtype) {
+  EXA_CHECK(name && (data || ndim == 0 || true), "load_weight: null argument");
+  EXA_CHECK(ndim >= 0 && ndim <= 5, "load_weight: ndim must be <= 5");
+  EXA_CHECK(dtype == EXA_DTYPE_F32 || dtype == EXA_DTYPE_I64, "load_weight: unknown dtype");
+  HostTensor t;
+  t.dtype = dtype;
+  int64_t n = 1;
+  for (int i = 0; i < ndim; ++i) {
+    EXA_CHECK(shape[i] >= 0, "load_weight: negative dim");
+    t.shape.push_back(shape[i]);
+    n *= shape[i];
+  }
+  EXA_CHECK(data != nullptr || n == 0, "load_weight: null data");
+  if (dtype == EXA_DTYPE_F32) {
+    t.f32.assign((const float*)data, (const float*)data + n);
+  } else {
+    t.i64.assign((const int64_t*)data, (const int64_t*)data + n);
+  }
+  raw_[name] = std::move(t);
+  finalized_ = false;
+  return Status::OK();
+}
+
+namespace {
+
+struct LayerSpec {
+  const char* prefix;
+  int conv_idx, bn_idx;
+  int cin, cout;
+};
+// unet3d.py:64-74 with trilinear=True, width_multiplier=1 (inference.py:419-420)
+const LayerSpec kLayers[18] = {
+    {"inc.double_conv", 0, 1, 1, 32},
+    {"inc.double_conv", 3, 4, 32, 32},
+    {"down1.maxpool_conv.1.double_conv", 0, 1, 32, 64},
+    {"down1.maxpool_conv.1.double_conv", 3, 4, 64, 64},
+    {"down2.maxpool_conv.1.double_conv", 0, 1, 64, 128},
+    {"down2.maxpool_conv.1.double_conv", 3, 4, 128, 128},
+    {"down3.maxpool_conv.1.double_conv", 0, 1, 128, 256},
+    {"down3.maxpool_conv.1.double_conv", 3, 4, 256, 256},
+    {"down4.maxpool_conv.1.double_conv", 0, 1, 256, 256},
+    {"down4.maxpool_conv.1.double_conv", 3, 4, 256, 256},
+    {"up1.conv.double_conv", 0, 1, 512, 256},
+    {"up1.conv.double_conv", 3, 4, 256, 128},
+    {"up2.conv.double_conv", 0, 1, 256, 128},
+    {"up2.conv.double_conv", 3, 4, 128, 64},
+    {"up3.conv.double_conv", 0, 1, 128, 64},
+    {"up3.conv.double_conv", 3, 4, 64, 32},
+    {"up4.conv.double_conv", 0, 1, 64, 32},
+    {"up4.conv.double_conv", 3, 4, 32, 32},
+};
+
+uint16_t f32_to_bf16_rn(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u) return (uint16_t)((u >> 16) | ((u & 0xFFFFu) ? 0x40 : 0));
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+
+}  // namespace
+
+Status Engine::finalize_weights() {
+  EXA_CUDA(cudaSetDevice(device_));
+  std::map<std::string, bool> used;
+  auto get = [&](const std::string& key, std::vector<int64_t> shape, int dtype,
+                 const HostTensor** out) -> Status {
+    auto it = raw_.find(key);
+    EXA_CHECK(it != raw_.end(), "missing state_dict entry: " + key);
+    const HostTensor& t = it->second;
+    EXA_CHECK(t.dtype == dtype, "wrong dtype for state_dict entry: " + key);
+    EXA_CHECK(t.shape == shape, "wrong shape for state_dict entry: " + key);
+    used[key] = true;
+    *out = &t;
+    return Status::OK();
+  };
+
+  // head first: its shape decides affinity (3) vs foreground (1) mode  (unet3d.py:75,318)
+  {
+    auto it = raw_.find("outc.conv.weight");
+    EXA_CHECK(it != raw_.end(), "missing state_dict entry: outc.conv.weight");
+    EXA_CHECK(it->second.shape.size() == 5 && it->second.shape[1] == 32 &&
+                  it->second.shape[2] == 1 && it->second.shape[3] == 1 &&
+                  it->second.shape[4] == 1 && it->second.shape[0] >= 1 &&
+                  it->second.shape[0] <= 8,
+              "wrong shape for state_dict entry: outc.conv.weight");
+    out_channels_ = (int)it->second.shape[0];
+  }
+  const HostTensor *hw = nullptr, *hb = nullptr;
+  EXA_TRY(get("outc.conv.weight", {out_channels_, 32, 1, 1, 1}, EXA_DTYPE_F32, &hw));
+  EXA_TRY(get("outc.conv.bias", {out_channels_}, EXA_DTYPE_F32, &hb));
+  free_dev(head_w_);
+  free_dev(head_b_);
+  head_w_ = head_b_ = nullptr;
+  EXA_CUDA(cudaMalloc(&head_w_, sizeof(float) * out_channels_ * 32));
+  EXA_CUDA(cudaMalloc(&head_b_, sizeof(float) * out_channels_));
+  EXA_CUDA(cudaMemcpy(head_w_, hw->f32.data(), sizeof(float) * out_channels_ * 32,
+                      cudaMemcpyHostToDevice));
+  EXA_CUDA(cudaMemcpy(head_b_, hb->f32.data(), sizeof(float) * out_channels_,
+                      cudaMemcpyHostToDevice));
+
+  for (int li = 0; li < 18; ++li) {
+    const LayerSpec& sp = kLayers[li];
+    ConvLayer& L = layers_[li];
+    L.conv_key = std::string(sp.prefix) + "." + std::to_string(sp.conv_idx);
+    L.bn_key = std::string(sp.prefix) + "." + std::to_string(sp.bn_idx);
+    L.cin = sp.cin;
+    L.cout = sp.cout;
+    const HostTensor *w, *b, *g, *be, *mu, *var, *nbt;
+    EXA_TRY(get(L.conv_key + ".weight", {sp.cout, sp.cin, 3, 3, 3}, EXA_DTYPE_F32, &w));
+    EXA_TRY(get(L.conv_key + ".bias", {sp.cout}, EXA_DTYPE_F32, &b));
+    EXA_TRY(get(L.bn_key + ".weight", {sp.cout}, EXA_DTYPE_F32, &g));
+    EXA_TRY(get(L.bn_key + ".bias", {sp.cout}, EXA_DTYPE_F32, &be));
+    EXA_TRY(get(L.bn_key + ".running_mean", {sp.cout}, EXA_DTYPE_F32, &mu));
+    EXA_TRY(get(L.bn_key + ".running_var", {sp.cout}, EXA_DTYPE_F32, &var));
+    EXA_TRY(get(L.bn_key + ".num_batches_tracked", {}, EXA_DTYPE_I64, &nbt));
+
+    // eval-mode BatchNorm3d folded into the conv: y = (conv(x)+b-mu)*g/sqrt(var+eps)+beta
+    // (unet3d.py:144,147; eps = 1e-5 default)
+    std::vector<double> scale(sp.cout);
+    std::vector<float> bias(sp.cout);
+    for (int co = 0; co < sp.cout; ++co) {
+      scale[co] = (double)g->f32[co] / sqrt((double)var->f32[co] + 1e-5);
+      bias[co] = (float)(((double)b->f32[co] - (double)mu->f32[co]) * scale[co] +
+                         (double)be->f32[co]);
+    }
+    free_dev(L.bias);
+    free_dev(L.w_bf16);
+    free_dev(L.w_f32);
+    L.bias = nullptr;
+    L.w_bf16 = nullptr;
+    L.w_f32 = nullptr;
+    EXA_CUDA(cudaMalloc(&L.bias, sizeof(float) * sp.cout));
+    EXA_CUDA(cudaMemcpy(L.bias, bias.data(), sizeof(float) * sp.cout, cudaMemcpyHostToDevice));
+
+    auto wsrc = [&](int co, int ci, int tap) -> double {
+      return (double)w->f32[((size_t)co * sp.cin + ci) * 27 + tap] * scale[co];
+    };
+    if (li == 0) {
+      for (int tap = 0; tap < 27; ++tap)
+        for (int co = 0; co < 32; ++co) stem_.w[tap][co] = (float)wsrc(co, 0, tap);
+      for (int co = 0; co < 32; ++co) stem_.b[co] = bias[co];
+      continue;
+    }
+    const size_t n = (size_t)27 * sp.cin * sp.cout;
+    if (precision_ == EXA_PRECISION_BF16) {
+      std::vector<uint16_t> pk(n);  // [tap][cout][cin]: K-major B operand of the implicit GEMM
+      for (int tap = 0; tap < 27; ++tap)
+        for (int co = 0; co < sp.cout; ++co)
+          for (int ci = 0; ci < sp.cin; ++ci)
+            pk[((size_t)tap * sp.cout + co) * sp.cin + ci] = f32_to_bf16_rn((float)wsrc(co, ci, tap));
+      EXA_CUDA(cudaMalloc(&L.w_bf16, n * 2));
+      EXA_CUDA(cudaMemcpy(L.w_bf16, pk.data(), n * 2, cudaMemcpyHostToDevice));
+    } else {
+      std::vector<float> pk(n);  // [tap][cin][cout]
+      for (int tap = 0; tap < 27; ++tap)
+        for (int ci = 0; ci < sp.cin; ++ci)
+          for (int co = 0; co < sp.cout; ++co)
+            pk[((size_t)tap * sp.cin + ci) * sp.cout + co] = (float)wsrc(co, ci, tap);
+      EXA_CUDA(cudaMalloc(&L.w_f32, n * 4));
+      EXA_CUDA(cudaMemcpy(L.w_f32, pk.data(), n * 4, cudaMemcpyHostToDevice));
+    }
+  }
+  // strict: no unexpected keys (load_state_dict(strict=True), inference.py:421)
+  for (auto& kv : raw_) {
+    EXA_CHECK(used.count(kv.first), "unexpected state_dict entry: " + kv.first);
+  }
+  finalized_ = true;
+  return Status::OK();
+}
+
+// ---------------------------------------------------------------------------
+// Engine: workspace
+// ---------------------------------------------------------------------------
+namespace {
+struct WsLayout {
+  // element offsets (in units of the activation element) of every buffer
+  size_t a0, cat4, p1, d1a, cat3, p2, d2a, cat2, p3, d3a, cat1, p4, d4a, x5, u1a, u1, u2a, u2, u3a,
+      u3, total;
+};
+WsLayout layout(int B, int pz, int py, int px) {
+  auto vox = [&](int lvl) { return (size_t)B * (pz >> lvl) * (py >> lvl) * (px >> lvl); };
+  WsLayout L{};
+  size_t off = 0;
+  auto take = [&](size_t n) {
+    size_t o = off;
+    off += (n + 127) / 128 * 128;  // 256-byte alignment for bf16, more for fp32
+    return o;
+  };
+  L.a0 = take(vox(0) * 32);    // inc.0 output; re-used for up4.0 output (A0 is dead by then)
+  L.cat4 = take(vox(0) * 64);  // [x1 | up(u3)]
+  L.p1 = take(vox(1) * 32);
+  L.d1a = take(vox(1) * 64);
+  L.cat3 = take(vox(1) * 128);  // [x2 | up(u2)]
+  L.p2 = take(vox(2) * 64);
+  L.d2a = take(vox(2) * 128);
+  L.cat2 = take(vox(2) * 256);  // [x3 | up(u1)]
+  L.p3 = take(vox(3) * 128);
+  L.d3a = take(vox(3) * 256);
+  L.cat1 = take(vox(3) * 512);  // [x4 | up(x5)]
+  L.p4 = take(vox(4) * 256);
+  L.d4a = take(vox(4) * 256);
+  L.x5 = take(vox(4) * 256);
+  L.u1a = take(vox(3) * 256);
+  L.u1 = take(vox(3) * 128);
+  L.u2a = take(vox(2) * 128);
+  L.u2 = take(vox(2) * 64);
+  L.u3a = take(vox(1) * 64);
+  L.u3 = take(vox(1) * 32);
+  L.total = off;
+  return L;
+}
+}  // namespace
+
+Status Engine::ensure_workspace(int batch, int pz, int py, int px) {
+  const size_t esz = precision_ == EXA_PRECISION_BF16 ? 2 : 4;
+  const size_t need = layout(batch, pz, py, px).total * esz;
+  if (need > ws_bytes_) {
+    free_dev(ws_);
+    ws_ = nullptr;
+    ws_bytes_ = 0;
+    EXA_CUDA(cudaMalloc(&ws_, need));
+    ws_bytes_ = need;
+  }
+  return Status::OK();
+}
+
+Status Engine::conv(const ConvLayer& L, const Act& in, const Act& out, const HeadParams* head,
+                    cudaStream_t s) {
+  ++launches;
+  if (precision_ == EXA_PRECISION_BF16) {
+    return launch_conv_umma(in, out, L.w_bf16, L.bias, head, num_sms_, s);
+  }
+  EXA_TRY(launch_conv_fp32(in, out, L.w_f32, L.bias, s));
+  if (head) {
+    ++launches;
+    EXA_TRY(launch_head_fp32(out, *head, s));
+  }
+  return Status::OK();
+}
+
+// One wave of `batch` patches through the whole network (unet3d.py:77-105).
+Status Engine::run_network(const PatchSource& src, int batch, int pz, int py, int px,
+                           const HeadParams& head, cudaStream_t s) {
+  EXA_CHECK(finalized_, "weights not finalised");
+  EXA_TRY(ensure_workspace(batch, pz, py, px));
+  const bool f32 = precision_ == EXA_PRECISION_FP32;
+  const size_t esz = f32 ? 4 : 2;
+  const WsLayout L = layout(batch, pz, py, px);
+  auto act = [&](size_t off, int lvl, int C, int cstride, int coff) {
+    Act a;
+    a.ptr = (char*)ws_ + off * esz;
+    a.B = batch;
+    a.D = pz >> lvl;
+    a.H = py >> lvl;
+    a.W = px >> lvl;
+    a.C = C;
+    a.cstride = cstride;
+    a.coff = coff;
+    a.fp32 = f32;
+    return a;
+  };
+  const Act a0 = act(L.a0, 0, 32, 32, 0);
+  const Act x1 = act(L.cat4, 0, 32, 64, 0), up4_slot = act(L.cat4, 0, 32, 64, 32),
+            cat4 = act(L.cat4, 0, 64, 64, 0);
+  const Act p1 = act(L.p1, 1, 32, 32, 0), d1a = act(L.d1a, 1, 64, 64, 0);
+  const Act x2 = act(L.cat3, 1, 64, 128, 0), up3_slot = act(L.cat3, 1, 64, 128, 64),
+            cat3 = act(L.cat3, 1, 128, 128, 0);
+  const Act p2 = act(L.p2, 2, 64, 64, 0), d2a = act(L.d2a, 2, 128, 128, 0);
+  const Act x3 = act(L.cat2, 2, 128, 256, 0), up2_slot = act(L.cat2, 2, 128, 256, 128),
+            cat2 = act(L.cat2, 2, 256, 256, 0);
+  const Act p3 = act(L.p3, 3, 128, 128, 0), d3a = act(L.d3a, 3, 256, 256, 0);
+  const Act x4 = act(L.cat1, 3, 256, 512, 0), up1_slot = act(L.cat1, 3, 256, 512, 256),
+            cat1 = act(L.cat1, 3, 512, 512, 0);
+  const Act p4 = act(L.p4, 4, 256, 256, 0), d4a = act(L.d4a, 4, 256, 256, 0),
+            x5 = act(L.x5, 4, 256, 256, 0);
+  const Act u1a = act(L.u1a, 3, 256, 256, 0), u1 = act(L.u1, 3, 128, 128, 0);
+  const Act u2a = act(L.u2a, 2, 128, 128, 0), u2 = act(L.u2, 2, 64, 64, 0);
+  const Act u3a = act(L.u3a, 1, 64, 64, 0), u3 = act(L.u3, 1, 32, 32, 0);
+  const Act u4a = a0;  // alias: A0 is dead after inc.3
+  // fp32 mode needs a real buffer for the last conv's activations before the head
+  const Act u4 = act(L.cat4, 0, 32, 32, 0);  // cat4 is dead once up4.0 has run
+
+  auto pool = [&](const Act& i, const Act& o) {
+    ++launches;
+    return launch_maxpool(i, o, s);
+  };
+  auto up = [&](const Act& i, const Act& o) {
+    ++launches;
+    return launch_upsample(i, o, s);
+  };
+
+  ++launches;
+  EXA_TRY(launch_stem(src, stem_, a0, s));                  // inc.0 (+gather/normalise)
+  EXA_TRY(conv(layers_[1], a0, x1, nullptr, s));            // inc.3 -> skip slot of CAT4
+  EXA_TRY(pool(x1, p1));
+  EXA_TRY(conv(layers_[2], p1, d1a, nullptr, s));
+  EXA_TRY(conv(layers_[3], d1a, x2, nullptr, s));
+  EXA_TRY(pool(x2, p2));
+  EXA_TRY(conv(layers_[4], p2, d2a, nullptr, s));
+  EXA_TRY(conv(layers_[5], d2a, x3, nullptr, s));
+  EXA_TRY(pool(x3, p3));
+  EXA_TRY(conv(layers_[6], p3, d3a, nullptr, s));
+  EXA_TRY(conv(layers_[7], d3a, x4, nullptr, s));
+  EXA_TRY(pool(x4, p4));
+  EXA_TRY(conv(layers_[8], p4, d4a, nullptr, s));
+  EXA_TRY(conv(layers_[9], d4a, x5, nullptr, s));
+  EXA_TRY(up(x5, up1_slot));                                // cat([x4, up(x5)])  unet3d.py:288
+  EXA_TRY(conv(layers_[10], cat1, u1a, nullptr, s));
+  EXA_TRY(conv(layers_[11], u1a, u1, nullptr, s));
+  EXA_TRY(up(u1, up2_slot));
+  EXA_TRY(conv(layers_[12], cat2, u2a, nullptr, s));
+  EXA_TRY(conv(layers_[13], u2a, u2, nullptr, s));
+  EXA_TRY(up(u2, up3_slot));
+  EXA_TRY(conv(layers_[14], cat3, u3a, nullptr, s));
+  EXA_TRY(conv(layers_[15], u3a, u3, nullptr, s));
+  EXA_TRY(up(u3, up4_slot));
+  EXA_TRY(conv(layers_[16], cat4, u4a, nullptr, s));
+  EXA_TRY(conv(layers_[17], u4a, u4, &head, s));            // + 1x1x1 head (+sigmoid, trim)
+  return Status::OK();
+}
+
+// ---------------------------------------------------------------------------
+// Engine: operator-level forward (replaces UNet3D.forward, unet3d.py:77-105)
+// ---------------------------------------------------------------------------
+Status Engine::forward(const float* x, float* logits, int batch, const int32_t patch[3],
+                       cudaStream_t s) {
+  EXA_CUDA(cudaSetDevice(device_));
+  EXA_CHECK(x && logits && batch > 0, "forward: bad arguments");
+  for (int i = 0; i < 3; ++i)
+    EXA_CHECK(patch[i] > 0 && patch[i] % 16 == 0, "forward: patch dims must be multiples of 16");
+  PatchSource src;
+  src.x = x;
+  HeadParams head;
+  head.w = head_w_;
+  head.b = head_b_;
+  head.out = logits;
+  head.C = out_channels_;
+  head.trim = 0;
+  head.apply_sigmoid = 0;
+  return run_network(src, batch, patch[0], patch[1], patch[2], head, s);
+}
+
+// ---------------------------------------------------------------------------
+// Engine: volume driver (replaces predict, inference.py:29-126)
+// ---------------------------------------------------------------------------
+Status Engine::histogram(const uint16_t* vol_dev, int64_t n, int clip, uint64_t* hist_dev,
+                         cudaStream_t s) {
+  EXA_CUDA(cudaSetDevice(device_));
+  EXA_CHECK(vol_dev && hist_dev && n >= 0, "histogram: bad arguments");
+  ++launches;
+  return launch_histogram(vol_dev, (size_t)n, clip, (unsigned long long*)hist_dev, s);
+}
+
+// LUT of (min(v,clip) - mn) / (mx - mn + 1e-8) clipped to [0,1], evaluated in float64 and
+// rounded to float32 exactly where the reference does (img_util.py:527-531; the cast happens
+// on assignment into the float32 batch array, inference.py:188-191).
+Status Engine::set_normalization(double mn, double mx, int clip) {
+  EXA_CUDA(cudaSetDevice(device_));
+  EXA_CHECK(clip >= 0 && clip <= 65535, "brightness_clip must be in [0, 65535]");
+  std::vector<float> lut(clip + 1);
+  const double den = mx - mn + 1e-8;
+  for (int v = 0; v <= clip; ++v) {
+    double t = ((double)v - mn) / den;
+    t = t < 0.0 ? 0.0 : (t > 1.0 ? 1.0 : t);
+    lut[v] = (float)t;
+  }
+  if (lut_clip_ != clip) {
+    free_dev(lut_);
+    lut_ = nullptr;
+    EXA_CUDA(cudaMalloc(&lut_, sizeof(float) * (clip + 1)));
+    lut_clip_ = clip;
+  }
+  EXA_CUDA(cudaMemcpy(lut_, lut.data(), sizeof(float) * (clip + 1), cudaMemcpyHostToDevice));
+  norm_set_ = true;
+  return Status::OK();
+}
+
+Status Engine::slab_run(const uint16_t* slab_dev, int D, int H, int W, const exa_predict_params& p,
+                        int row_begin, int row_end, cudaStream_t s) {
+  EXA_CUDA(cudaSetDevice(device_));
+  EXA_CHECK(finalized_, "weights not finalised");
+  EXA_CHECK(norm_set_, "normalisation not set (exa_set_normalization)");
+  EXA_CHECK(lut_clip_ == p.brightness_clip, "normalisation was set for a different brightness_clip");
+  EXA_TRY(make_plan(D, H, W, p, &plan_));
+  EXA_TRY(plan_slab(plan_, row_begin, row_end, &slab_));
+  row_begin_ = row_begin;
+  row_end_ = row_end;
+  job_ready_ = false;
+  const int rows = row_end - row_begin;
+  const int per_row = plan_.ay.n * plan_.ax.n;
+  const int n_slab = rows * per_row;
+  if (n_slab == 0) {
+    job_ready_ = true;
+    return Status::OK();
+  }
+  EXA_CHECK(slab_dev != nullptr, "slab_run: null volume");
+  const int t = p.trim;
+  const size_t per_patch =
+      (size_t)out_channels_ * (p.patch[0] - 2 * t) * (p.patch[1] - 2 * t) * (p.patch[2] - 2 * t);
+  const size_t need = per_patch * n_slab * sizeof(float);
+  if (need > probs_bytes_) {
+    free_dev(probs_);
+    probs_ = nullptr;
+    probs_bytes_ = 0;
+    EXA_CUDA(cudaMalloc(&probs_, need));
+    probs_bytes_ = need;
+  }
+  // patch starts of this slab in the reference's order (inference.py:394-397)
+  std::vector<int> starts((size_t)n_slab * 3);
+  {
+    size_t i = 0;
+    for (int kz = row_begin; kz < row_end; ++kz)
+      for (int ky = 0; ky < plan_.ay.n; ++ky)
+        for (int kx = 0; kx < plan_.ax.n; ++kx) {
+          starts[i++] = kz * plan_.az.stride;
+          starts[i++] = ky * plan_.ay.stride;
+          starts[i++] = kx * plan_.ax.stride;
+        }
+  }
+  if (starts.size() > starts_cap_) {
+    free_dev(starts_dev_);
+    starts_dev_ = nullptr;
+    starts_cap_ = 0;
+    EXA_CUDA(cudaMalloc(&starts_dev_, starts.size() * sizeof(int)));
+    starts_cap_ = starts.size();
+  }
+  EXA_CUDA(cudaMemcpyAsync(starts_dev_, starts.data(), starts.size() * sizeof(int),
+                           cudaMemcpyHostToDevice, s));
+  EXA_CUDA(cudaStreamSynchronize(s));  // `starts` is a stack-lifetime host buffer
+
+  int batch = p.batch > 0 ? p.batch : 32;
+  batch = std::min(batch, n_slab);
+  for (int i0 = 0; i0 < n_slab; i0 += batch) {
+    const int nb = std::min(batch, n_slab - i0);
+    PatchSource src;
+    src.vol = slab_dev;
+    src.gD = D;
+    src.gH = H;
+    src.gW = W;
+    src.vz0 = slab_.in_z0;
+    src.vD = slab_.in_z1 - slab_.in_z0;
+    src.lut = lut_;
+    src.clip = p.brightness_clip;
+    src.starts = starts_dev_ + (size_t)i0 * 3;
+    HeadParams head;
+    head.w = head_w_;
+    head.b = head_b_;
+    head.out = probs_ + (size_t)i0 * per_patch;
+    head.C = out_channels_;
+    head.trim = t;
+    head.apply_sigmoid = 1;  // inference.py:158
+    EXA_TRY(run_network(src, nb, p.patch[0], p.patch[1], p.patch[2], head, s));
+  }
+  job_ready_ = true;
+  return Status::OK();
+}
+
+static StitchArgs stitch_base(const Plan& plan, const float* probs, int C, int row_begin,
+                              int row_end) {
+  StitchArgs a;
+  a.probs = probs;
+  a.C = C;
+  a.az = plan.az;
+  a.ay = plan.ay;
+  a.ax = plan.ax;
+  a.row_begin = row_begin;
+  a.row_end = row_end;
+  return a;
+}
+
+Status Engine::slab_partial(float* halo_dev, cudaStream_t s) {
+  EXA_CUDA(cudaSetDevice(device_));
+  EXA_CHECK(job_ready_, "slab_partial: no slab job (call exa_slab_run first)");
+  const int nz = slab_.halo_z1 - slab_.halo_z0;
+  if (nz <= 0) return Status::OK();
+  EXA_CHECK(halo_dev != nullptr, "slab_partial: null buffer");
+  StitchArgs a = stitch_base(plan_, probs_, out_channels_, row_begin_, row_end_);
+  a.z_begin = slab_.halo_z0;
+  a.z_end = slab_.halo_z1;
+  a.out = halo_dev;
+  a.out_cstride = (size_t)nz * plan_.H * plan_.W;
+  a.finalize = 0;
+  ++launches;
+  return launch_stitch(a, s);
+}
+
+Status Engine::slab_stitch(const float* seed_dev, float* out_dev, cudaStream_t s) {
+  EXA_CUDA(cudaSetDevice(device_));
+  EXA_CHECK(job_ready_, "slab_stitch: no slab job (call exa_slab_run first)");
+  const int nz = slab_.out_z1 - slab_.out_z0;
+  if (nz <= 0) return Status::OK();
+  EXA_CHECK(out_dev != nullptr, "slab_stitch: null buffer");
+  StitchArgs a = stitch_base(plan_, probs_, out_channels_, row_begin_, row_end_);
+  a.z_begin = slab_.out_z0;
+  a.z_end = slab_.out_z1;
+  a.out = out_dev;
+  a.out_cstride = (size_t)nz * plan_.H * plan_.W;
+  a.finalize = 1;
+  if (seed_dev != nullptr && slab_.seed_z1 > slab_.seed_z0) {
+    a.seed = seed_dev;
+    a.seed_z0 = slab_.seed_z0;
+    a.seed_z1 = slab_.seed_z1;
+  }
+  ++launches;
+  return launch_stitch(a, s);
+}
+
+Status Engine::predict_device(const uint16_t* vol_dev, int D, int H, int W,
+                              const exa_predict_params& p, float* out_dev, cudaStream_t s) {
+  EXA_CUDA(cudaSetDevice(device_));
+  EXA_CHECK(vol_dev && out_dev, "predict: null buffer");
+  Plan plan;
+  EXA_TRY(make_plan(D, H, W, p, &plan));
+  const int bins = p.brightness_clip + 1;
+  if (!hist_dev_) EXA_CUDA(cudaMalloc(&hist_dev_, sizeof(unsigned long long) * 65536));
+  EXA_TRY(histogram(vol_dev, (int64_t)D * H * W, p.brightness_clip, (uint64_t*)hist_dev_, s));
+  std::vector<uint64_t> hist(bins);
+  EXA_CUDA(cudaMemcpyAsync(hist.data(), hist_dev_, sizeof(uint64_t) * bins, cudaMemcpyDeviceToHost,
+                           s));
+  EXA_CUDA(cudaStreamSynchronize(s));
+  double mn = 0, mx = 0;
+  EXA_TRY(percentiles_from_hist(hist.data(), bins, p.pct_lo, p.pct_hi, &mn, &mx));
+  EXA_TRY(set_normalization(mn, mx, p.brightness_clip));
+  EXA_TRY(slab_run(vol_dev, D, H, W, p, 0, plan.az.n, s));
+  if (plan.n_patches == 0) {  // volume smaller than one stride: the reference returns zeros
+    EXA_CUDA(cudaMemsetAsync(out_dev, 0, sizeof(float) * out_channels_ * (size_t)D * H * W, s));
+    return Status::OK();
+  }
+  return slab_stitch(nullptr, out_dev, s);
+}
+
+Status Engine::predict_host(const uint16_t* vol, int D, int H, int W, const exa_predict_params& p,
+                            float* out) {
+  EXA_CUDA(cudaSetDevice(device_));
+  EXA_CHECK(vol && out, "predict: null buffer");
+  EXA_CHECK(finalized_, "weights not finalised");
+  EXA_TRY(check_params(p));
+  EXA_CHECK(D > 0 && H > 0 && W > 0, "volume dims must be positive");
+  const size_t nvox = (size_t)D * H * W;
+  uint16_t* vol_dev = nullptr;
+  float* out_dev = nullptr;
+  Status st = Status::OK();
+  cudaStream_t s = nullptr;
+  do {
+    if (cudaMalloc(&vol_dev, nvox * 2 + 16) != cudaSuccess ||
+        cudaMalloc(&out_dev, nvox * 4 * out_channels_) != cudaSuccess) {
+      st = Status::Err(std::string("predict: device allocation failed: ") +
+                       cudaGetErrorString(cudaGetLastError()));
+      break;
+    }
+    if (cudaMemcpyAsync(vol_dev, vol, nvox * 2, cudaMemcpyHostToDevice, s) != cudaSuccess) {
+      st = Status::Err("predict: H2D copy failed");
+      break;
+    }
+    st = predict_device(vol_dev, D, H, W, p, out_dev, s);
+    if (!st.ok) break;
+    cudaError_t e =
+        cudaMemcpyAsync(out, out_dev, nvox * 4 * out_channels_, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) st = Status::Err(std::string("predict: D2H failed: ") + cudaGetErrorString(e));
+  } while (0);
+  free_dev(vol_dev);
+  free_dev(out_dev);
+  return st;
+}
+
+}  // namespace exa

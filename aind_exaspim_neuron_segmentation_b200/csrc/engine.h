@@ -1,0 +1,105 @@
+// Engine: owns folded/packed weights, activation workspaces and the per-volume job state.
+// Host-side mirror of reference inference.py:29-126 (predict) + unet3d.py:77-105 (forward),
+// scheduling the sm_100a kernels layer by layer over batches of patches.
+#pragma once
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/exaspim_b200.h"
+#include "kernels.h"
+
+namespace exa {
+
+struct HostTensor {
+  std::vector<int64_t> shape;
+  int dtype = EXA_DTYPE_F32;
+  std::vector<float> f32;
+  std::vector<int64_t> i64;
+};
+
+struct ConvLayer {
+  std::string conv_key, bn_key;
+  int cin = 0, cout = 0;
+  __nv_bfloat16* w_bf16 = nullptr;  // [27][cout][cin]   (tcgen05 path)
+  float* w_f32 = nullptr;           // [27][cin][cout]   (fp32 validation path)
+  float* bias = nullptr;            // [cout] folded
+};
+
+struct Plan {
+  int D = 0, H = 0, W = 0;
+  AxisGeom az, ay, ax;
+  int n_patches = 0;
+};
+
+// pure host helpers (also exported through the C ABI)
+std::vector<int> axis_starts(int dim, int patch, int overlap);
+Status make_plan(int D, int H, int W, const exa_predict_params& p, Plan* plan);
+Status plan_slab(const Plan& plan, int row_begin, int row_end, exa_slab_plan* out);
+Status percentiles_from_hist(const uint64_t* hist, int nbins, double q_lo, double q_hi, double* mn,
+                             double* mx);
+
+class Engine {
+ public:
+  Engine(int device, int precision) : device_(device), precision_(precision) {}
+  ~Engine();
+  Status init();
+  Status load_weight(const char* name, const void* data, const int64_t* shape, int ndim, int dtype);
+  Status finalize_weights();
+  int out_channels() const { return out_channels_; }
+
+  Status forward(const float* x, float* logits, int batch, const int32_t patch[3], cudaStream_t s);
+  Status predict_host(const uint16_t* vol, int D, int H, int W, const exa_predict_params& p,
+                      float* out);
+  Status predict_device(const uint16_t* vol_dev, int D, int H, int W, const exa_predict_params& p,
+                        float* out_dev, cudaStream_t s);
+  Status histogram(const uint16_t* vol_dev, int64_t n, int clip, uint64_t* hist_dev,
+                   cudaStream_t s);
+  Status set_normalization(double mn, double mx, int clip);
+  Status slab_run(const uint16_t* slab_dev, int D, int H, int W, const exa_predict_params& p,
+                  int row_begin, int row_end, cudaStream_t s);
+  Status slab_partial(float* halo_dev, cudaStream_t s);
+  Status slab_stitch(const float* seed_dev, float* out_dev, cudaStream_t s);
+
+  std::string last_error;
+  int64_t launches = 0;
+
+ private:
+  Status ensure_workspace(int batch, int pz, int py, int px);
+  Status run_network(const PatchSource& src, int batch, int pz, int py, int px,
+                     const HeadParams& head, cudaStream_t s);
+  Status conv(const ConvLayer& L, const Act& in, const Act& out, const HeadParams* head,
+              cudaStream_t s);
+
+  int device_, precision_;
+  int num_sms_ = 148;
+  bool finalized_ = false;
+  int out_channels_ = 0;
+  std::map<std::string, HostTensor> raw_;
+  ConvLayer layers_[18];
+  StemWeights stem_{};
+  float* head_w_ = nullptr;
+  float* head_b_ = nullptr;
+
+  // activation workspace
+  void* ws_ = nullptr;
+  size_t ws_bytes_ = 0;
+  int ws_batch_ = 0, ws_p_[3] = {0, 0, 0};
+  // normalisation LUT
+  float* lut_ = nullptr;
+  int lut_clip_ = -1;
+  bool norm_set_ = false;
+  // per-volume job
+  Plan plan_;
+  exa_slab_plan slab_{};
+  int row_begin_ = 0, row_end_ = 0;
+  bool job_ready_ = false;
+  float* probs_ = nullptr;
+  size_t probs_bytes_ = 0;
+  int* starts_dev_ = nullptr;
+  size_t starts_cap_ = 0;
+  unsigned long long* hist_dev_ = nullptr;
+};
+
+}  // namespace exa

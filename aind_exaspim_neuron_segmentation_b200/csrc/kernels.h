@@ -1,0 +1,81 @@
+// Internal launch API of the sm_100a kernels (host side).  Everything is
+// stream-ordered and returns a Status; nothing here synchronises.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace exa {
+
+// NDHWC activation view.  `C` channels are addressed inside a buffer whose voxel
+// stride is `cstride` elements, starting at channel `coff` (concat buffers).
+struct Act {
+  void* ptr = nullptr;
+  int B = 0, D = 0, H = 0, W = 0;
+  int C = 0, cstride = 0, coff = 0;
+  bool fp32 = false;
+  size_t voxels() const { return (size_t)B * D * H * W; }
+};
+
+// Folded weights of the Cin=1 stem conv (reference inc.double_conv.0 + BN .1).
+struct StemWeights {
+  float w[27][32];
+  float b[32];
+};
+
+struct PatchSource {
+  // (a) patches gathered from a uint16 volume slab with clip + LUT normalisation
+  //     (reference inference.py:79-80,188-191; img_util.py:378-379,424-428,526-531)
+  const uint16_t* vol = nullptr;
+  int gD = 0, gH = 0, gW = 0;  // global volume dims
+  int vz0 = 0, vD = 0;         // planes [vz0, vz0+vD) are resident in `vol`
+  const float* lut = nullptr;  // [clip+1] float32 normalised values
+  int clip = 0;
+  const int* starts = nullptr;  // device [B][3] (z, y, x)
+  // (b) ready-made float32 patches (B,1,P,P,P)  (operator-level forward)
+  const float* x = nullptr;
+};
+
+struct HeadParams {
+  const float* w = nullptr;  // [C][32]
+  const float* b = nullptr;  // [C]
+  float* out = nullptr;      // [B][C][D-2t][H-2t][W-2t]
+  int C = 0;
+  int trim = 0;
+  int apply_sigmoid = 0;
+};
+
+// Sliding-window geometry along one axis (reference inference.py:389-393, 101-105).
+struct AxisGeom {
+  int dim = 0, patch = 0, stride = 0, trim = 0, n = 0;
+};
+
+struct StitchArgs {
+  const float* probs = nullptr;  // [n_slots][C][Pt][Pt][Pt]
+  int C = 0;
+  AxisGeom az, ay, ax;
+  int row_begin = 0, row_end = 0;  // z rows whose patches are resident in `probs`
+  int z_begin = 0, z_end = 0;      // output planes to produce
+  float* out = nullptr;            // [C][z_end-z_begin][H][W] (plane z_begin first), stride below
+  size_t out_cstride = 0;          // elements between channels of `out`
+  int finalize = 1;                // 1: divide by coverage count; 0: raw partial sums
+  const float* seed = nullptr;     // optional partial sums [C][seed_z1-seed_z0][H][W] added FIRST
+  int seed_z0 = 0, seed_z1 = 0;
+};
+
+Status launch_stem(const PatchSource& src, const StemWeights& w, const Act& out, cudaStream_t s);
+Status launch_conv_umma(const Act& in, const Act& out, const __nv_bfloat16* w_packed,
+                        const float* bias, const HeadParams* head, int num_sms, cudaStream_t s);
+Status launch_conv_fp32(const Act& in, const Act& out, const float* w_packed, const float* bias,
+                        cudaStream_t s);
+Status launch_head_fp32(const Act& in, const HeadParams& head, cudaStream_t s);
+Status launch_maxpool(const Act& in, const Act& out, cudaStream_t s);
+Status launch_upsample(const Act& in, const Act& out, cudaStream_t s);
+Status launch_histogram(const uint16_t* vol, size_t n, int clip, unsigned long long* hist,
+                        cudaStream_t s);
+Status launch_stitch(const StitchArgs& a, cudaStream_t s);
+
+}  // namespace exa

@@ -1,0 +1,598 @@
+// Memory-bound kernels of the affinity-prediction path (all HBM-bound byte/elementwise
+// work: coalesced, 16-byte vectorised, no tensor cores) plus the fp32 validation conv.
+//
+//   K0   histogram of min(v, clip)                    reference inference.py:79, img_util.py:526
+//   K0b  patch gather + LUT normalise + reflect pad,
+//        fused with the Cin=1 stem conv               inference.py:188-191, img_util.py:378-379,
+//                                                     424-428, 527-531; unet3d.py:143-145 (inc.0)
+//   K3   2x2x2 max-pool                               unet3d.py:195
+//   K4   trilinear x2 upsample (align_corners=True)
+//        written into the concat slot                 unet3d.py:248-250, 288
+//   K5'  1x1x1 head + sigmoid + trim (fp32 mode)      unet3d.py:318, inference.py:158-162
+//   K6   overlap stitch + coverage normalisation      inference.py:99-125
+//   Kf   fp32 SIMT 3x3x3 conv (validation mode)       unet3d.py:143-148
+#include "kernels.h"
+
+namespace exa {
+
+// ---------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------
+template <typename T>
+struct Vec8;  // 8 channels
+template <>
+struct Vec8<__nv_bfloat16> {
+  uint4 raw;
+  __device__ void load(const __nv_bfloat16* p) { raw = *reinterpret_cast<const uint4*>(p); }
+  __device__ void store(__nv_bfloat16* p) const { *reinterpret_cast<uint4*>(p) = raw; }
+  __device__ void to_float(float (&f)[8]) const {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 t = __bfloat1622float2(h[i]);
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
+  }
+  __device__ void from_float(const float (&f)[8]) {
+    raw.x = pack_bf16x2(f[0], f[1]);
+    raw.y = pack_bf16x2(f[2], f[3]);
+    raw.z = pack_bf16x2(f[4], f[5]);
+    raw.w = pack_bf16x2(f[6], f[7]);
+  }
+};
+template <>
+struct Vec8<float> {
+  float4 a, b;
+  __device__ void load(const float* p) {
+    a = *reinterpret_cast<const float4*>(p);
+    b = *reinterpret_cast<const float4*>(p + 4);
+  }
+  __device__ void store(float* p) const {
+    *reinterpret_cast<float4*>(p) = a;
+    *reinterpret_cast<float4*>(p + 4) = b;
+  }
+  __device__ void to_float(float (&f)[8]) const {
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+    f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  }
+  __device__ void from_float(const float (&f)[8]) {
+    a = make_float4(f[0], f[1], f[2], f[3]);
+    b = make_float4(f[4], f[5], f[6], f[7]);
+  }
+};
+
+// np.pad(mode="reflect") index for position p >= 0 in a box of length L (edge not repeated).
+__device__ __forceinline__ int reflect_index(int p, int L) {
+  if (L <= 1) return 0;
+  const int period = 2 * (L - 1);
+  p %= period;
+  return p < L ? p : period - p;
+}
+
+// ---------------------------------------------------------------------------
+// K0: histogram
+// ---------------------------------------------------------------------------
+constexpr int HIST_SMEM_BINS = 4096;
+
+__global__ void __launch_bounds__(512)
+histogram_kernel(const uint16_t* __restrict__ vol, size_t n, int clip,
+                 unsigned long long* __restrict__ hist) {
+  extern __shared__ unsigned int sh[];
+  const int bins = clip + 1;
+  const bool use_smem = bins <= HIST_SMEM_BINS;
+  if (use_smem) {
+    for (int i = threadIdx.x; i < bins; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+  }
+  const size_t n8 = n / 8;
+  const uint4* v8 = reinterpret_cast<const uint4*>(vol);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    const uint4 q = __ldg(v8 + i);
+    const unsigned int w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int lo = min((int)(w[k] & 0xFFFFu), clip);
+      const int hi = min((int)(w[k] >> 16), clip);
+      if (use_smem) {
+        atomicAdd(&sh[lo], 1u);
+        atomicAdd(&sh[hi], 1u);
+      } else {
+        atomicAdd(&hist[lo], 1ull);
+        atomicAdd(&hist[hi], 1ull);
+      }
+    }
+  }
+  // tail (n not a multiple of 8)
+  if (blockIdx.x == 0) {
+    for (size_t i = n8 * 8 + threadIdx.x; i < n; i += blockDim.x) {
+      const int v = min((int)vol[i], clip);
+      if (use_smem) atomicAdd(&sh[v], 1u);
+      else atomicAdd(&hist[v], 1ull);
+    }
+  }
+  if (use_smem) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < bins; i += blockDim.x) {
+      const unsigned int c = sh[i];
+      if (c) atomicAdd(&hist[i], (unsigned long long)c);
+    }
+  }
+}
+
+Status launch_histogram(const uint16_t* vol, size_t n, int clip, unsigned long long* hist,
+                        cudaStream_t s) {
+  EXA_CHECK(clip >= 0 && clip <= 65535, "brightness_clip must be in [0, 65535]");
+  EXA_CHECK(((uintptr_t)vol & 15) == 0, "volume pointer must be 16-byte aligned");
+  EXA_CUDA(cudaMemsetAsync(hist, 0, sizeof(unsigned long long) * (clip + 1), s));
+  if (n == 0) return Status::OK();
+  const int bins = clip + 1;
+  const size_t smem = bins <= HIST_SMEM_BINS ? sizeof(unsigned int) * bins : 0;
+  int blocks = (int)std::min<size_t>((n / 8 + 511) / 512 + 1, 148 * 4);
+  histogram_kernel<<<blocks, 512, smem, s>>>(vol, n, clip, hist);
+  EXA_CUDA(cudaGetLastError());
+  return Status::OK();
+}
+
+// ---------------------------------------------------------------------------
+// K0b + stem conv (Cin = 1 -> 32), SIMT fp32
+// ---------------------------------------------------------------------------
+struct StemArgs {
+  PatchSource src;
+  int B, Pz, Py, Px;
+  void* out;
+};
+
+constexpr int ST_TX = 16, ST_TY = 8, ST_TZ = 8;
+
+template <typename T, bool FROM_VOLUME>
+__global__ void __launch_bounds__(128)
+stem_kernel(const __grid_constant__ StemWeights wt, const StemArgs a) {
+  __shared__ float tile[ST_TZ + 2][ST_TY + 2][ST_TX + 2];
+  const int ntx = a.Px / ST_TX;
+  const int x0 = (blockIdx.x % ntx) * ST_TX;
+  const int y0 = (blockIdx.x / ntx) * ST_TY;
+  const int z0 = blockIdx.y * ST_TZ;
+  const int b = blockIdx.z;
+
+  int sz = 0, sy = 0, sx = 0, Lz = 0, Ly = 0, Lx = 0;
+  if (FROM_VOLUME) {
+    sz = a.src.starts[3 * b + 0];
+    sy = a.src.starts[3 * b + 1];
+    sx = a.src.starts[3 * b + 2];
+    Lz = min(a.Pz, a.src.gD - sz);  // clipped box lengths (img_util.py:424-428)
+    Ly = min(a.Py, a.src.gH - sy);
+    Lx = min(a.Px, a.src.gW - sx);
+  }
+  constexpr int TILE_N = (ST_TZ + 2) * (ST_TY + 2) * (ST_TX + 2);
+  for (int i = threadIdx.x; i < TILE_N; i += blockDim.x) {
+    const int lx = i % (ST_TX + 2);
+    const int ly = (i / (ST_TX + 2)) % (ST_TY + 2);
+    const int lz = i / ((ST_TX + 2) * (ST_TY + 2));
+    const int px = x0 + lx - 1, py = y0 + ly - 1, pz = z0 + lz - 1;
+    float v = 0.f;  // conv zero padding outside the patch (unet3d.py:143, padding=1)
+    if (px >= 0 && px < a.Px && py >= 0 && py < a.Py && pz >= 0 && pz < a.Pz) {
+      if (FROM_VOLUME) {
+        const int gz = sz + (pz < Lz ? pz : reflect_index(pz, Lz));
+        const int gy = sy + (py < Ly ? py : reflect_index(py, Ly));
+        const int gx = sx + (px < Lx ? px : reflect_index(px, Lx));
+        const size_t idx = ((size_t)(gz - a.src.vz0) * a.src.gH + gy) * a.src.gW + gx;
+        const int raw = min((int)__ldg(a.src.vol + idx), a.src.clip);
+        v = __ldg(a.src.lut + raw);
+      } else {
+        v = __ldg(a.src.x + (((size_t)b * a.Pz + pz) * a.Py + py) * a.Px + px);
+      }
+    }
+    tile[lz][ly][lx] = v;
+  }
+  __syncthreads();
+
+  const int tx = threadIdx.x % ST_TX, ty = threadIdx.x / ST_TX;
+  T* outp = reinterpret_cast<T*>(a.out);
+#pragma unroll 1
+  for (int tz = 0; tz < ST_TZ; ++tz) {
+    float acc[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) acc[c] = wt.b[c];
+#pragma unroll
+    for (int kz = 0; kz < 3; ++kz)
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const float v = tile[tz + kz][ty + ky][tx + kx];
+#pragma unroll
+          for (int c = 0; c < 32; ++c) acc[c] = fmaf(v, wt.w[kz * 9 + ky * 3 + kx][c], acc[c]);
+        }
+    const size_t vox = (((size_t)b * a.Pz + (z0 + tz)) * a.Py + (y0 + ty)) * a.Px + (x0 + tx);
+    T* dst = outp + vox * 32;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = leaky_relu(acc[8 * g + j]);
+      Vec8<T> o;
+      o.from_float(f);
+      o.store(dst + 8 * g);
+    }
+  }
+}
+
+Status launch_stem(const PatchSource& src, const StemWeights& w, const Act& out, cudaStream_t s) {
+  EXA_CHECK(out.C == 32 && out.cstride == 32 && out.coff == 0, "stem output must be dense C=32");
+  EXA_CHECK(out.W % ST_TX == 0 && out.H % ST_TY == 0 && out.D % ST_TZ == 0,
+            "patch dims must be multiples of 16");
+  StemArgs a;
+  a.src = src;
+  a.B = out.B;
+  a.Pz = out.D;
+  a.Py = out.H;
+  a.Px = out.W;
+  a.out = out.ptr;
+  dim3 grid((out.W / ST_TX) * (out.H / ST_TY), out.D / ST_TZ, out.B);
+  const bool from_vol = src.vol != nullptr;
+  EXA_CHECK(from_vol || src.x != nullptr, "stem: no input source");
+  if (out.fp32) {
+    if (from_vol) stem_kernel<float, true><<<grid, 128, 0, s>>>(w, a);
+    else stem_kernel<float, false><<<grid, 128, 0, s>>>(w, a);
+  } else {
+    if (from_vol) stem_kernel<__nv_bfloat16, true><<<grid, 128, 0, s>>>(w, a);
+    else stem_kernel<__nv_bfloat16, false><<<grid, 128, 0, s>>>(w, a);
+  }
+  EXA_CUDA(cudaGetLastError());
+  return Status::OK();
+}
+
+// ---------------------------------------------------------------------------
+// K3: 2x2x2 max-pool, NDHWC, 8 channels (16 B for bf16) per thread
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+maxpool_kernel(const T* __restrict__ in, int in_cstride, int in_coff, T* __restrict__ out,
+               int out_cstride, int out_coff, int B, int Do, int Ho, int Wo, int C) {
+  const int cv = C / 8;
+  const size_t total = (size_t)B * Do * Ho * Wo * cv;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c8 = (int)(i % cv);
+  size_t v = i / cv;
+  const int xo = (int)(v % Wo);
+  v /= Wo;
+  const int yo = (int)(v % Ho);
+  v /= Ho;
+  const int zo = (int)(v % Do);
+  const int b = (int)(v / Do);
+  const int Di = 2 * Do, Hi = 2 * Ho, Wi = 2 * Wo;
+  float m[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+#pragma unroll
+  for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const size_t vox = (((size_t)b * Di + 2 * zo + dz) * Hi + 2 * yo + dy) * Wi + 2 * xo + dx;
+        Vec8<T> q;
+        q.load(in + vox * in_cstride + in_coff + 8 * c8);
+        float f[8];
+        q.to_float(f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
+      }
+  const size_t ovox = (((size_t)b * Do + zo) * Ho + yo) * Wo + xo;
+  Vec8<T> o;
+  o.from_float(m);  // max of bf16 values is a bf16 value: no extra rounding
+  o.store(out + ovox * out_cstride + out_coff + 8 * c8);
+}
+
+Status launch_maxpool(const Act& in, const Act& out, cudaStream_t s) {
+  EXA_CHECK(in.fp32 == out.fp32 && in.C == out.C && in.C % 8 == 0, "maxpool: type/channel mismatch");
+  EXA_CHECK(in.D == 2 * out.D && in.H == 2 * out.H && in.W == 2 * out.W && in.B == out.B,
+            "maxpool: shape mismatch");
+  const size_t total = out.voxels() * (out.C / 8);
+  const int blocks = (int)ceil_div64((int64_t)total, 256);
+  if (in.fp32)
+    maxpool_kernel<float><<<blocks, 256, 0, s>>>((const float*)in.ptr, in.cstride, in.coff,
+                                                  (float*)out.ptr, out.cstride, out.coff, out.B,
+                                                  out.D, out.H, out.W, out.C);
+  else
+    maxpool_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(
+        (const __nv_bfloat16*)in.ptr, in.cstride, in.coff, (__nv_bfloat16*)out.ptr, out.cstride,
+        out.coff, out.B, out.D, out.H, out.W, out.C);
+  EXA_CUDA(cudaGetLastError());
+  return Status::OK();
+}
+
+// ---------------------------------------------------------------------------
+// K4: trilinear x2 upsample, align_corners=True, into a concat slot
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+upsample_kernel(const T* __restrict__ in, int in_cstride, int in_coff, T* __restrict__ out,
+                int out_cstride, int out_coff, int B, int Di, int Hi, int Wi, int C) {
+  const int Do = 2 * Di, Ho = 2 * Hi, Wo = 2 * Wi;
+  const int cv = C / 8;
+  const size_t total = (size_t)B * Do * Ho * Wo * cv;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c8 = (int)(i % cv);
+  size_t v = i / cv;
+  const int xo = (int)(v % Wo);
+  v /= Wo;
+  const int yo = (int)(v % Ho);
+  v /= Ho;
+  const int zo = (int)(v % Do);
+  const int b = (int)(v / Do);
+  // src = dst * (in-1)/(out-1), computed in fp32 like ATen's area_pixel_compute_source_index
+  const float sz = (Do > 1) ? (float)(Di - 1) / (float)(Do - 1) : 0.f;
+  const float sy = (Ho > 1) ? (float)(Hi - 1) / (float)(Ho - 1) : 0.f;
+  const float sx = (Wo > 1) ? (float)(Wi - 1) / (float)(Wo - 1) : 0.f;
+  const float fz = sz * zo, fy = sy * yo, fx = sx * xo;
+  const int z0 = (int)fz, y0 = (int)fy, x0 = (int)fx;
+  const int z1 = z0 + (z0 < Di - 1 ? 1 : 0), y1 = y0 + (y0 < Hi - 1 ? 1 : 0),
+            x1 = x0 + (x0 < Wi - 1 ? 1 : 0);
+  const float wz1 = fz - z0, wy1 = fy - y0, wx1 = fx - x0;
+  const float wz0 = 1.f - wz1, wy0 = 1.f - wy1, wx0 = 1.f - wx1;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  const int zs[2] = {z0, z1}, ys[2] = {y0, y1}, xs[2] = {x0, x1};
+  const float wz[2] = {wz0, wz1}, wy[2] = {wy0, wy1}, wx[2] = {wx0, wx1};
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int bb = 0; bb < 2; ++bb)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const size_t vox = (((size_t)b * Di + zs[a]) * Hi + ys[bb]) * Wi + xs[c];
+        Vec8<T> q;
+        q.load(in + vox * in_cstride + in_coff + 8 * c8);
+        float f[8];
+        q.to_float(f);
+        const float w = wz[a] * wy[bb] * wx[c];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(w, f[j], acc[j]);
+      }
+  const size_t ovox = (((size_t)b * Do + zo) * Ho + yo) * Wo + xo;
+  Vec8<T> o;
+  o.from_float(acc);
+  o.store(out + ovox * out_cstride + out_coff + 8 * c8);
+}
+
+Status launch_upsample(const Act& in, const Act& out, cudaStream_t s) {
+  EXA_CHECK(in.fp32 == out.fp32 && in.C == out.C && in.C % 8 == 0, "upsample: type/channel mismatch");
+  EXA_CHECK(out.D == 2 * in.D && out.H == 2 * in.H && out.W == 2 * in.W && in.B == out.B,
+            "upsample: shape mismatch");
+  const size_t total = out.voxels() * (out.C / 8);
+  const int blocks = (int)ceil_div64((int64_t)total, 256);
+  if (in.fp32)
+    upsample_kernel<float><<<blocks, 256, 0, s>>>((const float*)in.ptr, in.cstride, in.coff,
+                                                   (float*)out.ptr, out.cstride, out.coff, in.B,
+                                                   in.D, in.H, in.W, in.C);
+  else
+    upsample_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(
+        (const __nv_bfloat16*)in.ptr, in.cstride, in.coff, (__nv_bfloat16*)out.ptr, out.cstride,
+        out.coff, in.B, in.D, in.H, in.W, in.C);
+  EXA_CUDA(cudaGetLastError());
+  return Status::OK();
+}
+
+// ---------------------------------------------------------------------------
+// K5' (fp32 validation mode): 1x1x1 head + sigmoid + trim
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+head_fp32_kernel(const float* __restrict__ in, int cstride, int coff, int B, int D, int H, int W,
+                 const float* __restrict__ hw, const float* __restrict__ hb, float* __restrict__ out,
+                 int C, int trim, int apply_sigmoid) {
+  const int Dz = D - 2 * trim, Hy = H - 2 * trim, Wx = W - 2 * trim;
+  const size_t total = (size_t)B * Dz * Hy * Wx;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int x = (int)(i % Wx);
+  size_t v = i / Wx;
+  const int y = (int)(v % Hy);
+  v /= Hy;
+  const int z = (int)(v % Dz);
+  const int b = (int)(v / Dz);
+  const size_t vox = (((size_t)b * D + z + trim) * H + y + trim) * W + x + trim;
+  const float* src = in + vox * cstride + coff;
+  float f[32];
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    const float4 q = *reinterpret_cast<const float4*>(src + 4 * g);
+    f[4 * g] = q.x; f[4 * g + 1] = q.y; f[4 * g + 2] = q.z; f[4 * g + 3] = q.w;
+  }
+  for (int oc = 0; oc < C; ++oc) {
+    float s = __ldg(hb + oc);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) s = fmaf(__ldg(hw + oc * 32 + j), f[j], s);
+    if (apply_sigmoid) s = 1.f / (1.f + expf(-s));
+    out[((((size_t)b * C + oc) * Dz + z) * Hy + y) * Wx + x] = s;
+  }
+}
+
+Status launch_head_fp32(const Act& in, const HeadParams& h, cudaStream_t s) {
+  EXA_CHECK(in.fp32 && in.C == 32, "head_fp32 expects 32 fp32 channels");
+  const size_t total =
+      (size_t)in.B * (in.D - 2 * h.trim) * (in.H - 2 * h.trim) * (in.W - 2 * h.trim);
+  const int blocks = (int)ceil_div64((int64_t)total, 256);
+  head_fp32_kernel<<<blocks, 256, 0, s>>>((const float*)in.ptr, in.cstride, in.coff, in.B, in.D,
+                                           in.H, in.W, h.w, h.b, h.out, h.C, h.trim,
+                                           h.apply_sigmoid);
+  EXA_CUDA(cudaGetLastError());
+  return Status::OK();
+}
+
+// ---------------------------------------------------------------------------
+// K6: overlap stitch (gather form) + coverage normalisation
+// ---------------------------------------------------------------------------
+// For an output coordinate p along an axis, windows k with
+//   k*stride + trim <= p < min(k*stride + trim + keep, dim)      (inference.py:101-105)
+// cover it; keep = patch - 2*trim.  [k_lo, k_hi] is that index range clamped to [0, n).
+__device__ __forceinline__ void cover_range(const AxisGeom& g, int p, int& k_lo, int& k_hi) {
+  const int keep = g.patch - 2 * g.trim;
+  const int q = p - g.trim;  // need k*stride <= q  and  q < k*stride + keep
+  if (q < 0) {
+    k_lo = 0;
+    k_hi = -1;
+    return;
+  }
+  k_hi = min(q / g.stride, g.n - 1);
+  const int t = q - keep + 1;  // need k*stride >= t
+  k_lo = t <= 0 ? 0 : (t + g.stride - 1) / g.stride;
+}
+
+__global__ void __launch_bounds__(256)
+stitch_kernel(const StitchArgs a) {
+  const int H = a.ay.dim, W = a.ax.dim;
+  const int nz = a.z_end - a.z_begin;
+  const size_t total = (size_t)nz * H * W;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int x = (int)(i % W);
+  const int y = (int)((i / W) % H);
+  const int zl = (int)(i / ((size_t)W * H));
+  const int z = a.z_begin + zl;
+
+  int kz0, kz1, ky0, ky1, kx0, kx1;
+  cover_range(a.az, z, kz0, kz1);
+  cover_range(a.ay, y, ky0, ky1);
+  cover_range(a.ax, x, kx0, kx1);
+  // global coverage count (all rows, also those owned by other slabs)
+  const int cnt = max(kz1 - kz0 + 1, 0) * max(ky1 - ky0 + 1, 0) * max(kx1 - kx0 + 1, 0);
+  // restrict z rows to the resident slab
+  const int rz0 = max(kz0, a.row_begin), rz1 = min(kz1, a.row_end - 1);
+
+  const int Pt_z = a.az.patch - 2 * a.az.trim, Pt_y = a.ay.patch - 2 * a.ay.trim,
+            Pt_x = a.ax.patch - 2 * a.ax.trim;
+  const size_t chan = (size_t)Pt_z * Pt_y * Pt_x;
+  for (int c = 0; c < a.C; ++c) {
+    float acc = 0.f;
+    if (a.seed != nullptr && z >= a.seed_z0 && z < a.seed_z1) {
+      acc = a.seed[(((size_t)c * (a.seed_z1 - a.seed_z0) + (z - a.seed_z0)) * H + y) * W + x];
+    }
+    // same order as the reference's patch loop: z-major, then y, then x (inference.py:396,115)
+    for (int kz = rz0; kz <= rz1; ++kz) {
+      const int lz = z - (kz * a.az.stride + a.az.trim);
+      for (int ky = ky0; ky <= ky1; ++ky) {
+        const int ly = y - (ky * a.ay.stride + a.ay.trim);
+        for (int kx = kx0; kx <= kx1; ++kx) {
+          const int lx = x - (kx * a.ax.stride + a.ax.trim);
+          const size_t slot = ((size_t)(kz - a.row_begin) * a.ay.n + ky) * a.ax.n + kx;
+          acc += __ldg(a.probs + (slot * a.C + c) * chan + ((size_t)lz * Pt_y + ly) * Pt_x + lx);
+        }
+      }
+    }
+    if (a.finalize && cnt > 0) acc = acc / (float)cnt;
+    a.out[(size_t)c * a.out_cstride + ((size_t)zl * H + y) * W + x] = acc;
+  }
+}
+
+Status launch_stitch(const StitchArgs& a, cudaStream_t s) {
+  const size_t total = (size_t)(a.z_end - a.z_begin) * a.ay.dim * a.ax.dim;
+  if (total == 0) return Status::OK();
+  const int blocks = (int)ceil_div64((int64_t)total, 256);
+  stitch_kernel<<<blocks, 256, 0, s>>>(a);
+  EXA_CUDA(cudaGetLastError());
+  return Status::OK();
+}
+
+// ---------------------------------------------------------------------------
+// Kf: fp32 SIMT 3x3x3 conv + bias + LeakyReLU (validation mode)
+//   block = 128 voxels (linear run of the flattened B*D*H*W index) x 32 output channels,
+//   256 threads, each 4 voxels x 4 channels; K loop = 27 taps x 16-channel chunks.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+conv3x3_fp32_kernel(const float* __restrict__ in, int in_cstride, int in_coff,
+                    const float* __restrict__ w,  // [27][Cin][Cout]
+                    const float* __restrict__ bias, float* __restrict__ out, int out_cstride,
+                    int out_coff, int B, int D, int H, int W, int Cin, int Cout) {
+  __shared__ float As[16][128 + 4];
+  __shared__ __align__(16) float Ws[16][32];
+  const size_t nvox = (size_t)B * D * H * W;
+  const size_t v0 = (size_t)blockIdx.x * 128;
+  const int n0 = blockIdx.y * 32;
+  const int t = threadIdx.x;
+  // loader role: voxel lv, channel half lh (8 channels)
+  const int lv = t >> 1, lh = (t & 1) * 8;
+  const size_t lvox = v0 + lv;
+  int lx = 0, ly = 0, lz = 0, lb = 0;
+  const bool lvalid = lvox < nvox;
+  if (lvalid) {
+    size_t r = lvox;
+    lx = (int)(r % W); r /= W;
+    ly = (int)(r % H); r /= H;
+    lz = (int)(r % D);
+    lb = (int)(r / D);
+  }
+  // compute role
+  const int vg = t & 31, cg = t >> 5;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int tap = 0; tap < 27; ++tap) {
+    const int kz = tap / 9 - 1, ky = (tap / 3) % 3 - 1, kx = tap % 3 - 1;
+    const int sx = lx + kx, sy = ly + ky, sz = lz + kz;
+    const bool inb = lvalid && sx >= 0 && sx < W && sy >= 0 && sy < H && sz >= 0 && sz < D;
+    const float* src = in + ((((size_t)lb * D + sz) * H + sy) * W + sx) * in_cstride + in_coff + lh;
+    for (int c0 = 0; c0 < Cin; c0 += 16) {
+      float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;
+      if (inb) {
+        q0 = *reinterpret_cast<const float4*>(src + c0);
+        q1 = *reinterpret_cast<const float4*>(src + c0 + 4);
+      }
+      // weights: 16 x 32 floats, 2 per thread
+      const int wr = t >> 4, wc = (t & 15) * 2;
+      const float2 wq = *reinterpret_cast<const float2*>(w + ((size_t)tap * Cin + c0 + wr) * Cout + n0 + wc);
+      __syncthreads();
+      As[lh + 0][lv] = q0.x; As[lh + 1][lv] = q0.y; As[lh + 2][lv] = q0.z; As[lh + 3][lv] = q0.w;
+      As[lh + 4][lv] = q1.x; As[lh + 5][lv] = q1.y; As[lh + 6][lv] = q1.z; As[lh + 7][lv] = q1.w;
+      Ws[wr][wc] = wq.x;
+      Ws[wr][wc + 1] = wq.y;
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const float4 av = *reinterpret_cast<const float4*>(&As[k][vg * 4]);
+        const float4 wv = *reinterpret_cast<const float4*>(&Ws[k][cg * 4]);
+        const float a4[4] = {av.x, av.y, av.z, av.w};
+        const float w4[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a4[i], w4[j], acc[i][j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const size_t vox = v0 + vg * 4 + i;
+    if (vox < nvox) {
+      float4 o;
+      o.x = leaky_relu(acc[i][0] + bias[n0 + cg * 4 + 0]);
+      o.y = leaky_relu(acc[i][1] + bias[n0 + cg * 4 + 1]);
+      o.z = leaky_relu(acc[i][2] + bias[n0 + cg * 4 + 2]);
+      o.w = leaky_relu(acc[i][3] + bias[n0 + cg * 4 + 3]);
+      *reinterpret_cast<float4*>(out + vox * out_cstride + out_coff + n0 + cg * 4) = o;
+    }
+  }
+}
+
+Status launch_conv_fp32(const Act& in, const Act& out, const float* w, const float* bias,
+                        cudaStream_t s) {
+  EXA_CHECK(in.fp32 && out.fp32, "conv_fp32 expects fp32 activations");
+  EXA_CHECK(in.C % 16 == 0 && out.C % 32 == 0, "conv_fp32: Cin%16 / Cout%32");
+  EXA_CHECK(in.B == out.B && in.D == out.D && in.H == out.H && in.W == out.W, "conv_fp32: shape");
+  dim3 grid((unsigned)ceil_div64((int64_t)in.voxels(), 128), out.C / 32);
+  conv3x3_fp32_kernel<<<grid, 256, 0, s>>>((const float*)in.ptr, in.cstride, in.coff, w, bias,
+                                           (float*)out.ptr, out.cstride, out.coff, in.B, in.D,
+                                           in.H, in.W, in.C, out.C);
+  EXA_CUDA(cudaGetLastError());
+  return Status::OK();
+}
+
+}  // namespace exa

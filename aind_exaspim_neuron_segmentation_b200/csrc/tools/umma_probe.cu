@@ -1,0 +1,305 @@
+// Hardware probe (development tool, not on the product path).
+//
+// Answers three design questions for the implicit-GEMM conv kernel on a real
+// B200 before the kernel is built around them:
+//  1. descriptor sanity: TMA(SWIZZLE_128B / 64B) -> tcgen05.mma -> tcgen05.ld
+//     reproduces a CPU GEMM exactly (small-integer data);
+//  2. "halo view": can one TMA-loaded (18 x 10) halo tile be re-used for all
+//     9 in-plane taps by only moving the UMMA descriptor start address by
+//     (ky*10 + kx) rows with SBO = 10 rows (unaligned 8-row groups)?
+//  3. issue-rate of M=128 MMAs from shared memory as a function of N.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o umma_probe umma_probe.cu
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../common.cuh"
+#include "../tmap.h"
+
+using namespace exa;
+
+#define CK(x)                                                                          \
+  do {                                                                                 \
+    cudaError_t e = (x);                                                               \
+    if (e != cudaSuccess) {                                                            \
+      printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__);   \
+      exit(2);                                                                         \
+    }                                                                                  \
+  } while (0)
+
+struct ProbeArgs {
+  int halo;         // 1: halo box (10 x 18) + offset descriptor; 0: plain (8 x 16) box at shifted coords
+  int ky, kx;       // in-plane tap
+  int z;            // input plane
+  int tap;          // weight tap index for B
+  int n;            // MMA N
+  int use_base_offset;
+  int b_row_off;    // B descriptor starts at this row (multiple of 8)
+  float* out;       // [128][n]
+};
+
+template <int ROW_BYTES>
+__global__ void __launch_bounds__(128, 1)
+probe_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+             const ProbeArgs a) {
+  constexpr int KC = ROW_BYTES / 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;                       // up to 180 rows
+  uint8_t* sB = smem + 32768;               // up to 256 rows
+  uint64_t* bars = (uint64_t*)(smem + 32768 + 32768);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bars[0]), 1);
+    mbar_init(smem_u32(&bars[1]), 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (threadIdx.x == 0) {
+    const int rowsA = a.halo ? 180 : 128;
+    mbar_expect_tx(smem_u32(&bars[0]), rowsA * ROW_BYTES + 256 * ROW_BYTES);
+    if (a.halo)
+      tma_load_5d(smem_u32(sA), &tmap_x, smem_u32(&bars[0]), 0, -1, -1, a.z, 0);
+    else
+      tma_load_5d(smem_u32(sA), &tmap_x, smem_u32(&bars[0]), 0, a.kx - 1, a.ky - 1, a.z, 0);
+    tma_load_3d(smem_u32(sB), &tmap_w, smem_u32(&bars[0]), 0, 0, a.tap);
+    mbar_wait(smem_u32(&bars[0]), 0);
+    tc_fence_after();
+    uint32_t a_addr = smem_u32(sA);
+    uint64_t adesc;
+    if (a.halo) {
+      a_addr += (a.ky * 10 + a.kx) * ROW_BYTES;
+      adesc = umma_smem_desc<ROW_BYTES>(a_addr);
+      // SBO = 10 rows
+      adesc &= ~((uint64_t)0x3FFF << 32);
+      adesc |= (uint64_t)((10 * ROW_BYTES) >> 4) << 32;
+      if (a.use_base_offset) adesc |= (uint64_t)((a_addr >> 7) & 7) << 49;
+    } else {
+      adesc = umma_smem_desc<ROW_BYTES>(a_addr);
+    }
+    uint64_t bdesc = umma_smem_desc<ROW_BYTES>(smem_u32(sB) + a.b_row_off * ROW_BYTES);
+    const uint32_t idesc = umma_idesc_bf16(128, a.n);
+    for (int k = 0; k < KC / 16; ++k) umma_bf16(tmem, adesc + 2 * k, bdesc + 2 * k, idesc, k > 0);
+    umma_commit(smem_u32(&bars[1]));
+  }
+  __syncwarp();
+  mbar_wait(smem_u32(&bars[1]), 0);
+  tc_fence_after();
+  const int row = warp * 32 + lane;
+  for (int c0 = 0; c0 < a.n; c0 += 32) {
+    uint32_t r[32];
+    tmem_ld_32x32(tmem + ((uint32_t)(warp * 32) << 16) + c0, r);
+    tmem_ld_wait();
+    for (int j = 0; j < 32; ++j) a.out[row * a.n + c0 + j] = __uint_as_float(r[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 256);
+}
+
+// ---- issue-rate probe ------------------------------------------------------
+// 32 MMAs fully unrolled per loop trip with compile-time descriptor offsets, so the
+// single issuing thread is not the limiter.  ACCS = number of TMEM accumulators cycled.
+template <int N, int ACCS>
+__global__ void __launch_bounds__(128, 1)
+rate_kernel(int iters, long long* cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + 196608);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 4);
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 196608 / 16; i += blockDim.x) ((uint4*)smem)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bars[0]), 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), 512);
+    tmem_relinquish();
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int warp_u = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  if (warp_u == 0) {
+    constexpr uint32_t idesc = umma_idesc_bf16(128, N);
+    const uint64_t a0 = umma_smem_desc<128>(smem_u32(smem));
+    const uint64_t b0 = umma_smem_desc<128>(smem_u32(smem) + 98304);
+    long long t0 = clock64();
+    if (elect_one()) {
+      for (int it = 0; it < iters; it += 32) {
+#pragma unroll
+        for (int u = 0; u < 32; ++u) {
+          const uint64_t adesc = a0 + (uint64_t)(((u >> 2) & 3) * 1024 + 2 * (u & 3));
+          const uint64_t bdesc = b0 + (uint64_t)(((u >> 2) & 1) * 2048 + 2 * (u & 3));
+          umma_bf16(tmem + (uint32_t)(((u >> 2) % ACCS) * N), adesc, bdesc, idesc, 1);
+        }
+      }
+      umma_commit(smem_u32(&bars[0]));
+    }
+    __syncwarp();
+    mbar_wait(smem_u32(&bars[0]), 0);
+    long long t1 = clock64();
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+template <int N, int ACCS>
+static void run_rate(int sms, long long* dcyc) {
+  const size_t smem_bytes = 196608 + 64 + 1024;
+  CK(cudaFuncSetAttribute(rate_kernel<N, ACCS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  const int iters = 8192;
+  for (int grid : {1, sms}) {
+    rate_kernel<N, ACCS><<<grid, 128, smem_bytes>>>(iters, dcyc);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("rate kernel error %s\n", cudaGetErrorString(e)); exit(3); }
+    std::vector<long long> h(grid);
+    CK(cudaMemcpy(h.data(), dcyc, sizeof(long long) * grid, cudaMemcpyDeviceToHost));
+    long long mx = 0;
+    for (auto v : h) mx = v > mx ? v : mx;
+    double cyc = (double)mx / iters;
+    printf("RATE accs=%d N=%3d grid=%3d : %.2f cyc/MMA (ideal %.1f) -> %.1f%% of tensor peak\n", ACCS, N,
+           grid, cyc, N / 2.0, 100.0 * (N / 2.0) / cyc);
+  }
+}
+
+// ---- host ------------------------------------------------------------------
+static inline float bf16_to_f(uint16_t h) {
+  uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+static inline uint16_t f_to_bf16(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  return (uint16_t)(u >> 16);  // exact for the small values used here
+}
+
+int main() {
+  const int D = 3, H = 24, W = 16, NW = 256;
+  int failures = 0;
+  for (int rb : {128, 64}) {
+    const int C = rb / 2;
+    std::vector<uint16_t> hx((size_t)D * H * W * C), hw((size_t)27 * NW * C);
+    uint32_t s = 12345u + rb;
+    auto rnd = [&]() {
+      s = s * 1664525u + 1013904223u;
+      return (float)((int)((s >> 16) % 9) - 4) * 0.25f;
+    };
+    for (auto& v : hx) v = f_to_bf16(rnd());
+    for (auto& v : hw) v = f_to_bf16(rnd());
+    uint16_t *dx, *dw;
+    float* dout;
+    CK(cudaMalloc(&dx, hx.size() * 2));
+    CK(cudaMalloc(&dw, hw.size() * 2));
+    CK(cudaMalloc(&dout, 128 * 256 * 4));
+    CK(cudaMemcpy(dx, hx.data(), hx.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dw, hw.data(), hw.size() * 2, cudaMemcpyHostToDevice));
+
+    CUtensorMap tx_plain, tx_halo, tw;
+    {
+      uint64_t dims[5] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)D, 1};
+      uint64_t str[4] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2,
+                         (uint64_t)D * H * W * C * 2};
+      uint32_t box_plain[5] = {(uint32_t)C, 8, 16, 1, 1};
+      uint32_t box_halo[5] = {(uint32_t)C, 10, 18, 1, 1};
+      Status st = make_tmap_bf16(&tx_plain, dx, 5, dims, str, box_plain, rb);
+      if (!st.ok) { printf("tmap plain: %s\n", st.msg.c_str()); return 2; }
+      st = make_tmap_bf16(&tx_halo, dx, 5, dims, str, box_halo, rb);
+      if (!st.ok) { printf("tmap halo: %s\n", st.msg.c_str()); return 2; }
+      uint64_t wd[3] = {(uint64_t)C, (uint64_t)NW, 27};
+      uint64_t ws[2] = {(uint64_t)C * 2, (uint64_t)NW * C * 2};
+      uint32_t wb[3] = {(uint32_t)C, 256, 1};
+      st = make_tmap_bf16(&tw, dw, 3, wd, ws, wb, rb);
+      if (!st.ok) { printf("tmap w: %s\n", st.msg.c_str()); return 2; }
+    }
+    const size_t smem_bytes = 32768 + 32768 + 64 + 1024;
+    if (rb == 128) CK(cudaFuncSetAttribute(probe_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    else CK(cudaFuncSetAttribute(probe_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+
+    // tile origin (x0,y0) = (0,0) so the halo box starts at (-1,-1): exercises OOB zero fill,
+    // and H=24 > 16+1, W=16 > 8+1 so the far halo is real data.
+    auto run = [&](int halo, int ky, int kx, int z, int n, int use_bo, int b_row_off, const char* name) {
+      ProbeArgs a;
+      a.halo = halo; a.ky = ky; a.kx = kx; a.z = z; a.tap = (ky * 3 + kx); a.n = n;
+      a.use_base_offset = use_bo; a.b_row_off = b_row_off; a.out = dout;
+      CK(cudaMemset(dout, 0xff, 128 * 256 * 4));
+      if (rb == 128) probe_kernel<128><<<1, 128, smem_bytes>>>(halo ? tx_halo : tx_plain, tw, a);
+      else probe_kernel<64><<<1, 128, smem_bytes>>>(halo ? tx_halo : tx_plain, tw, a);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) {
+        printf("[rb=%d] %-28s ky=%d kx=%d n=%d : LAUNCH ERROR %s\n", rb, name, ky, kx, n, cudaGetErrorString(e));
+        exit(3);
+      }
+      std::vector<float> ho((size_t)128 * n);
+      CK(cudaMemcpy(ho.data(), dout, ho.size() * 4, cudaMemcpyDeviceToHost));
+      double maxerr = 0;
+      int bad = 0;
+      for (int r = 0; r < 128; ++r) {
+        const int ty = r / 8, tx = r % 8;
+        const int y = ty + ky - 1, x = tx + kx - 1;
+        for (int j = 0; j < n; ++j) {
+          float ref = 0.f;
+          if (y >= 0 && y < H && x >= 0 && x < W)
+            for (int c = 0; c < C; ++c)
+              ref += bf16_to_f(hx[(((size_t)z * H + y) * W + x) * C + c]) *
+                     bf16_to_f(hw[((size_t)a.tap * NW + b_row_off + j) * C + c]);
+          double err = fabs((double)ref - (double)ho[(size_t)r * n + j]);
+          if (!(err <= 1e-6)) ++bad;
+          if (err > maxerr || err != err) maxerr = err;
+        }
+      }
+      printf("[rb=%3d] %-28s ky=%d kx=%d z=%d n=%3d brow=%3d : max_err=%g bad=%d %s\n", rb, name, ky, kx, z, n,
+             b_row_off, maxerr, bad, bad ? "MISMATCH" : "ok");
+      return bad;
+    };
+    // 1. plain path, several N
+    for (int n : {32, 64, 96, 128, 256}) failures += run(0, 1, 1, 1, n, 0, 0, "plain") ? 1 : 0;
+    failures += run(0, 0, 0, 0, 32, 0, 0, "plain/oob") ? 1 : 0;
+    failures += run(0, 2, 2, 2, 64, 0, 32, "plain/b_row_off") ? 1 : 0;
+    // 2. halo view, base_offset = 0
+    int halo_bad0 = 0, halo_bad1 = 0;
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) halo_bad0 += run(1, ky, kx, 1, 96, 0, 0, "halo/base_offset=0") ? 1 : 0;
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) halo_bad1 += run(1, ky, kx, 1, 96, 1, 0, "halo/base_offset=addr") ? 1 : 0;
+    printf("[rb=%3d] SUMMARY halo base_offset=0: %d/9 taps bad; base_offset=addr: %d/9 taps bad\n", rb, halo_bad0,
+           halo_bad1);
+    cudaFree(dx); cudaFree(dw); cudaFree(dout);
+  }
+
+  // 3. issue rate
+  {
+    int dev = 0, sms = 0;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    long long* dcyc;
+    CK(cudaMalloc(&dcyc, sizeof(long long) * sms));
+    run_rate<32, 1>(sms, dcyc);  run_rate<32, 4>(sms, dcyc);
+    run_rate<64, 1>(sms, dcyc);  run_rate<64, 4>(sms, dcyc);
+    run_rate<96, 1>(sms, dcyc);  run_rate<96, 4>(sms, dcyc);
+    run_rate<128, 1>(sms, dcyc); run_rate<128, 4>(sms, dcyc);
+    run_rate<192, 1>(sms, dcyc); run_rate<192, 2>(sms, dcyc);
+    run_rate<256, 1>(sms, dcyc); run_rate<256, 2>(sms, dcyc);
+    cudaFree(dcyc);
+  }
+  printf("PROBE DONE failures(plain)=%d\n", failures);
+  return 0;
+}

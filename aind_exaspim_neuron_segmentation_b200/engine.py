@@ -1,0 +1,171 @@
+"""Python handle on one native engine (one CUDA device): packed weights, workspaces, job state.
+
+Thin by design -- every method is one call through the C ABI declared in
+``include/exaspim_b200.h``; tensors cross the boundary as raw device pointers.
+"""
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _native
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream_ptr(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class Engine:
+    """Owns an ``exa_engine``; built from a ``state_dict`` with the reference's layout."""
+
+    def __init__(self, state_dict, device, precision="bf16"):
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError(
+                "exaspim_b200 runs on CUDA devices only (no CPU fallback); got device "
+                f"'{device}'"
+            )
+        self.device = torch.device("cuda", device.index if device.index is not None
+                                   else torch.cuda.current_device())
+        self.precision = precision
+        self._lib = _native.lib()
+        handle = ctypes.c_void_p()
+        code = self._lib.exa_create(
+            self.device.index,
+            _native.PRECISION_BF16 if precision == "bf16" else _native.PRECISION_FP32,
+            ctypes.byref(handle),
+        )
+        _native.check(code, None, "exa_create")
+        self._h = handle
+        self._load(state_dict)
+
+    # -- weights ---------------------------------------------------------------
+    def _load(self, state_dict):
+        for name, value in state_dict.items():
+            t = value.detach().to("cpu")
+            if t.dtype == torch.int64:
+                dtype, arr = _native.DTYPE_I64, t.numpy().astype(np.int64, copy=False)
+            else:
+                dtype, arr = _native.DTYPE_F32, t.to(torch.float32).numpy()
+            arr = np.ascontiguousarray(arr)
+            shape = (ctypes.c_int64 * max(arr.ndim, 1))(*arr.shape)
+            code = self._lib.exa_load_weight(
+                self._h, name.encode(), arr.ctypes.data_as(ctypes.c_void_p), shape, arr.ndim, dtype
+            )
+            _native.check(code, self._h, f"exa_load_weight({name})")
+        _native.check(self._lib.exa_finalize_weights(self._h), self._h, "exa_finalize_weights")
+        self.out_channels = self._lib.exa_out_channels(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.exa_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launch_count(self):
+        return int(self._lib.exa_launch_count(self._h))
+
+    # -- operator level ----------------------------------------------------------
+    def forward(self, x):
+        """float32 (B,1,Pz,Py,Px) cuda tensor -> float32 logits (B,C,Pz,Py,Px)."""
+        if x.device != self.device:
+            raise RuntimeError(f"input is on {x.device}, engine on {self.device}")
+        if x.dim() != 5 or x.shape[1] != 1:
+            raise ValueError("expected input of shape (B, 1, D, H, W)")
+        x = x.to(torch.float32).contiguous()
+        b, _, pz, py, px = x.shape
+        out = torch.empty((b, self.out_channels, pz, py, px), dtype=torch.float32,
+                          device=self.device)
+        patch = (ctypes.c_int32 * 3)(pz, py, px)
+        code = self._lib.exa_forward(self._h, _ptr(x), _ptr(out), b, patch,
+                                     _stream_ptr(self.device))
+        _native.check(code, self._h, "exa_forward")
+        return out
+
+    # -- whole path ---------------------------------------------------------------
+    def predict_host(self, vol_u16, params):
+        """numpy uint16 (D,H,W) -> numpy float32 (C,D,H,W), host buffers end to end."""
+        vol_u16 = np.ascontiguousarray(vol_u16, dtype=np.uint16)
+        d, h, w = vol_u16.shape
+        out = np.empty((self.out_channels, d, h, w), dtype=np.float32)
+        code = self._lib.exa_predict(
+            self._h, vol_u16.ctypes.data_as(ctypes.c_void_p), d, h, w, ctypes.byref(params),
+            out.ctypes.data_as(ctypes.c_void_p),
+        )
+        _native.check(code, self._h, "exa_predict")
+        return out
+
+    def predict_device(self, vol_dev, params, out=None):
+        """cuda uint16 (D,H,W) tensor -> cuda float32 (C,D,H,W) tensor (stream-ordered)."""
+        assert vol_dev.dtype == torch.uint16 and vol_dev.is_contiguous()
+        d, h, w = vol_dev.shape
+        if out is None:
+            out = torch.empty((self.out_channels, d, h, w), dtype=torch.float32,
+                              device=self.device)
+        code = self._lib.exa_predict_device(
+            self._h, _ptr(vol_dev), d, h, w, ctypes.byref(params), _ptr(out),
+            _stream_ptr(self.device),
+        )
+        _native.check(code, self._h, "exa_predict_device")
+        return out
+
+    # -- slab pieces (z-row sharding) -----------------------------------------------
+    def histogram(self, vol_dev, clip):
+        hist = torch.zeros(clip + 1, dtype=torch.int64, device=self.device)
+        code = self._lib.exa_histogram(self._h, _ptr(vol_dev), vol_dev.numel(), clip, _ptr(hist),
+                                       _stream_ptr(self.device))
+        _native.check(code, self._h, "exa_histogram")
+        return hist
+
+    def set_normalization(self, mn, mx, clip):
+        _native.check(self._lib.exa_set_normalization(self._h, float(mn), float(mx), int(clip)),
+                      self._h, "exa_set_normalization")
+
+    def slab_run(self, slab_dev, shape, params, row_begin, row_end):
+        d, h, w = shape
+        code = self._lib.exa_slab_run(self._h, _ptr(slab_dev), d, h, w, ctypes.byref(params),
+                                      row_begin, row_end, _stream_ptr(self.device))
+        _native.check(code, self._h, "exa_slab_run")
+
+    def slab_partial(self, halo_dev):
+        _native.check(self._lib.exa_slab_partial(self._h, _ptr(halo_dev),
+                                                 _stream_ptr(self.device)),
+                      self._h, "exa_slab_partial")
+
+    def slab_stitch(self, seed_dev, out_dev):
+        _native.check(self._lib.exa_slab_stitch(self._h, _ptr(seed_dev), _ptr(out_dev),
+                                                _stream_ptr(self.device)),
+                      self._h, "exa_slab_stitch")
+
+
+# -- host helpers that need no GPU --------------------------------------------------
+def plan_slab(shape, params, row_begin, row_end):
+    plan = _native.SlabPlan()
+    d, h, w = shape
+    code = _native.lib().exa_plan_slab(d, h, w, ctypes.byref(params), row_begin, row_end,
+                                       ctypes.byref(plan))
+    _native.check(code, None, "exa_plan_slab")
+    return plan.as_dict()
+
+
+def percentiles_from_hist(hist, q_lo, q_hi):
+    hist = np.ascontiguousarray(hist, dtype=np.uint64)
+    mn, mx = ctypes.c_double(), ctypes.c_double()
+    code = _native.lib().exa_percentiles_from_hist(
+        hist.ctypes.data_as(ctypes.c_void_p), hist.size, q_lo, q_hi, ctypes.byref(mn),
+        ctypes.byref(mx))
+    _native.check(code, None, "exa_percentiles_from_hist")
+    return mn.value, mx.value

@@ -1,0 +1,121 @@
+"""3D U-Net whose forward pass runs in the native sm_100a engine.
+
+Drop-in for reference machine_learning/unet3d.py:16-336 on the configuration
+``inference.load_model`` builds (``trilinear=True, width_multiplier=1``): the
+module tree exists to hold parameters under exactly the reference's
+``state_dict`` names (128 entries), so checkpoints written by
+the reference's Trainer load with ``strict=True`` and vice versa.  The
+arithmetic is not done by these torch modules -- ``forward`` hands the input to
+``Engine.forward`` (C ABI ``exa_forward``), which folds the eval-mode BatchNorm
+into the convolutions and runs the CUDA kernels.  On a CPU tensor ``forward``
+raises: there is no fallback path.
+"""
+
+import torch
+import torch.nn as nn
+
+from ..engine import Engine
+
+_WIDTHS = (32, 64, 128, 256, 512)
+
+
+def _conv_bn_act(cin, cout):
+    return [nn.Conv3d(cin, cout, kernel_size=3, padding=1), nn.BatchNorm3d(cout),
+            nn.LeakyReLU(0.01, inplace=True)]
+
+
+class DoubleConv(nn.Module):
+    """Parameter holder for (Conv3d 3^3 -> BatchNorm3d -> LeakyReLU) x 2, unet3d.py:108-165."""
+
+    def __init__(self, in_channels, out_channels, mid_channels=None):
+        super().__init__()
+        mid = mid_channels or out_channels
+        self.double_conv = nn.Sequential(*_conv_bn_act(in_channels, mid),
+                                         *_conv_bn_act(mid, out_channels))
+
+
+class Down(nn.Module):
+    """MaxPool3d(2) then DoubleConv, unet3d.py:168-212."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.maxpool_conv = nn.Sequential(nn.MaxPool3d(2), DoubleConv(in_channels, out_channels))
+
+
+class Up(nn.Module):
+    """Trilinear x2 upsample, concat [skip, upsampled], DoubleConv, unet3d.py:215-289."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.up = nn.Upsample(scale_factor=2, mode="trilinear", align_corners=True)
+        self.conv = DoubleConv(in_channels, out_channels, mid_channels=in_channels // 2)
+
+
+class OutConv(nn.Module):
+    """1x1x1 head, unet3d.py:292-336."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.conv = nn.Conv3d(in_channels, out_channels, kernel_size=1)
+
+
+class UNet3D(nn.Module):
+    """Same constructor and state_dict as the reference ``UNet3D`` (unet3d.py:16-105).
+
+    Only ``trilinear=True, width_multiplier=1`` is implemented natively (that is what
+    ``load_model`` constructs, inference.py:419-420); other values raise.
+    ``precision`` selects the engine arithmetic: ``"bf16"`` (tcgen05 tensor cores, fp32
+    accumulation) or ``"fp32"`` (validation mode).
+    """
+
+    def __init__(self, output_channels=1, trilinear=True, width_multiplier=1, precision="bf16"):
+        super().__init__()
+        if not trilinear or width_multiplier != 1:
+            raise NotImplementedError(
+                "the B200 engine implements the load_model configuration only "
+                "(trilinear=True, width_multiplier=1)"
+            )
+        c = list(_WIDTHS)
+        self.channels = c
+        self.trilinear = trilinear
+        self.precision = precision
+        self.inc = DoubleConv(1, c[0])
+        self.down1 = Down(c[0], c[1])
+        self.down2 = Down(c[1], c[2])
+        self.down3 = Down(c[2], c[3])
+        self.down4 = Down(c[3], c[4] // 2)
+        self.up1 = Up(c[4], c[3] // 2)
+        self.up2 = Up(c[3], c[2] // 2)
+        self.up3 = Up(c[2], c[1] // 2)
+        self.up4 = Up(c[1], c[0])
+        self.outc = OutConv(c[0], output_channels)
+        self._engines = {}
+
+    # -- engine cache -----------------------------------------------------------------
+    def _fingerprint(self):
+        return tuple((k, v.data_ptr(), v._version) for k, v in self.state_dict().items())
+
+    def engine(self, precision=None):
+        """Native engine holding this module's current weights (rebuilt when they change)."""
+        precision = precision or self.precision
+        device = next(self.parameters()).device
+        key = (precision, str(device))
+        fp = self._fingerprint()
+        cached = self._engines.get(key)
+        if cached is None or cached[0] != fp:
+            if self.training:
+                raise RuntimeError("the native engine implements eval-mode BatchNorm only; "
+                                   "call model.eval() first (inference.py:423)")
+            if cached is not None:
+                cached[1].close()
+            self._engines[key] = (fp, Engine(self.state_dict(), device, precision))
+        return self._engines[key][1]
+
+    def forward(self, x):
+        """(B,1,D,H,W) float32 -> logits (B,C,D,H,W) float32, unet3d.py:77-105."""
+        if not x.is_cuda:
+            raise RuntimeError("UNet3D (B200 engine) needs CUDA tensors; there is no CPU fallback")
+        if self.training:
+            raise RuntimeError("training-mode forward is outside this engine's scope")
+        with torch.no_grad():
+            return self.engine().forward(x)

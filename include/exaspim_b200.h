@@ -1,0 +1,136 @@
+/*
+ * exaspim_b200 -- C ABI of the B200-native affinity-prediction hot path.
+ *
+ * This is the drop-in boundary for ONE path of
+ * AllenNeuralDynamics/aind-exaspim-neuron-segmentation:
+ *     inference.predict(img, model, affinity_mode=True, patch_shape=(96,96,96))
+ * (reference src/aind_exaspim_neuron_segmentation/inference.py:29-126) and the model it
+ * drives (machine_learning/unet3d.py:16-336, loaded by inference.py:400-424).
+ *
+ * The reference is pure Python and has no FFI of its own; its boundary for this path is
+ * two Python functions plus the nn.Module call convention.  The
+ * entry points below are what a ctypes binding of those functions needs -- see
+ * INTEGRATION.md for the reference-side stub.  Each one cites the reference interface it
+ * replaces.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success and a
+ * negative code on failure and never throws; exa_last_error() returns a message for the
+ * last failure on that engine.  An engine is bound to one CUDA device, owns its packed
+ * weights / workspaces, and is not thread-safe.  There is NO CPU fallback: without a CUDA
+ * device exa_create fails.
+ */
+#ifndef EXASPIM_B200_H_
+#define EXASPIM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct exa_engine exa_engine;
+
+enum { EXA_PRECISION_BF16 = 0, EXA_PRECISION_FP32 = 1 };
+enum { EXA_DTYPE_F32 = 0, EXA_DTYPE_I64 = 1 };
+
+enum {
+  EXA_OK = 0,
+  EXA_ERR_INVALID = -1, /* bad argument / unsupported configuration */
+  EXA_ERR_CUDA = -2,    /* CUDA runtime or driver failure           */
+  EXA_ERR_STATE = -3    /* call sequence error (e.g. weights not finalised) */
+};
+
+/* Keyword arguments of reference predict(), inference.py:29-40.  batch is the number of
+ * patches the engine runs per wave (numerically irrelevant, SURVEY.md 8a invariants);
+ * 0 selects a default. */
+typedef struct {
+  int32_t patch[3];    /* patch_shape (z, y, x); multiples of 16 */
+  int32_t overlap[3];  /* overlap (z, y, x)                      */
+  int32_t trim;        /* trim                                   */
+  int32_t brightness_clip;
+  double pct_lo, pct_hi; /* normalization_percentiles            */
+  int32_t batch;
+  int32_t reserved;
+} exa_predict_params;
+
+/* ---- engine lifetime ------------------------------------------------------------ */
+int exa_create(int device, int precision, exa_engine** out);
+int exa_destroy(exa_engine* e);
+const char* exa_last_error(const exa_engine* e); /* e may be NULL: last create error */
+const char* exa_version(void);
+
+/* ---- weights: replaces UNet3D.load_state_dict, inference.py:420-421 --------------
+ * One call per state_dict entry (128 entries for the reference architecture, names and
+ * shapes as in unet3d.py:64-75,142-149,318).  Data is copied from host memory.
+ * exa_finalize_weights checks the key set strictly, folds eval-mode BatchNorm
+ * (unet3d.py:144,147) into the conv weights in fp32 and packs them for the kernels. */
+int exa_load_weight(exa_engine* e, const char* name, const void* data, const int64_t* shape,
+                    int ndim, int dtype);
+int exa_finalize_weights(exa_engine* e);
+int exa_out_channels(const exa_engine* e); /* 3 (affinity_mode) or 1 */
+
+/* ---- operator level: replaces UNet3D.forward, unet3d.py:77-105 --------------------
+ * x: device float32 (B,1,Pz,Py,Px); logits: device float32 (B,C,Pz,Py,Px).
+ * stream: cudaStream_t (may be NULL).  Asynchronous. */
+int exa_forward(exa_engine* e, const float* x, float* logits, int batch, const int32_t patch[3],
+                void* stream);
+
+/* ---- whole path, host buffers: replaces predict(), inference.py:29-126 -------------
+ * vol: host uint16 (D,H,W), not modified.  out: host float32 (C,D,H,W), fully written
+ * (uncovered border voxels are 0.0 exactly as in the reference).  Synchronous. */
+int exa_predict(exa_engine* e, const uint16_t* vol, int D, int H, int W,
+                const exa_predict_params* p, float* out);
+
+/* Same with device-resident buffers (the bench's device-timed region). Asynchronous on
+ * `stream` except for one small D2H of the 1001-bin histogram. */
+int exa_predict_device(exa_engine* e, const uint16_t* vol_dev, int D, int H, int W,
+                       const exa_predict_params* p, float* out_dev, void* stream);
+
+/* ---- slab pieces for z-row sharding across GPUs --------------------
+ * A volume's patch grid has nz rows of patches along z.  A rank owns rows
+ * [row_begin,row_end); it needs input planes [exa_slab_in_z0, exa_slab_in_z1) resident and
+ * produces output planes [exa_slab_out_z0, exa_slab_out_z1).  The planes
+ * [halo_z0, halo_z1) at its upper end are also covered by the next rank's first row: the
+ * rank sends raw partial sums for them (exa_slab_partial) and the next rank seeds its
+ * stitch with them so that the summation order matches inference.py:99-116 bit for bit. */
+typedef struct {
+  int32_t nz, ny, nx;              /* patch grid                               */
+  int32_t n_patches;               /* nz*ny*nx  (count_patches, inference.py:340-365) */
+  int32_t in_z0, in_z1;            /* input planes needed                      */
+  int32_t out_z0, out_z1;          /* output planes owned                      */
+  int32_t halo_z0, halo_z1;        /* planes to hand to the next rank (empty if last) */
+  int32_t seed_z0, seed_z1;        /* planes to receive from the previous rank */
+} exa_slab_plan;
+
+int exa_plan_slab(int D, int H, int W, const exa_predict_params* p, int row_begin, int row_end,
+                  exa_slab_plan* plan);
+/* histogram of min(v, clip) over n uint16 values on the device -> hist_dev[clip+1] (uint64) */
+int exa_histogram(exa_engine* e, const uint16_t* vol_dev, int64_t n, int clip,
+                  uint64_t* hist_dev, void* stream);
+/* exact np.percentile(method="linear") from a histogram (host, no GPU needed):
+ * inference.py:80 -> img_util.py:526 */
+int exa_percentiles_from_hist(const uint64_t* hist, int nbins, double q_lo, double q_hi,
+                              double* mn, double* mx);
+/* normalisation scalars (img_util.py:526-531) for the following slab calls */
+int exa_set_normalization(exa_engine* e, double mn, double mx, int clip);
+/* run all patches of rows [row_begin,row_end); slab_dev holds planes [in_z0,in_z1) */
+int exa_slab_run(exa_engine* e, const uint16_t* slab_dev, int D, int H, int W,
+                 const exa_predict_params* p, int row_begin, int row_end, void* stream);
+/* raw partial sums of the halo planes -> halo_dev (C, halo_z1-halo_z0, H, W) */
+int exa_slab_partial(exa_engine* e, float* halo_dev, void* stream);
+/* finished planes [out_z0,out_z1) -> out_dev (C, out_z1-out_z0, H, W); seed_dev may be NULL */
+int exa_slab_stitch(exa_engine* e, const float* seed_dev, float* out_dev, void* stream);
+
+/* host helpers mirroring count_patches / generate_patch_starts (inference.py:340-397);
+ * starts receives n_patches*3 int32 (z,y,x) in the reference's order */
+int exa_count_patches(int D, int H, int W, const int32_t patch[3], const int32_t overlap[3]);
+int exa_patch_starts(int D, int H, int W, const int32_t patch[3], const int32_t overlap[3],
+                     int32_t* starts, int capacity);
+
+/* number of kernel launches issued by this engine since creation (bench bookkeeping) */
+int64_t exa_launch_count(const exa_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EXASPIM_B200_H_ */

@@ -1,0 +1,131 @@
+"""CPU restatement of the reference 3D U-Net forward -- TEST INFRASTRUCTURE ONLY.
+
+Functional torch (fp32, CPU) driven directly by a ``state_dict`` with the
+reference's key layout, so it shares no code with either the reference's
+``nn.Module`` tree or the product's.  ``REF`` = src/aind_exaspim_neuron_segmentation.
+
+``emulate_bf16=True`` reproduces the *numerics contract* of the CUDA bf16 path
+(DESIGN.md): BatchNorm folded into the conv in fp32, folded weights rounded to
+bf16 once, every layer output rounded to bf16 once, fp32 accumulation, fp32
+stem input, fp32 1x1x1 head.  It is used to separate "rounding noise" from
+"bug" when the GPU result is compared with the fp32 oracle.
+"""
+
+import torch
+import torch.nn.functional as F
+
+BLOCKS = [
+    # (state_dict prefix, kind)
+    ("inc.double_conv", "plain"),
+    ("down1.maxpool_conv.1.double_conv", "down"),
+    ("down2.maxpool_conv.1.double_conv", "down"),
+    ("down3.maxpool_conv.1.double_conv", "down"),
+    ("down4.maxpool_conv.1.double_conv", "down"),
+    ("up1.conv.double_conv", "up"),
+    ("up2.conv.double_conv", "up"),
+    ("up3.conv.double_conv", "up"),
+    ("up4.conv.double_conv", "up"),
+]
+
+
+def _bf16(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def _conv_bn_act(x, sd, prefix, conv_idx, bn_idx, emulate_bf16, round_input=True):
+    """Conv3d(k=3,p=1) -> BatchNorm3d(eval) -> LeakyReLU(0.01): REF/machine_learning/unet3d.py:143-148."""
+    w = sd[f"{prefix}.{conv_idx}.weight"].float()
+    b = sd[f"{prefix}.{conv_idx}.bias"].float()
+    g = sd[f"{prefix}.{bn_idx}.weight"].float()
+    beta = sd[f"{prefix}.{bn_idx}.bias"].float()
+    mu = sd[f"{prefix}.{bn_idx}.running_mean"].float()
+    var = sd[f"{prefix}.{bn_idx}.running_var"].float()
+    if not emulate_bf16:
+        y = F.conv3d(x, w, b, padding=1)
+        y = F.batch_norm(y, mu, var, g, beta, training=False, eps=1e-5)
+        return F.leaky_relu(y, 0.01)
+    scale = (g.double() / torch.sqrt(var.double() + 1e-5))
+    wf = (w.double() * scale.view(-1, 1, 1, 1, 1)).float()
+    bf = ((b.double() - mu.double()) * scale + beta.double()).float()
+    if w.shape[1] > 1:  # the Cin=1 stem runs in fp32 on the fp32 normalised input
+        wf = _bf16(wf)
+    y = F.leaky_relu(F.conv3d(x, wf, None, padding=1) + bf.view(1, -1, 1, 1, 1), 0.01)
+    return y
+
+
+def _double_conv(x, sd, prefix, emulate_bf16, last=False):
+    y = _conv_bn_act(x, sd, prefix, 0, 1, emulate_bf16)
+    if emulate_bf16:
+        y = _bf16(y)
+    y = _conv_bn_act(y, sd, prefix, 3, 4, emulate_bf16)
+    if emulate_bf16 and not last:
+        y = _bf16(y)
+    return y
+
+
+def unet_forward(x, sd, emulate_bf16=False):
+    """REF/machine_learning/unet3d.py:77-105.  x: float32 (B,1,D,H,W) -> logits (B,C,D,H,W)."""
+    x = torch.as_tensor(x, dtype=torch.float32)
+    with torch.no_grad():
+        skips = []
+        h = _double_conv(x, sd, BLOCKS[0][0], emulate_bf16)
+        skips.append(h)
+        for prefix, _ in BLOCKS[1:5]:
+            h = F.max_pool3d(h, 2)  # unet3d.py:195
+            h = _double_conv(h, sd, prefix, emulate_bf16)
+            skips.append(h)
+        skips.pop()  # x5 is not a skip
+        for i, (prefix, _) in enumerate(BLOCKS[5:]):
+            # unet3d.py:248-250 (trilinear, align_corners=True) and :288 (cat [skip, upsampled])
+            up = F.interpolate(h, scale_factor=2, mode="trilinear", align_corners=True)
+            if emulate_bf16:
+                up = _bf16(up)
+            h = torch.cat([skips.pop(), up], dim=1)
+            h = _double_conv(h, sd, prefix, emulate_bf16, last=(i == 3))
+        # unet3d.py:318 -- the head stays fp32 in both modes
+        logits = F.conv3d(h, sd["outc.conv.weight"].float(), sd["outc.conv.bias"].float())
+    return logits
+
+
+def make_forward_fn(sd, emulate_bf16=False):
+    """numpy (B,1,P,P,P) -> numpy logits, for oracle.predict_ref.predict_ref."""
+    def fn(x):
+        return unet_forward(torch.from_numpy(x), sd, emulate_bf16).numpy()
+    return fn
+
+
+def rescaled_state_dict(seed, out_channels=3):
+    """'Well-scaled' random-init weights of the reference architecture (SURVEY.md 8c caveat).
+
+    PyTorch's default init collapses activations (logits std ~0.13) and leaves BatchNorm an
+    identity, which hides deep-layer and BN-folding bugs.  This builds a state_dict with the
+    reference's exact key/shape layout but He-normal conv weights, randomised BN statistics
+    and a head scaled so that sigmoid spans roughly (0.02, 0.98).
+    """
+    gen = torch.Generator().manual_seed(seed)
+    sd = {}
+    chans = {
+        "inc.double_conv": (1, 32, 32),
+        "down1.maxpool_conv.1.double_conv": (32, 64, 64),
+        "down2.maxpool_conv.1.double_conv": (64, 128, 128),
+        "down3.maxpool_conv.1.double_conv": (128, 256, 256),
+        "down4.maxpool_conv.1.double_conv": (256, 256, 256),
+        "up1.conv.double_conv": (512, 256, 128),
+        "up2.conv.double_conv": (256, 128, 64),
+        "up3.conv.double_conv": (128, 64, 32),
+        "up4.conv.double_conv": (64, 32, 32),
+    }
+    for prefix, (cin, mid, cout) in chans.items():
+        for conv_idx, bn_idx, ci, co in ((0, 1, cin, mid), (3, 4, mid, cout)):
+            fan_in = ci * 27
+            std = (2.0 / (1 + 0.01 ** 2)) ** 0.5 / fan_in ** 0.5
+            sd[f"{prefix}.{conv_idx}.weight"] = torch.randn((co, ci, 3, 3, 3), generator=gen) * std
+            sd[f"{prefix}.{conv_idx}.bias"] = torch.randn((co,), generator=gen) * 0.1
+            sd[f"{prefix}.{bn_idx}.weight"] = torch.rand((co,), generator=gen) + 0.5
+            sd[f"{prefix}.{bn_idx}.bias"] = torch.randn((co,), generator=gen) * 0.1
+            sd[f"{prefix}.{bn_idx}.running_mean"] = torch.randn((co,), generator=gen) * 0.1
+            sd[f"{prefix}.{bn_idx}.running_var"] = torch.rand((co,), generator=gen) * 1.5 + 0.5
+            sd[f"{prefix}.{bn_idx}.num_batches_tracked"] = torch.tensor(0, dtype=torch.int64)
+    sd["outc.conv.weight"] = torch.randn((out_channels, 32, 1, 1, 1), generator=gen) * (1.0 / 32 ** 0.5)
+    sd["outc.conv.bias"] = torch.randn((out_channels,), generator=gen) * 0.1
+    return sd

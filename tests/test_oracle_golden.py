@@ -1,0 +1,60 @@
+"""Pin the CPU oracle against outputs of the unmodified reference (tests/golden/*.npz)."""
+
+import numpy as np
+import pytest
+
+from oracle import predict_ref as pr
+from oracle.unet_ref import make_forward_fn
+
+from helpers import compare_with_golden, load_golden, make_volume, state_dict_for
+
+
+def _run_oracle(meta):
+    vol = make_volume(meta["shape"], meta["vol_seed"])
+    sd = state_dict_for(*meta["weights"])
+    kw = dict(meta["kwargs"])
+    for key in ("patch_shape", "overlap", "normalization_percentiles"):
+        if key in kw:
+            kw[key] = tuple(kw[key])
+    return pr.predict_ref(vol, make_forward_fn(sd), **kw)
+
+
+@pytest.mark.parametrize("name", ["small_p32", "small_p48_trim0ish", "c1_rescaled_96"])
+def test_oracle_matches_reference_golden(golden_meta, name):
+    out = _run_oracle(golden_meta["cases"][name])
+    # same fp32 arithmetic (torch CPU conv) -> only thread-count dependent reduction order differs
+    worst = compare_with_golden(out, load_golden(name), atol=2e-6)
+    assert worst <= 2e-6
+
+
+def test_oracle_default_init_case(golden_meta):
+    out = _run_oracle(golden_meta["cases"]["c1_default_96"])
+    compare_with_golden(out, load_golden("c1_default_96"), atol=2e-6)
+    assert out[:, :8].max() == 0.0 and out[:, 88:].max() == 0.0
+
+
+def test_tiling_matches_reference(golden_meta):
+    for t in golden_meta["tiling"]:
+        starts = pr.patch_starts(t["dims"], t["patch"], t["overlap"])
+        assert len(starts) == t["n"] == pr.n_patches(t["dims"], t["patch"], t["overlap"])
+        assert [list(s) for s in starts[:3]] == t["first"]
+        assert [list(s) for s in starts[-3:]] == t["last"]
+        checksum = sum((i + 1) * (z * 1000003 + y * 1009 + x) for i, (z, y, x) in enumerate(starts))
+        assert checksum == t["checksum"]
+
+
+def test_normalisation_matches_reference(golden_meta):
+    for n in golden_meta["norms"]:
+        vol = make_volume(n["shape"], n["seed"])
+        normed, mn, mx = pr.clip_and_normalize(vol, n["clip"], tuple(n["pct"]))
+        assert mn == n["mn"] and mx == n["mx"]
+        assert float(normed.mean()) == pytest.approx(n["mean"], rel=0, abs=1e-15)
+        sample = normed.ravel()[::max(1, normed.size // 16)][:16]
+        assert [float(v) for v in sample] == n["sample"]
+
+
+def test_reflect_padding_excludes_edge():
+    vol = np.arange(64, dtype=np.float64).reshape(1, 1, 64) * np.ones((2, 2, 1))
+    patch = pr.extract_patch(vol, (0, 0, 0), (2, 2, 96))
+    assert patch.shape == (2, 2, 96)
+    assert patch[0, 0, 64:].tolist() == [float(v) for v in range(62, 30, -1)]
