@@ -86,22 +86,20 @@ Status plan_slab(const Plan& plan, int row_begin, int row_end, exa_slab_plan* ou
 }
 
 // np.percentile(a, q) with the default method="linear" on the sorted multiset described by
-// `hist` (img_util.py:526).  Mirrors numpy's arithmetic step by step so that the float64
-// results are bit-identical: virtual index n*q + (alpha + q*(1-alpha-beta)) - 1 with
-// alpha = beta = 1, gamma = index - floor(index), and numpy's two-sided lerp.
+// `hist` (img_util.py:526).  Mirrors numpy (>= 1.22, checked against 2.3) step by step so
+// that the float64 results are bit-identical: q = pct/100, virtual index (n-1)*q,
+// gamma = index - floor(index), neighbours clamped as in numpy's _get_indexes, and numpy's
+// two-sided _lerp.
 static double percentile_linear(const uint64_t* hist, int nbins, uint64_t n, double pct) {
   const double q = pct / 100.0;
-  const double alpha = 1.0, beta = 1.0;
-  double vidx = (double)n * q + (alpha + q * (1.0 - alpha - beta)) - 1.0;
-  double prev = floor(vidx);
-  double gamma = vidx - prev;
+  const double vidx = (double)(n - 1) * q;
+  const double prev = floor(vidx);
+  const double gamma = vidx - prev;
+  const int64_t last = (int64_t)n - 1;
   int64_t i0 = (int64_t)prev;
   int64_t i1 = i0 + 1;
-  const int64_t last = (int64_t)n - 1;
-  if (i0 < 0) i0 = 0;  // numpy clips / wraps indexes that fall outside [0, n-1]
-  if (i0 > last) i0 = last;
-  if (i1 < 0) i1 = 0;
-  if (i1 > last) i1 = last;
+  if (vidx >= (double)last) i0 = i1 = last;
+  if (vidx < 0) i0 = i1 = 0;
   // order statistics i0, i1 from the histogram
   double a = 0, b = 0;
   uint64_t cum = 0;

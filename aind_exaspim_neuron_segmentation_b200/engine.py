@@ -54,10 +54,11 @@ class Engine:
                 dtype, arr = _native.DTYPE_I64, t.numpy().astype(np.int64, copy=False)
             else:
                 dtype, arr = _native.DTYPE_F32, t.to(torch.float32).numpy()
+            dims = tuple(arr.shape)  # ascontiguousarray would promote 0-d to 1-d
             arr = np.ascontiguousarray(arr)
-            shape = (ctypes.c_int64 * max(arr.ndim, 1))(*arr.shape)
+            shape = (ctypes.c_int64 * max(len(dims), 1))(*dims)
             code = self._lib.exa_load_weight(
-                self._h, name.encode(), arr.ctypes.data_as(ctypes.c_void_p), shape, arr.ndim, dtype
+                self._h, name.encode(), arr.ctypes.data_as(ctypes.c_void_p), shape, len(dims), dtype
             )
             _native.check(code, self._h, f"exa_load_weight({name})")
         _native.check(self._lib.exa_finalize_weights(self._h), self._h, "exa_finalize_weights")

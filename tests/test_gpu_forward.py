@@ -1,0 +1,94 @@
+"""GPU parity: the native U-Net forward (C ABI exa_forward) vs the CPU oracle."""
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import state_dict_for
+
+pytestmark = pytest.mark.gpu
+
+BF16_LOGIT_TOL = 6e-2   # bf16 operands, fp32 accumulation, 18 layers (sigmoid tolerance is 1e-2)
+FP32_LOGIT_TOL = 2e-4
+
+
+def _oracle(x, sd, emulate=False):
+    from oracle.unet_ref import unet_forward
+
+    return unet_forward(x.cpu(), sd, emulate_bf16=emulate)
+
+
+def _engine(sd, precision):
+    from aind_exaspim_neuron_segmentation_b200.engine import Engine
+
+    return Engine(sd, "cuda:0", precision)
+
+
+@pytest.mark.parametrize("shape", [(1, 16, 16, 16), (3, 32, 32, 32), (2, 48, 32, 16), (1, 64, 64, 64)])
+def test_forward_fp32_mode_matches_oracle(shape):
+    sd = state_dict_for("rescaled", 5)
+    eng = _engine(sd, "fp32")
+    torch.manual_seed(1)
+    x = torch.rand((shape[0], 1) + shape[1:])
+    y = eng.forward(x.cuda()).cpu()
+    ref = _oracle(x, sd)
+    assert y.shape == ref.shape and y.dtype == torch.float32
+    err = (y - ref).abs().max().item()
+    assert err <= FP32_LOGIT_TOL, err
+    assert (torch.sigmoid(y) - torch.sigmoid(ref)).abs().max().item() <= 1e-4
+
+
+@pytest.mark.parametrize("shape", [(1, 16, 16, 16), (3, 32, 32, 32), (2, 48, 32, 16), (5, 16, 32, 48),
+                                   (1, 96, 96, 96)])
+def test_forward_bf16_mode_matches_oracle(shape):
+    sd = state_dict_for("rescaled", 6)
+    eng = _engine(sd, "bf16")
+    torch.manual_seed(2)
+    x = torch.rand((shape[0], 1) + shape[1:])
+    y = eng.forward(x.cuda()).cpu()
+    ref = _oracle(x, sd)
+    emu = _oracle(x, sd, emulate=True)
+    # against the bf16-emulating oracle only accumulation order / rounding ties differ
+    err_emu = (y - emu).abs().max().item()
+    err_ref = (torch.sigmoid(y) - torch.sigmoid(ref)).abs().max().item()
+    assert err_ref <= 1e-2, (err_ref, err_emu)          # north_star tolerance (BF16)
+    assert (y - ref).abs().max().item() <= BF16_LOGIT_TOL
+    assert err_emu <= 3e-2, err_emu
+
+
+def test_forward_default_init_and_single_channel():
+    sd = state_dict_for("default", 0, out_channels=1)
+    eng = _engine(sd, "bf16")
+    assert eng.out_channels == 1
+    x = torch.rand(2, 1, 32, 32, 32)
+    y = eng.forward(x.cuda()).cpu()
+    ref = _oracle(x, sd)
+    assert y.shape == (2, 1, 32, 32, 32)
+    assert (y - ref).abs().max().item() <= 5e-3
+
+
+def test_batch_is_numerically_irrelevant():
+    sd = state_dict_for("rescaled", 7)
+    eng = _engine(sd, "bf16")
+    x = torch.rand(4, 1, 32, 32, 32).cuda()
+    whole = eng.forward(x)
+    parts = torch.cat([eng.forward(x[i:i + 1]) for i in range(4)])
+    assert torch.equal(whole, parts)
+
+
+def test_module_forward_and_error_paths():
+    from aind_exaspim_neuron_segmentation_b200 import UNet3D
+
+    torch.manual_seed(0)
+    model = UNet3D(output_channels=3).cuda().eval()
+    x = torch.rand(1, 1, 32, 32, 32)
+    y = model(x.cuda())
+    ref = _oracle(x, {k: v.cpu() for k, v in model.state_dict().items()})
+    assert (y.cpu() - ref).abs().max().item() <= 5e-3
+    with pytest.raises(RuntimeError):
+        model(x)                      # CPU tensor: no fallback
+    with pytest.raises(RuntimeError):
+        model.engine().forward(torch.rand(1, 1, 20, 32, 32).cuda())   # not a multiple of 16
+    n0 = model.engine().launch_count
+    model(x.cuda())
+    assert model.engine().launch_count > n0

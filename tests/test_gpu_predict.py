@@ -1,0 +1,152 @@
+"""GPU parity of the whole path (C ABI exa_predict, host buffers) vs the oracle / goldens."""
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import (compare_with_golden, lightsheet_volume, load_golden, make_volume,
+                     state_dict_for)
+
+pytestmark = pytest.mark.gpu
+
+BF16_TOL = 1e-2   # north_star: max-abs affinity error in BF16
+FP32_TOL = 1e-4   # north_star: FP32 validation mode
+
+
+def _model(kind, seed, precision="bf16", out_channels=3):
+    from aind_exaspim_neuron_segmentation_b200 import UNet3D
+
+    m = UNet3D(output_channels=out_channels, precision=precision)
+    m.load_state_dict(state_dict_for(kind, seed, out_channels), strict=True)
+    return m.cuda().eval()
+
+
+def _kwargs(meta):
+    kw = dict(meta["kwargs"])
+    for key in ("patch_shape", "overlap", "normalization_percentiles"):
+        if key in kw:
+            kw[key] = tuple(kw[key])
+    return kw
+
+
+@pytest.mark.parametrize("name", ["c1_default_96", "c1_rescaled_96", "mixed_160x160x100", "small_p32",
+                                  "small_p48_trim0ish"])
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_predict_matches_reference_golden(golden_meta, name, precision):
+    from aind_exaspim_neuron_segmentation_b200 import predict
+
+    meta = golden_meta["cases"][name]
+    if precision == "fp32" and name == "mixed_160x160x100":
+        pytest.skip("fp32 validation mode is the slow SIMT path; covered by the other cases")
+    vol = make_volume(meta["shape"], meta["vol_seed"])
+    model = _model(*meta["weights"], precision=precision)
+    before = vol.copy()
+    out = predict(vol, model, verbose=False, **_kwargs(meta))
+    assert out.dtype == np.float32 and out.shape == (3,) + tuple(meta["shape"])
+    assert out.flags["C_CONTIGUOUS"] and np.array_equal(vol, before)
+    worst = compare_with_golden(out, load_golden(name), BF16_TOL if precision == "bf16" else FP32_TOL)
+    print(name, precision, "max abs err vs reference golden:", worst)
+
+
+def test_predict_full_volume_vs_oracle_fp32():
+    """Whole-array comparison (not only the golden sub-sample) on a ragged small case."""
+    from aind_exaspim_neuron_segmentation_b200 import predict
+    from oracle.predict_ref import predict_ref
+    from oracle.unet_ref import make_forward_fn
+
+    sd = state_dict_for("rescaled", 11)
+    vol = lightsheet_volume((70, 45, 83), 12)
+    kw = dict(patch_shape=(32, 32, 48), overlap=(8, 16, 16), trim=4)
+    ref = predict_ref(vol, make_forward_fn(sd), **kw)
+    for precision, tol in (("fp32", FP32_TOL), ("bf16", BF16_TOL)):
+        out = predict(vol, _model("rescaled", 11, precision), verbose=False, **kw)
+        err = np.abs(out - ref).max()
+        assert err <= tol, (precision, err)
+        assert np.array_equal(out == 0, ref == 0)   # uncovered shell is exactly zero
+
+
+def test_foreground_mode_and_reference_module_interop():
+    from aind_exaspim_neuron_segmentation_b200 import predict
+    from oracle.predict_ref import predict_ref
+    from oracle.unet_ref import make_forward_fn
+
+    sd = state_dict_for("rescaled", 13, out_channels=1)
+    vol = make_volume((40, 40, 40), 14)
+    kw = dict(patch_shape=(32, 32, 32), overlap=(16, 16, 16), trim=4)
+    out = predict(vol, _model("rescaled", 13, "bf16", 1), affinity_mode=False, verbose=False, **kw)
+    ref = predict_ref(vol, make_forward_fn(sd), n_channels=1, **kw)[0]
+    assert out.shape == (40, 40, 40)
+    assert np.abs(out - ref).max() <= BF16_TOL
+    with pytest.raises(ValueError):
+        predict(vol, _model("rescaled", 13, "bf16", 1), affinity_mode=True, verbose=False, **kw)
+
+
+def test_load_model_round_trip(tmp_path):
+    from aind_exaspim_neuron_segmentation_b200 import load_model, predict
+
+    sd = state_dict_for("rescaled", 15)
+    path = tmp_path / "UNet3d-test.pth"
+    torch.save(sd, path)
+    model = load_model(str(path), affinity_mode=True, device="cuda")
+    assert not model.training and next(model.parameters()).is_cuda
+    vol = make_volume((32, 32, 32), 16)
+    out = predict(vol, model, verbose=False, patch_shape=(32, 32, 32), overlap=(8, 8, 8), trim=4)
+    assert out.shape == (3, 32, 32, 32) and out[:, 4:28, 4:28, 4:28].min() > 0
+    assert out[:, :4].max() == 0 and out[:, 28:].max() == 0
+
+
+def test_device_path_equals_host_path_and_slabs_equal_single():
+    """exa_predict_device == exa_predict; z-row slabs with partial-sum hand-over == single slab."""
+    from aind_exaspim_neuron_segmentation_b200 import _native
+    from aind_exaspim_neuron_segmentation_b200.engine import percentiles_from_hist, plan_slab
+
+    model = _model("rescaled", 17)
+    eng = model.engine()
+    shape = (150, 40, 56)
+    vol = lightsheet_volume(shape, 18)
+    params = _native.make_params((32, 32, 32), (8, 8, 8), 4, 1000, (1, 99.9), batch=7)
+    host = eng.predict_host(vol, params)
+    vdev = torch.from_numpy(vol).cuda()
+    dev = eng.predict_device(vdev, params).cpu().numpy()
+    assert np.array_equal(host, dev)
+
+    hist = eng.histogram(vdev, 1000).cpu().numpy()
+    assert np.array_equal(hist, np.bincount(np.minimum(vol, 1000).ravel(), minlength=1001))
+    mn, mx = percentiles_from_hist(hist, 1, 99.9)
+    nz = plan_slab(shape, params, 0, 0)["nz"]
+    for cuts in ([0, 2, nz], [0, 1, 3, nz], [0, nz]):
+        out = np.zeros_like(host)
+        seed = None
+        for r0, r1 in zip(cuts, cuts[1:]):
+            pl = plan_slab(shape, params, r0, r1)
+            slab = vdev[pl["in_z0"]:pl["in_z1"]].contiguous()
+            eng.set_normalization(mn, mx, 1000)
+            eng.slab_run(slab, shape, params, r0, r1)
+            own = torch.empty((3, pl["out_z1"] - pl["out_z0"], shape[1], shape[2]), device="cuda")
+            eng.slab_stitch(seed, own)
+            out[:, pl["out_z0"]:pl["out_z1"]] = own.cpu().numpy()
+            nh = pl["halo_z1"] - pl["halo_z0"]
+            if nh > 0:
+                seed = torch.empty((3, nh, shape[1], shape[2]), device="cuda")
+                eng.slab_partial(seed)
+            else:
+                seed = None
+        assert np.array_equal(out, host), cuts   # bit-identical: same summation order
+
+
+def test_full_size_properties_512():
+    """BASELINE config 2 size: properties that do not need the (17-minute) CPU oracle."""
+    from aind_exaspim_neuron_segmentation_b200 import predict
+
+    model = _model("rescaled", 19)
+    vol = lightsheet_volume((512, 512, 512), 20, n_paths=300)
+    out = predict(vol, model, verbose=False)
+    assert out.shape == (3, 512, 512, 512) and out.dtype == np.float32
+    assert np.isfinite(out).all() and out.min() >= 0 and out.max() <= 1
+    # uncovered shell: first 8 planes on every axis; overhang axes are covered to the end
+    assert out[:, :8].max() == 0 and out[:, :, :8].max() == 0 and out[:, :, :, :8].max() == 0
+    assert out[:, 8:, 8:, 8:].min() > 0
+    # tiling invariance: the sub-volume [0:160)^3 shares its first patch rows with the big one
+    # only up to normalisation, so compare instead against a second run (determinism)
+    again = predict(vol, model, verbose=False, batch_size=64)
+    assert np.array_equal(out, again)

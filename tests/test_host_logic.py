@@ -1,0 +1,167 @@
+"""CPU tests of the host-side logic behind the C ABI (no compute calls, no GPU)."""
+
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from aind_exaspim_neuron_segmentation_b200 import _native, inference
+from aind_exaspim_neuron_segmentation_b200.engine import percentiles_from_hist, plan_slab
+from oracle import predict_ref as pr
+
+from helpers import ROOT, make_volume
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "exaspim_b200.h")).read()
+    declared = set(re.findall(r"\b(exa_[a-z_0-9]+)\s*\(", header))
+    assert len(declared) >= 18
+    handle = ctypes.CDLL(_native.build())
+    for name in declared:
+        assert hasattr(handle, name), f"{name} declared in the header but not exported"
+    assert declared == set(_native.EXPORTED_SYMBOLS)
+    assert b"sm_100a" in _native.lib().exa_version()
+
+
+def test_create_fails_loudly_without_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    h = ctypes.c_void_p()
+    code = _native.lib().exa_create(0, 0, ctypes.byref(h))
+    assert code < 0 and not h.value
+    assert b"no CPU fallback" in _native.lib().exa_last_error(None)
+    with pytest.raises(RuntimeError):
+        from aind_exaspim_neuron_segmentation_b200 import UNet3D
+
+        UNet3D(3).eval()(torch.zeros(1, 1, 16, 16, 16))
+
+
+def test_count_and_starts_match_oracle_and_c_abi(golden_meta):
+    lib = _native.lib()
+    for t in golden_meta["tiling"]:
+        dims, patch, ov = t["dims"], t["patch"], t["overlap"]
+        shape5 = (1, 1) + tuple(dims)
+        assert inference.count_patches(shape5, patch, ov) == t["n"]
+        starts = list(inference.generate_patch_starts(shape5, patch, ov))
+        assert starts == [tuple(s) for s in pr.patch_starts(dims, patch, ov)]
+        p3 = (ctypes.c_int32 * 3)(*patch)
+        o3 = (ctypes.c_int32 * 3)(*ov)
+        n = lib.exa_count_patches(*dims, p3, o3)
+        assert n == t["n"]
+        buf = (ctypes.c_int32 * (3 * n))()
+        assert lib.exa_patch_starts(*dims, p3, o3, buf, n) == n
+        assert np.array(buf[:]).reshape(-1, 3).tolist() == [list(s) for s in starts]
+    with pytest.raises(AssertionError):
+        inference.count_patches((96, 96, 96), (96, 96, 96), (32, 32, 32))
+
+
+def test_percentiles_from_histogram_are_bit_exact():
+    rng = np.random.default_rng(0)
+    cases = [((96, 96, 96), 1000, (1, 99.9)), ((33, 17, 29), 700, (5, 99)), ((20, 20, 20), 300, (50, 50.5)),
+             ((7, 5, 3), 1000, (0, 100)), ((64, 64, 64), 1000, (1, 99.9)), ((11, 13, 17), 50, (2.5, 97.5))]
+    for shape, clip, pct in cases:
+        for hi in (2000, 1200, 40):
+            vol = rng.integers(0, hi, shape, dtype=np.uint16)
+            clipped = np.minimum(vol, clip)
+            hist = np.bincount(clipped.ravel(), minlength=clip + 1)
+            mn, mx = percentiles_from_hist(hist, *pct)
+            rmn, rmx = np.percentile(clipped, pct)
+            assert mn == float(rmn) and mx == float(rmx), (shape, clip, pct, hi)
+    # many random percentiles on one skewed volume
+    vol = (rng.gamma(2.0, 60.0, (40, 40, 40))).astype(np.uint16)
+    clipped = np.minimum(vol, 1000)
+    hist = np.bincount(clipped.ravel(), minlength=1001)
+    for q in rng.uniform(0, 100, 200):
+        a, b = percentiles_from_hist(hist, float(q), float(100 - q))
+        ra, rb = np.percentile(clipped, (q, 100 - q))
+        assert a == float(ra) and b == float(rb)
+
+
+def test_golden_norm_scalars(golden_meta):
+    for n in golden_meta["norms"]:
+        clipped = np.minimum(make_volume(n["shape"], n["seed"]), n["clip"])
+        hist = np.bincount(clipped.ravel(), minlength=n["clip"] + 1)
+        mn, mx = percentiles_from_hist(hist, *n["pct"])
+        assert mn == n["mn"] and mx == n["mx"]
+
+
+def _params(patch=(96, 96, 96), overlap=(32, 32, 32), trim=8):
+    return _native.make_params(patch, overlap, trim, 1000, (1, 99.9))
+
+
+def test_slab_plans_tile_the_volume():
+    for dims, patch, ov, trim in [((1024, 64, 64), (96,) * 3, (32,) * 3, 8), ((512, 40, 40), (96,) * 3, (32,) * 3, 8),
+                                  ((512, 40, 40), (128,) * 3, (32,) * 3, 8), ((200, 40, 40), (32,) * 3, (8,) * 3, 4),
+                                  ((96, 96, 96), (96,) * 3, (32,) * 3, 8)]:
+        p = _params(patch, ov, trim)
+        nz = plan_slab(dims, p, 0, 0)["nz"]
+        cover = pr.coverage_count_axis(dims[0], patch[0], ov[0], trim)
+        for world in (1, 2, 3, 4, 8):
+            rows = inference.split_rows(nz, world)
+            assert rows[0][0] == 0 and rows[-1][1] == nz
+            assert all(a[1] == b[0] for a, b in zip(rows, rows[1:]))
+            owned = np.zeros(dims[0], int)
+            prev = None
+            for r in rows:
+                if r[1] == r[0]:
+                    continue
+                pl = plan_slab(dims, p, *r)
+                owned[pl["out_z0"]:pl["out_z1"]] += 1
+                stride = patch[0] - ov[0]
+                assert pl["in_z0"] == stride * r[0]
+                assert pl["in_z1"] == min(stride * (r[1] - 1) + patch[0], dims[0])
+                if prev is not None:
+                    assert (prev["halo_z0"], prev["halo_z1"]) == (pl["seed_z0"], pl["seed_z1"])
+                    # the shared planes are exactly those of this slab covered twice at its start
+                    assert all(cover[z] == 2 for z in range(pl["seed_z0"], pl["seed_z1"]))
+                    assert pl["seed_z0"] == pl["out_z0"]
+                # every owned plane is only covered by own rows or the previous slab's last row
+                prev = pl
+            assert (owned == 1).all()
+            assert prev["halo_z1"] - prev["halo_z0"] == 0
+
+
+def test_slab_plan_rejects_triple_overlap():
+    p = _params((64, 64, 64), (48, 32, 32), 0)
+    with pytest.raises(RuntimeError):
+        plan_slab((256, 64, 64), p, 0, 2)
+
+
+def test_input_handling():
+    vol = make_volume((8, 9, 10), 1)
+    out = inference._as_volume_u16(vol[None, None], 1000)
+    assert out.dtype == np.uint16 and out.shape == (8, 9, 10) and np.array_equal(out, vol)
+    big = vol.astype(np.int64) * 100
+    out = inference._as_volume_u16(big, 1000)
+    assert np.array_equal(out, np.minimum(big, 1000))
+    with pytest.raises(TypeError):
+        inference._as_volume_u16(vol.astype(np.float32), 1000)
+    with pytest.raises(ValueError):
+        inference._as_volume_u16(np.zeros((2, 1, 4, 4, 4), np.uint16), 1000)
+
+
+def test_state_dict_layout_matches_reference(golden_meta):
+    import torch
+
+    from aind_exaspim_neuron_segmentation_b200 import UNet3D
+
+    sd = UNet3D(output_channels=3).state_dict()
+    ref = golden_meta["state_dict"]
+    assert list(sd) == list(ref) and len(sd) == 128
+    for k, v in sd.items():
+        assert [list(v.shape), str(v.dtype)] == ref[k]
+    assert sum(v.numel() for v in sd.values()) == 12951285
+    # strict round trip through a file, as load_model does (inference.py:420-421)
+    from oracle.unet_ref import rescaled_state_dict
+
+    m = UNet3D(output_channels=3)
+    m.load_state_dict(rescaled_state_dict(0), strict=True)
+    with pytest.raises(RuntimeError):
+        UNet3D(output_channels=3).load_state_dict(
+            {k: v for k, v in sd.items() if k != "outc.conv.bias"}, strict=True)
+    assert torch.equal(m.state_dict()["inc.double_conv.0.weight"],
+                       rescaled_state_dict(0)["inc.double_conv.0.weight"])
