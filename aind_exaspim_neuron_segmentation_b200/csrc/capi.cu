@@ -208,6 +208,14 @@ int exa_patch_starts(int D, int H, int W, const int32_t patch[3], const int32_t 
   return n;
 }
 
+int exa_profile_begin(exa_engine* e) {
+  return guarded(e, [&] { return e->impl.profile_begin(); });
+}
+
+int exa_profile_end(exa_engine* e, double* ms_by_category, int64_t* launches_by_category, int n) {
+  return guarded(e, [&] { return e->impl.profile_end(ms_by_category, launches_by_category, n); });
+}
+
 int64_t exa_launch_count(const exa_engine* e) { return e ? e->impl.launches : -1; }
 
 }  // extern "C"

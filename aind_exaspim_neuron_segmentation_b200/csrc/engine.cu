@@ -141,6 +141,10 @@ static void free_dev(void* p) {
 
 Engine::~Engine() {
   cudaSetDevice(device_);
+  for (auto& r : prof_) {
+    cudaEventDestroy(r.start);
+    cudaEventDestroy(r.stop);
+  }
   for (auto& L : layers_) {
     free_dev(L.w_bf16);
     free_dev(L.w_f32);
@@ -172,6 +176,57 @@ Status Engine::init() {
                                   std::to_string(prop.major) + std::to_string(prop.minor));
   num_sms_ = prop.multiProcessorCount;
   return Status::OK();
+}
+
+// ---------------------------------------------------------------------------
+// Engine: profiling scopes
+// ---------------------------------------------------------------------------
+Engine::Scope::Scope(Engine* eng, int cat, cudaStream_t st) : e(eng), s(st) {
+  ++e->launches;
+  if (!e->prof_on_) return;
+  ProfRec r;
+  r.cat = cat;
+  if (cudaEventCreate(&r.start) != cudaSuccess || cudaEventCreate(&r.stop) != cudaSuccess) return;
+  cudaEventRecord(r.start, s);
+  stop = r.stop;
+  e->prof_.push_back(r);
+}
+Engine::Scope::~Scope() {
+  if (stop) cudaEventRecord(stop, s);
+}
+
+Status Engine::profile_begin() {
+  EXA_CUDA(cudaSetDevice(device_));
+  for (auto& r : prof_) {
+    cudaEventDestroy(r.start);
+    cudaEventDestroy(r.stop);
+  }
+  prof_.clear();
+  prof_on_ = true;
+  return Status::OK();
+}
+
+Status Engine::profile_end(double* ms_by_cat, int64_t* launches_by_cat, int n) {
+  EXA_CUDA(cudaSetDevice(device_));
+  EXA_CHECK(ms_by_cat && launches_by_cat && n >= CAT_COUNT, "profile_end: need 7 categories");
+  prof_on_ = false;
+  for (int i = 0; i < n; ++i) {
+    ms_by_cat[i] = 0;
+    launches_by_cat[i] = 0;
+  }
+  Status st = Status::OK();
+  for (auto& r : prof_) {
+    float ms = 0.f;
+    cudaError_t e = cudaEventSynchronize(r.stop);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, r.start, r.stop);
+    if (e != cudaSuccess && st.ok) st = Status::Err(std::string("cudaEventElapsedTime: ") + cudaGetErrorString(e));
+    ms_by_cat[r.cat] += ms;
+    launches_by_cat[r.cat] += 1;
+    cudaEventDestroy(r.start);
+    cudaEventDestroy(r.stop);
+  }
+  prof_.clear();
+  return st;
 }
 
 // ---------------------------------------------------------------------------
@@ -407,13 +462,16 @@ Status Engine::ensure_workspace(int batch, int pz, int py, int px) {
 
 Status Engine::conv(const ConvLayer& L, const Act& in, const Act& out, const HeadParams* head,
                     cudaStream_t s) {
-  ++launches;
   if (precision_ == EXA_PRECISION_BF16) {
+    Scope sc(this, CAT_CONV, s);
     return launch_conv_umma(in, out, L.w_bf16, L.bias, head, num_sms_, s);
   }
-  EXA_TRY(launch_conv_fp32(in, out, L.w_f32, L.bias, s));
+  {
+    Scope sc(this, CAT_CONV, s);
+    EXA_TRY(launch_conv_fp32(in, out, L.w_f32, L.bias, s));
+  }
   if (head) {
-    ++launches;
+    Scope sc(this, CAT_HEAD, s);
     EXA_TRY(launch_head_fp32(out, *head, s));
   }
   return Status::OK();
@@ -462,16 +520,18 @@ Status Engine::run_network(const PatchSource& src, int batch, int pz, int py, in
   const Act u4 = act(L.cat4, 0, 32, 32, 0);  // cat4 is dead once up4.0 has run
 
   auto pool = [&](const Act& i, const Act& o) {
-    ++launches;
+    Scope sc(this, CAT_POOL, s);
     return launch_maxpool(i, o, s);
   };
   auto up = [&](const Act& i, const Act& o) {
-    ++launches;
+    Scope sc(this, CAT_UPSAMPLE, s);
     return launch_upsample(i, o, s);
   };
 
-  ++launches;
-  EXA_TRY(launch_stem(src, stem_, a0, s));                  // inc.0 (+gather/normalise)
+  {
+    Scope sc(this, CAT_STEM, s);
+    EXA_TRY(launch_stem(src, stem_, a0, s));                // inc.0 (+gather/normalise)
+  }
   EXA_TRY(conv(layers_[1], a0, x1, nullptr, s));            // inc.3 -> skip slot of CAT4
   EXA_TRY(pool(x1, p1));
   EXA_TRY(conv(layers_[2], p1, d1a, nullptr, s));
@@ -528,7 +588,7 @@ Status Engine::histogram(const uint16_t* vol_dev, int64_t n, int clip, uint64_t*
                          cudaStream_t s) {
   EXA_CUDA(cudaSetDevice(device_));
   EXA_CHECK(vol_dev && hist_dev && n >= 0, "histogram: bad arguments");
-  ++launches;
+  Scope sc(this, CAT_HIST, s);
   return launch_histogram(vol_dev, (size_t)n, clip, (unsigned long long*)hist_dev, s);
 }
 
@@ -661,7 +721,7 @@ Status Engine::slab_partial(float* halo_dev, cudaStream_t s) {
   a.out = halo_dev;
   a.out_cstride = (size_t)nz * plan_.H * plan_.W;
   a.finalize = 0;
-  ++launches;
+  Scope sc(this, CAT_STITCH, s);
   return launch_stitch(a, s);
 }
 
@@ -682,7 +742,7 @@ Status Engine::slab_stitch(const float* seed_dev, float* out_dev, cudaStream_t s
     a.seed_z0 = slab_.seed_z0;
     a.seed_z1 = slab_.seed_z1;
   }
-  ++launches;
+  Scope sc(this, CAT_STITCH, s);
   return launch_stitch(a, s);
 }
 

@@ -62,6 +62,12 @@ class Engine {
   Status slab_partial(float* halo_dev, cudaStream_t s);
   Status slab_stitch(const float* seed_dev, float* out_dev, cudaStream_t s);
 
+  // per-category kernel timing with CUDA events on the launching stream (bench / roofline)
+  enum Category { CAT_HIST = 0, CAT_STEM, CAT_CONV, CAT_POOL, CAT_UPSAMPLE, CAT_HEAD, CAT_STITCH,
+                  CAT_COUNT };
+  Status profile_begin();
+  Status profile_end(double* ms_by_cat, int64_t* launches_by_cat, int n);
+
   std::string last_error;
   int64_t launches = 0;
 
@@ -71,6 +77,20 @@ class Engine {
                      const HeadParams& head, cudaStream_t s);
   Status conv(const ConvLayer& L, const Act& in, const Act& out, const HeadParams* head,
               cudaStream_t s);
+
+  struct ProfRec {
+    int cat;
+    cudaEvent_t start, stop;
+  };
+  struct Scope {  // counts the launch and, when profiling, brackets it with two events
+    Engine* e;
+    cudaStream_t s;
+    cudaEvent_t stop = nullptr;
+    Scope(Engine* eng, int cat, cudaStream_t st);
+    ~Scope();
+  };
+  bool prof_on_ = false;
+  std::vector<ProfRec> prof_;
 
   int device_, precision_;
   int num_sms_ = 148;

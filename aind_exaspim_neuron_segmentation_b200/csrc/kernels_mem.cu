@@ -85,8 +85,11 @@ histogram_kernel(const uint16_t* __restrict__ vol, size_t n, int clip,
     for (int i = threadIdx.x; i < bins; i += blockDim.x) sh[i] = 0;
     __syncthreads();
   }
-  const size_t n8 = n / 8;
-  const uint4* v8 = reinterpret_cast<const uint4*>(vol);
+  // scalar head up to the first 16-byte boundary, 16-byte vector body, scalar tail
+  size_t head = ((16 - ((uintptr_t)vol & 15)) & 15) / 2;
+  if (head > n) head = n;
+  const size_t n8 = (n - head) / 8;
+  const uint4* v8 = reinterpret_cast<const uint4*>(vol + head);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
     const uint4 q = __ldg(v8 + i);
@@ -104,9 +107,10 @@ histogram_kernel(const uint16_t* __restrict__ vol, size_t n, int clip,
       }
     }
   }
-  // tail (n not a multiple of 8)
   if (blockIdx.x == 0) {
-    for (size_t i = n8 * 8 + threadIdx.x; i < n; i += blockDim.x) {
+    const size_t tail0 = head + n8 * 8;
+    for (size_t j = threadIdx.x; j < head + (n - tail0); j += blockDim.x) {
+      const size_t i = j < head ? j : tail0 + (j - head);
       const int v = min((int)vol[i], clip);
       if (use_smem) atomicAdd(&sh[v], 1u);
       else atomicAdd(&hist[v], 1ull);
@@ -124,7 +128,7 @@ histogram_kernel(const uint16_t* __restrict__ vol, size_t n, int clip,
 Status launch_histogram(const uint16_t* vol, size_t n, int clip, unsigned long long* hist,
                         cudaStream_t s) {
   EXA_CHECK(clip >= 0 && clip <= 65535, "brightness_clip must be in [0, 65535]");
-  EXA_CHECK(((uintptr_t)vol & 15) == 0, "volume pointer must be 16-byte aligned");
+  EXA_CHECK(((uintptr_t)vol & 1) == 0, "volume pointer must be 2-byte aligned");
   EXA_CUDA(cudaMemsetAsync(hist, 0, sizeof(unsigned long long) * (clip + 1), s));
   if (n == 0) return Status::OK();
   const int bins = clip + 1;

@@ -79,6 +79,19 @@ class Engine:
     def launch_count(self):
         return int(self._lib.exa_launch_count(self._h))
 
+    PROFILE_CATEGORIES = ("histogram", "stem", "conv", "pool", "upsample", "head", "stitch")
+
+    def profile_begin(self):
+        _native.check(self._lib.exa_profile_begin(self._h), self._h, "exa_profile_begin")
+
+    def profile_end(self):
+        """-> {category: (device ms, launches)} since profile_begin (synchronises)."""
+        n = len(self.PROFILE_CATEGORIES)
+        ms = (ctypes.c_double * n)()
+        cnt = (ctypes.c_int64 * n)()
+        _native.check(self._lib.exa_profile_end(self._h, ms, cnt, n), self._h, "exa_profile_end")
+        return {k: (ms[i], int(cnt[i])) for i, k in enumerate(self.PROFILE_CATEGORIES)}
+
     # -- operator level ----------------------------------------------------------
     def forward(self, x):
         """float32 (B,1,Pz,Py,Px) cuda tensor -> float32 logits (B,C,Pz,Py,Px)."""
@@ -97,11 +110,15 @@ class Engine:
         return out
 
     # -- whole path ---------------------------------------------------------------
-    def predict_host(self, vol_u16, params):
+    def predict_host(self, vol_u16, params, out=None):
         """numpy uint16 (D,H,W) -> numpy float32 (C,D,H,W), host buffers end to end."""
         vol_u16 = np.ascontiguousarray(vol_u16, dtype=np.uint16)
         d, h, w = vol_u16.shape
-        out = np.empty((self.out_channels, d, h, w), dtype=np.float32)
+        if out is None:
+            out = np.empty((self.out_channels, d, h, w), dtype=np.float32)
+        elif (out.dtype != np.float32 or out.shape != (self.out_channels, d, h, w)
+              or not out.flags["C_CONTIGUOUS"]):
+            raise ValueError("out must be a C-contiguous float32 array of shape (C, D, H, W)")
         code = self._lib.exa_predict(
             self._h, vol_u16.ctypes.data_as(ctypes.c_void_p), d, h, w, ctypes.byref(params),
             out.ctypes.data_as(ctypes.c_void_p),

@@ -129,8 +129,13 @@ def predict(
     trim=8,
     verbose=True,
     precision=None,
+    out=None,
 ):
     """Affinity (or foreground) prediction for a 3-D volume; see reference inference.py:29-126.
+
+    ``precision`` ("bf16" | "fp32") and ``out`` (a preallocated C-contiguous float32
+    ``(C, D, H, W)`` array, e.g. pinned memory, filled and returned instead of a new array)
+    are extensions; defaults keep the reference behaviour.
 
     Returns a new C-contiguous float32 array ``(3, D, H, W)`` (``(D, H, W)`` when
     ``affinity_mode=False``).  ``batch_size`` is accepted for compatibility and used as
@@ -155,7 +160,7 @@ def predict(
         pbar = tqdm(total=n_patches, desc="Predict")
     params = _native.make_params(patch_shape, overlap, trim, brightness_clip,
                                  normalization_percentiles, batch=max(int(batch_size), 32))
-    out = engine.predict_host(vol, params)
+    out = engine.predict_host(vol, params, out=out)
     if pbar is not None:
         pbar.update(n_patches)
         pbar.close()
@@ -198,6 +203,121 @@ class _EngineSlabBackend:
     def to_device(self, host_u16):
         return torch.from_numpy(host_u16).to(self.device, non_blocking=True)
 
+    def sync(self):
+        torch.cuda.current_stream(self.device).synchronize()
+
+
+class SlabJob:
+    """One rank's share of a volume sharded by z patch-rows.
+
+    Exchange steps, all small next to the convolutions:
+    C1 all-reduce of the (clip+1)-bin histogram -> global percentiles,
+    C2 send of raw partial sums for the planes shared with the next rank's first row
+       (summed there in the reference's patch order, so the result is bit-identical to
+       the single-GPU one),
+    C3 all-gather of the owned output planes.
+    ``backend`` is a test seam for the slab compute; the default is the native engine.
+    """
+
+    def __init__(self, shape, params, n_channels, backend, group=None):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.shape = tuple(int(v) for v in shape)
+        self.params = params
+        self.backend = backend
+        self.n_channels = n_channels
+        if backend.out_channels != n_channels:
+            raise ValueError("model output channels do not match affinity_mode")
+        nz = plan_slab(self.shape, params, 0, 0)["nz"]
+        self.all_rows = split_rows(nz, self.world)
+        self.all_plans = [plan_slab(self.shape, params, *r) for r in self.all_rows]
+        self.rows = self.all_rows[self.rank]
+        self.plan = self.all_plans[self.rank]
+        self.has_rows = self.rows[1] > self.rows[0]
+        # plane range this rank histograms: from its slab start to the next slab's start
+        nxt = [p["in_z0"] for p, r in zip(self.all_plans, self.all_rows) if r[1] > r[0]]
+        nxt.append(self.shape[0])
+        order = sum(1 for r in self.all_rows[:self.rank] if r[1] > r[0])
+        self.hist_range = (nxt[order], nxt[order + 1]) if self.has_rows else (0, 0)
+        self.own_planes = [max(p["out_z1"] - p["out_z0"], 0) if r[1] > r[0] else 0
+                           for p, r in zip(self.all_plans, self.all_rows)]
+
+    def slab_bounds(self):
+        """Input planes [z0, z1) this rank needs resident."""
+        return (self.plan["in_z0"], self.plan["in_z1"]) if self.has_rows else (0, 0)
+
+    def upload(self, vol_host):
+        z0, z1 = self.slab_bounds()
+        return self.backend.to_device(vol_host[z0:z1])
+
+    def _peer(self, group_rank):
+        if self.group is None:
+            return group_rank
+        return self.dist.get_global_rank(self.group, group_rank)
+
+    def run(self, slab, gather=True):
+        """slab: device uint16 planes [in_z0, in_z1).  -> device float32 (C, D|own, H, W)."""
+        dist, be, p = self.dist, self.backend, self.params
+        dev = be.device
+        c, (d, h, w) = self.n_channels, self.shape
+        clip = p.brightness_clip
+        # C1: global histogram -> exact percentiles
+        if self.has_rows and self.hist_range[1] > self.hist_range[0]:
+            z0 = self.plan["in_z0"]
+            hist = be.histogram(slab[self.hist_range[0] - z0:self.hist_range[1] - z0], clip)
+        else:
+            hist = torch.zeros(clip + 1, dtype=torch.int64, device=dev)
+        if self.world > 1:
+            dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=self.group)
+        mn, mx = percentiles_from_hist(hist.cpu().numpy().astype(np.uint64), p.pct_lo, p.pct_hi)
+        if self.has_rows:
+            be.run(slab, self.shape, p, self.rows, mn, mx)
+        # C2: partial sums of the shared planes go to their owner (the next rank)
+        seed = None
+        if self.world > 1 and self.has_rows:
+            n_halo = self.plan["halo_z1"] - self.plan["halo_z0"]
+            n_seed = self.plan["seed_z1"] - self.plan["seed_z0"]
+            ops, halo = [], None
+            if n_seed > 0:
+                seed = torch.empty((c, n_seed, h, w), dtype=torch.float32, device=dev)
+                ops.append(dist.P2POp(dist.irecv, seed, self._peer(self.rank - 1), self.group))
+            if n_halo > 0:
+                halo = torch.empty((c, n_halo, h, w), dtype=torch.float32, device=dev)
+                be.partial(halo)
+                ops.append(dist.P2POp(dist.isend, halo, self._peer(self.rank + 1), self.group))
+            if ops:
+                be.sync()  # partial sums are produced on the engine's stream
+                for req in dist.batch_isend_irecv(ops):
+                    req.wait()
+        nz_own = self.own_planes[self.rank]
+        own = torch.zeros((c, nz_own, h, w), dtype=torch.float32, device=dev)
+        if self.has_rows and nz_own > 0:
+            be.stitch(seed, own)
+        if not gather or self.world == 1:
+            return own
+        # C3: gather of the owned planes (channel-major output: concatenate along z)
+        be.sync()
+        pieces = [torch.empty((c, n, h, w), dtype=torch.float32, device=dev)
+                  for n in self.own_planes]
+        if len(set(self.own_planes)) == 1:
+            dist.all_gather(pieces, own, group=self.group)
+        else:
+            for g in range(self.world):  # ragged slabs: one broadcast per rank
+                if self.own_planes[g] == 0:
+                    continue
+                if g == self.rank:
+                    pieces[g].copy_(own)
+                dist.broadcast(pieces[g], src=self._peer(g), group=self.group)
+        return torch.cat(pieces, dim=1)
+
+    def own_bounds(self):
+        z0 = self.plan["out_z0"] if self.has_rows else 0
+        return z0, z0 + self.own_planes[self.rank]
+
 
 def predict_sharded(
     img,
@@ -213,115 +333,23 @@ def predict_sharded(
     group=None,
     gather=True,
     backend=None,
-    device_out=False,
 ):
     """``predict`` sharded by z patch-rows over the ranks of a ``torch.distributed`` group.
 
-    Every rank passes the same ``img`` (only its slab plus a 32-plane input halo is
-    uploaded).  Exchange steps, all small next to the convolutions:
-    C1 all-reduce of the 1001-bin histogram (global percentiles), C2 send of raw partial
-    sums for the planes shared with the next rank's first row (summed there in the
-    reference's order), C3 gather of the owned output slabs to every rank.
-
-    Returns the full ``(C, D, H, W)`` array on every rank when ``gather`` is true, else
-    ``(z0, z1, slab)`` with the rank's own planes.  ``backend`` is a test seam for the slab
-    compute; the default is the native engine.
+    One process per GPU; every rank passes the same ``img`` (only its slab, including the
+    input halo it shares with the next rank, is uploaded).  With ``gather`` every rank
+    returns the full ``(C, D, H, W)`` array; otherwise ``(z0, z1, planes)`` with the planes
+    it owns.  With a world size of 1 this is the same computation as ``predict``.
     """
-    import torch.distributed as dist
-
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
-    rank = dist.get_rank(group) if dist.is_initialized() else 0
     vol = _as_volume_u16(img, brightness_clip)
-    shape = vol.shape
     if backend is None:
         backend = _EngineSlabBackend(_engine_for(model, precision))
-    n_channels = 3 if affinity_mode else 1
-    if backend.out_channels != n_channels:
-        raise ValueError("model output channels do not match affinity_mode")
     params = _native.make_params(patch_shape, overlap, trim, brightness_clip,
                                  normalization_percentiles, batch=max(int(batch_size), 32))
-    clip = params.brightness_clip
-    full = plan_slab(shape, params, 0, 0)  # grid sizes only
-    rows = split_rows(full["nz"], world)[rank]
-    plan = plan_slab(shape, params, rows[0], rows[1])
-    dev = backend.device
-    h, w = shape[1], shape[2]
-
-    # C1: global histogram -> exact percentiles.  Ranks histogram disjoint plane ranges.
-    cuts = [round(shape[0] * g / world) for g in range(world + 1)]
-    part = backend.to_device(vol[cuts[rank]:cuts[rank + 1]])
-    hist = backend.histogram(part, clip) if part.numel() else torch.zeros(
-        clip + 1, dtype=torch.int64, device=dev)
-    if world > 1:
-        dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
-    mn, mx = percentiles_from_hist(hist.cpu().numpy().astype(np.uint64),
-                                   params.pct_lo, params.pct_hi)
-
-    # slab upload + all patches of the rank's rows
-    has_rows = rows[1] > rows[0]
-    if has_rows:
-        slab = backend.to_device(vol[plan["in_z0"]:plan["in_z1"]])
-        backend.run(slab, shape, params, rows, mn, mx)
-
-    # C2: partial sums of the shared planes go to the owner (the next rank)
-    seed = None
-    reqs = []
-    n_halo = plan["halo_z1"] - plan["halo_z0"]
-    n_seed = plan["seed_z1"] - plan["seed_z0"]
-    if world > 1:
-        if has_rows and n_seed > 0:
-            seed = torch.empty((n_channels, n_seed, h, w), dtype=torch.float32, device=dev)
-            reqs.append(dist.irecv(seed, src=_global_rank(group, rank - 1), group=group))
-        if has_rows and n_halo > 0 and rank + 1 < world:
-            halo = torch.empty((n_channels, n_halo, h, w), dtype=torch.float32, device=dev)
-            backend.partial(halo)
-            if dev.type == "cuda":
-                torch.cuda.current_stream(dev).synchronize()
-            reqs.append(dist.isend(halo, dst=_global_rank(group, rank + 1), group=group))
-        for r in reqs:
-            r.wait()
-
-    # own planes
-    nz_own = max(plan["out_z1"] - plan["out_z0"], 0) if has_rows else 0
-    own = torch.zeros((n_channels, nz_own, h, w), dtype=torch.float32, device=dev)
-    if has_rows and nz_own > 0:
-        backend.stitch(seed, own)
-    if not gather:
-        return plan["out_z0"], plan["out_z0"] + nz_own, own
-
-    # C3: gather of the owned slabs (channel-major output => one strided copy per rank)
-    if world == 1:
-        result = own
-    else:
-        all_plans = [plan_slab(shape, params, *r) for r in split_rows(full["nz"], world)]
-        sizes = [max(p["out_z1"] - p["out_z0"], 0) if r[1] > r[0] else 0
-                 for p, r in zip(all_plans, split_rows(full["nz"], world))]
-        pieces = [torch.empty((n_channels, s, h, w), dtype=torch.float32, device=dev)
-                  for s in sizes]
-        dist.all_gather(pieces, own, group=group) if len(set(sizes)) == 1 else \
-            _all_gather_ragged(pieces, own, rank, world, group)
-        result = torch.cat(pieces, dim=1)
-    if device_out:
-        return result if affinity_mode else result[0]
+    job = SlabJob(vol.shape, params, 3 if affinity_mode else 1, backend, group)
+    result = job.run(job.upload(vol), gather=gather)
     out = result.cpu().numpy()
-    return out if affinity_mode else out[0]
-
-
-def _global_rank(group, group_rank):
-    import torch.distributed as dist
-
-    if group is None:
-        return group_rank
-    return dist.get_global_rank(group, group_rank)
-
-
-def _all_gather_ragged(pieces, own, rank, world, group):
-    """all_gather for per-rank slabs of different plane counts: one broadcast per rank."""
-    import torch.distributed as dist
-
-    for g in range(world):
-        if pieces[g].numel() == 0:
-            continue
-        if g == rank:
-            pieces[g].copy_(own)
-        dist.broadcast(pieces[g], src=_global_rank(group, g), group=group)
+    if gather:
+        return out if affinity_mode else out[0]
+    z0, z1 = job.own_bounds()
+    return z0, z1, (out if affinity_mode else out[0])

@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""Benchmark of the affinity-prediction hot path (BASELINE.json metric: affinity voxels/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the whole path over one synthetic uint16 volume:
+histogram -> percentiles -> (gather+normalise+stem, 17 tcgen05 convs, pools, upsamples, fused
+head+sigmoid+trim) per wave of patches -> overlap stitch -> (N>1: halo exchange + all-gather).
+N=1 runs BASELINE config 2 (512^3, patch 96^3 -> 512 patches); N GPUs run N x 512^3 voxels
+(1024x512x512, 1024x1024x512, 1024^3 = BASELINE config 3), sharded by z patch-rows: weak scaling.
+
+`value`   : voxels/s with the rank's uint16 slab already resident in HBM, device-timed (CUDA
+            events), max over ranks.
+`e2e`     : same metric through the public API with HOST buffers: pinned H2D of the slab and
+            D2H of the rank's output planes inside the timed region.
+`roofline`: the conv3x3x3 tcgen05 kernels (the dominant kernels), executed FLOPs / summed CUDA
+            event time of their launches inside the timed steps, against the measured dense
+            bf16 peak (MEASURED_PEAKS.json, sustained figure: timed inside a long step).
+`cpu_baseline` / `--impl reference`: the CPU oracle port of the reference path (oracle/),
+            all host threads, on a bounded sample (4 patches) of the same workload.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PATCH = (96, 96, 96)
+OVERLAP = (32, 32, 32)
+TRIM = 8
+F_PATCH_96 = 370_145_230_848          # 2*MACs of the 19 convs per 96^3 patch
+F_STEM_96 = 2 * 96 ** 3 * 32 * 27     # inc.double_conv.0 (SIMT stem kernel)
+F_HEAD_96 = 2 * 96 ** 3 * 3 * 32      # outc (fused into the last conv's epilogue)
+F_CONV_96 = F_PATCH_96 - F_STEM_96 - F_HEAD_96  # executed by the tcgen05 conv kernels
+
+
+def volume_shape(n_gpus):
+    shape = [512, 512, 512]
+    k, axis = n_gpus, 0
+    while k > 1:
+        shape[axis] *= 2
+        k //= 2
+        axis += 1
+        if axis == 3:
+            axis = 0
+    return tuple(shape)
+
+
+def synth_planes(shape, z0, z1, seed=1):
+    """Planes [z0, z1) of a deterministic lightsheet-like uint16 volume of `shape`.
+
+    Poisson(40) background plus sparse bright straight 'neurite' segments (peak intensity
+    log-uniform 150..4000, 3-voxel cross-section) so that both the 1000-clip and the 99.9th
+    percentile bite.  Generated in 64-plane chunks seeded by (seed, chunk) so that any rank can
+    produce any plane range without building the whole volume.
+    """
+    d, h, w = shape
+    out = np.empty((z1 - z0, h, w), np.uint16)
+    for c in range(z0 // 64, (z1 + 63) // 64):
+        rng = np.random.default_rng([seed, c])
+        a, b = c * 64, min(c * 64 + 64, d)
+        chunk = rng.poisson(40, (b - a, h, w)).astype(np.uint16)
+        n_seg = max(8, (b - a) * h * w // 200_000)
+        p0 = np.stack([rng.uniform(0, b - a, n_seg), rng.uniform(0, h, n_seg),
+                       rng.uniform(0, w, n_seg)], 1)
+        dirs = rng.normal(size=(n_seg, 3))
+        dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+        amp = np.exp(rng.uniform(np.log(150), np.log(4000), n_seg))
+        t = np.arange(0, 60, 0.5)[None, :, None]
+        pts = np.rint(p0[:, None, :] + dirs[:, None, :] * t).astype(np.int64)  # (n_seg, T, 3)
+        val = np.broadcast_to(amp[:, None], pts.shape[:2]).ravel()
+        pts = pts.reshape(-1, 3)
+        for dz in (0, 1):
+            for dy in (-1, 0, 1):
+                for dx in (-1, 0, 1):
+                    q = pts + (dz, dy, dx)
+                    ok = ((q[:, 0] >= 0) & (q[:, 0] < b - a) & (q[:, 1] >= 0) & (q[:, 1] < h)
+                          & (q[:, 2] >= 0) & (q[:, 2] < w))
+                    qq = q[ok]
+                    np.maximum.at(chunk, (qq[:, 0], qq[:, 1], qq[:, 2]),
+                                  np.minimum(val[ok] + 40, 65535).astype(np.uint16))
+        lo, hi = max(a, z0), min(b, z1)
+        out[lo - z0:hi - z0] = chunk[lo - a:hi - a]
+    return out
+
+
+# --- clocks -------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "200", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"bf16_tflops": p.get("bf16_tflops_sustained", p.get("bf16_tflops")),
+                "hbm_gbs": p.get("hbm_gbs"), "source": "measured (MEASURED_PEAKS.json, sustained)"}
+    return {"bf16_tflops": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def ncu_traffic():
+    """Per-launch DRAM bytes of the dominant conv kernel from the committed ncu capture."""
+    path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get("traffic_bytes_per_launch")
+    return None
+
+
+# --- CPU oracle leg ----------------------------------------------------------------------
+CPU_SAMPLE_SHAPE = (96, 160, 160)  # 1 x 2 x 2 patches of the same synthetic volume
+
+
+def cpu_oracle_step(sd, vol):
+    from oracle.predict_ref import predict_ref
+    from oracle.unet_ref import make_forward_fn
+
+    t0 = time.perf_counter()
+    out = predict_ref(vol, make_forward_fn(sd), patch_shape=PATCH, overlap=OVERLAP, trim=TRIM)
+    return time.perf_counter() - t0, out
+
+
+def cpu_baseline(steps=1, warmup=0):
+    import torch
+
+    from oracle.unet_ref import rescaled_state_dict
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = rescaled_state_dict(0)
+    vol = synth_planes(volume_shape(1), 0, 96)[:, :160, :160].copy()
+    for _ in range(warmup):
+        cpu_oracle_step(sd, vol)
+    times = [cpu_oracle_step(sd, vol)[0] for _ in range(max(steps, 1))]
+    sec = float(np.mean(times))
+    n_patch = 4
+    vox_per_patch = 512 ** 3 / 512  # stitched output voxels per patch of the 512^3 workload
+    return {"value": n_patch * vox_per_patch / sec, "unit": "voxels/s", "cores": cores,
+            "kind": "port",
+            "sample": (f"oracle/ CPU port of reference predict (torch fp32 convs, {cores} threads) on "
+                       f"a {CPU_SAMPLE_SHAPE} corner of the same volume = 4 patches, "
+                       f"{sec:.2f} s/step; scaled by the workload's 262144 output voxels per patch"),
+            "sec_per_patch": sec / n_patch}, sec
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base, sec = cpu_baseline(steps=args.steps, warmup=min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": "affinity voxels/sec", "value": base["value"],
+        "unit": "voxels/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": "voxels/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n):
+    shape = volume_shape(n)
+    return {"workload": f"predict() on a synthetic {shape[0]}x{shape[1]}x{shape[2]} uint16 volume, "
+                        f"patch 96^3 overlap 32 trim 8 ({(shape[0] // 64) * (shape[1] // 64) * (shape[2] // 64)} "
+                        "patches), random-init UNet3D, affinity_mode=True",
+            "volume": list(shape), "patch_shape": list(PATCH), "overlap": list(OVERLAP), "trim": TRIM,
+            "sharding": f"z patch-rows over {n} GPU(s)" if n > 1 else "single GPU",
+            "l2": "per-wave activations (~8 GB) and the volume are far larger than the 126 MB L2; "
+                  "no flush needed between steps"}
+
+
+# --- B200 arm ------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from aind_exaspim_neuron_segmentation_b200 import UNet3D, _native
+    from aind_exaspim_neuron_segmentation_b200.inference import SlabJob, _EngineSlabBackend
+    from oracle.unet_ref import rescaled_state_dict  # weights recipe only (seeded random init)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n = max(world, 1)
+    shape = volume_shape(n)
+    model = UNet3D(output_channels=3)
+    model.load_state_dict(rescaled_state_dict(0), strict=True)
+    model = model.to(dev).eval()
+    engine = model.engine("bf16")
+    params = _native.make_params(PATCH, OVERLAP, TRIM, 1000, (1, 99.9), batch=args.batch)
+    job = SlabJob(shape, params, 3, _EngineSlabBackend(engine), None)
+    z0, z1 = job.slab_bounds()
+    host = torch.from_numpy(synth_planes(shape, z0, z1)).pin_memory()
+    slab = host.to(dev, non_blocking=True)
+    torch.cuda.synchronize()
+    oz0, oz1 = job.own_bounds()
+    host_out = torch.empty((3, oz1 - oz0, shape[1], shape[2]), dtype=torch.float32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        return job.run(slab, gather=True)
+
+    def step_e2e():
+        s = host.to(dev, non_blocking=True)
+        own = job.run(s, gather=False)
+        host_out.copy_(own, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return own
+
+    for _ in range(max(args.warmup, 3)):
+        out = step_device()
+    del out
+    barrier()
+
+    # ---- device-timed region: K steps ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = engine.launch_count
+    engine.profile_begin()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        out = step_device()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    prof = engine.profile_end()
+    launches = engine.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    checksum = float(out[:, ::37, ::41, ::43].double().sum().item())
+    del out
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = t.item() / args.steps
+    voxels = float(np.prod(shape))
+
+    # ---- end-to-end (host buffers, pinned H2D + D2H inside the timed region) ----
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record()
+    barrier()
+    wall = (time.perf_counter() - t0) * 1e3
+    t = torch.tensor([max(e0.elapsed_time(e1), wall)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = t.item() / args.steps
+    h2d = torch.tensor([host.numel() * 2], dtype=torch.float64, device=dev)
+    d2h = torch.tensor([host_out.numel() * 4], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(h2d)
+        dist.all_reduce(d2h)
+
+    if rank == 0:
+        peaks = measured_peaks()
+        n_patches_rank = (job.rows[1] - job.rows[0]) * (shape[1] // 64) * (shape[2] // 64)
+        conv_ms, conv_launches = prof["conv"]
+        conv_flops = n_patches_rank * F_CONV_96 * args.steps
+        achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        line = {
+            "metric": "affinity voxels/sec", "value": voxels / (ms_step * 1e-3), "unit": "voxels/s",
+            "n_gpus": n, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(n),
+            "e2e": {"value": voxels / (e2e_ms * 1e-3), "unit": "voxels/s",
+                    "h2d_bytes_per_step": int(h2d.item()), "d2h_bytes_per_step": int(d2h.item()),
+                    "ms_per_step": e2e_ms,
+                    "note": "pinned uint16 slab H2D + owned fp32 planes D2H per step, every rank"},
+            "gpu_launches": int(launches),
+            "roofline": {
+                "kernel": "conv3x3_umma_kernel (17 launches per wave of patches; rank 0)",
+                "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"],
+                "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
+                "peak_source": peaks["source"], "traffic": ncu_traffic(),
+                "launches": conv_launches, "avg_launch_ms": conv_ms / max(conv_launches, 1),
+                "flops_per_patch": F_CONV_96,
+                "share_of_step": conv_ms / (ms_step * args.steps),
+            },
+            "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
+            "clocks": clocks,
+            "checksum": checksum,
+        }
+        if n == 1 and not args.no_cpu:
+            line["cpu_baseline"], _ = cpu_baseline(steps=1)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="patches per wave")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # convenience: launched without torchrun -> start one process per GPU ourselves
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+               f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1", "--master-port",
+               "29531", os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -127,6 +127,16 @@ int exa_count_patches(int D, int H, int W, const int32_t patch[3], const int32_t
 int exa_patch_starts(int D, int H, int W, const int32_t patch[3], const int32_t overlap[3],
                      int32_t* starts, int capacity);
 
+/* ---- measurement (bench.py roofline; no reference analogue) ------------------------
+ * Between exa_profile_begin and exa_profile_end every kernel launch of this engine is
+ * bracketed by two CUDA events on its stream; exa_profile_end synchronises and returns
+ * summed device milliseconds and launch counts per category:
+ * 0 histogram, 1 stem(gather+normalise+inc.0), 2 conv3x3x3, 3 max-pool, 4 upsample,
+ * 5 head (fp32 mode only; fused into the last conv otherwise), 6 stitch.  n >= 7. */
+enum { EXA_PROFILE_CATEGORIES = 7 };
+int exa_profile_begin(exa_engine* e);
+int exa_profile_end(exa_engine* e, double* ms_by_category, int64_t* launches_by_category, int n);
+
 /* number of kernel launches issued by this engine since creation (bench bookkeeping) */
 int64_t exa_launch_count(const exa_engine* e);
 
