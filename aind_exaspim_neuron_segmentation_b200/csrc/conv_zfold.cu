@@ -1,0 +1,98 @@
+// Host launcher for the z-folded halo-tile tcgen05 conv (kernel in conv_zfold.cuh).
+#include "conv_zfold.cuh"
+
+#include "kernels.h"
+#include "tmap.h"
+
+namespace exa {
+
+namespace {
+
+template <int CIN, int EPI>
+Status launch_zf(const CUtensorMap& tx, const CUtensorMap& tw, const ZfArgs& a, int grid,
+                 cudaStream_t s) {
+  using S = ZfSmem<CIN>;
+  static bool configured = false;
+  if (!configured) {
+    EXA_CUDA(cudaFuncSetAttribute(conv3x3_zfold_kernel<CIN, EPI>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    configured = true;
+  }
+  conv3x3_zfold_kernel<CIN, EPI><<<grid, 256, S::TOTAL, s>>>(tx, tw, a);
+  EXA_CUDA(cudaGetLastError());
+  return Status::OK();
+}
+
+}  // namespace
+
+bool conv_zfold_supported(const Act& in, int cout) {
+  return !in.fp32 && (in.C == 32 || in.C == 64) && (cout == 32 || cout == 64) &&
+         in.W % 8 == 0 && in.H % 16 == 0 && in.D >= 2;
+}
+
+// w_zfold: bf16 [9 taps (ky,kx)][3 (kz = 2,1,0)][Cout][Cin]
+Status launch_conv_zfold(const Act& in, const Act& out, const __nv_bfloat16* w_zfold,
+                         const float* bias, const HeadParams* head, const ConvRegion* region,
+                         int num_sms, cudaStream_t s) {
+  const int Cin = in.C, Cout = head ? 32 : out.C;
+  EXA_CHECK(conv_zfold_supported(in, Cout), "conv_zfold: unsupported layer shape");
+  ZfArgs a{};
+  a.B = in.B; a.D = in.D; a.H = in.H; a.W = in.W;
+  int x0 = 0, x1 = in.W, y0 = 0, y1 = in.H, z0 = 0, z1 = in.D;
+  if (region) {
+    x0 = region->lo[2]; x1 = region->hi[2];
+    y0 = region->lo[1]; y1 = region->hi[1];
+    z0 = region->lo[0]; z1 = region->hi[0];
+    EXA_CHECK(0 <= x0 && x0 < x1 && x1 <= in.W && 0 <= y0 && y0 < y1 && y1 <= in.H && 0 <= z0 &&
+                  z0 < z1 && z1 <= in.D,
+              "conv_zfold: bad output region");
+  }
+  a.ox = x0; a.oy = y0; a.oz = z0;
+  a.ntx = ceil_div(x1 - x0, 8);
+  a.nty = ceil_div(y1 - y0, 16);
+  a.nzp = z1 - z0;
+  a.n_halves = Cout / 32;
+  a.tiles_total = in.B * a.nty * a.ntx;
+  a.bias = bias;
+  if (head) {
+    EXA_CHECK(Cout == 32, "fused head needs Cout == 32");
+    a.head_w = head->w; a.head_b = head->b; a.head_out = head->out;
+    a.head_c = head->C; a.trim = head->trim; a.apply_sigmoid = head->apply_sigmoid;
+  } else {
+    EXA_CHECK(!out.fp32 && out.B == in.B && out.D == in.D && out.H == in.H && out.W == in.W,
+              "conv_zfold: output shape mismatch");
+    EXA_CHECK((out.cstride % 8) == 0 && (out.coff % 8) == 0, "conv_zfold: output alignment");
+    a.out = (__nv_bfloat16*)out.ptr; a.out_cstride = out.cstride; a.out_coff = out.coff;
+  }
+
+  CUtensorMap tx, tw;
+  {
+    // activations: 5-D (C, W, H, D, B), box = (Cin, 10, 18, 1, 1): the halo tile of one plane
+    const uint64_t cs = (uint64_t)in.cstride * 2;
+    uint64_t dims[5] = {(uint64_t)Cin, (uint64_t)in.W, (uint64_t)in.H, (uint64_t)in.D,
+                        (uint64_t)in.B};
+    uint64_t strides[4] = {cs, cs * in.W, cs * in.W * in.H, cs * in.W * in.H * in.D};
+    uint32_t box[5] = {(uint32_t)Cin, 10, 18, 1, 1};
+    void* base = (void*)((__nv_bfloat16*)in.ptr + in.coff);
+    EXA_TRY(make_tmap_bf16(&tx, base, 5, dims, strides, box, Cin * 2));
+  }
+  {
+    // weights: 4-D (Cin, Cout, 3, 9), box = (Cin, 32, 3, 1): one tap, one 32-channel slice
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Cout, 3, 9};
+    uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)Cin * Cout * 2,
+                           (uint64_t)Cin * Cout * 3 * 2};
+    uint32_t box[4] = {(uint32_t)Cin, 32, 3, 1};
+    EXA_TRY(make_tmap_bf16(&tw, (void*)w_zfold, 4, dims, strides, box, Cin * 2));
+  }
+  int grid = num_sms - num_sms % a.n_halves;
+  if (grid > a.tiles_total * a.n_halves) grid = a.tiles_total * a.n_halves;
+
+  if (Cin == 32) {
+    if (head) return launch_zf<32, EPI_HEAD>(tx, tw, a, grid, s);
+    return launch_zf<32, EPI_STORE>(tx, tw, a, grid, s);
+  }
+  if (head) return launch_zf<64, EPI_HEAD>(tx, tw, a, grid, s);
+  return launch_zf<64, EPI_STORE>(tx, tw, a, grid, s);
+}
+
+}  // namespace exa

@@ -3,6 +3,7 @@
 #include "engine.h"
 
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -148,6 +149,7 @@ Engine::~Engine() {
   for (auto& L : layers_) {
     free_dev(L.w_bf16);
     free_dev(L.w_f32);
+    free_dev(L.w_zfold);
     free_dev(L.bias);
   }
   free_dev(head_w_);
@@ -175,6 +177,8 @@ Status Engine::init() {
   EXA_CHECK(prop.major == 10, "this library is built for sm_100a (B200) only; found sm_" +
                                   std::to_string(prop.major) + std::to_string(prop.minor));
   num_sms_ = prop.multiProcessorCount;
+  const char* nz = getenv("EXA_NO_ZFOLD");
+  use_zfold_ = !(nz && nz[0] == '1');
   return Status::OK();
 }
 
@@ -362,6 +366,8 @@ Status Engine::finalize_weights() {
     free_dev(L.bias);
     free_dev(L.w_bf16);
     free_dev(L.w_f32);
+    free_dev(L.w_zfold);
+    L.w_zfold = nullptr;
     L.bias = nullptr;
     L.w_bf16 = nullptr;
     L.w_f32 = nullptr;
@@ -386,6 +392,18 @@ Status Engine::finalize_weights() {
             pk[((size_t)tap * sp.cout + co) * sp.cin + ci] = f32_to_bf16_rn((float)wsrc(co, ci, tap));
       EXA_CUDA(cudaMalloc(&L.w_bf16, n * 2));
       EXA_CUDA(cudaMemcpy(L.w_bf16, pk.data(), n * 2, cudaMemcpyHostToDevice));
+      if ((sp.cin == 32 || sp.cin == 64) && (sp.cout == 32 || sp.cout == 64)) {
+        // z-folded layout: B operand rows of one in-plane tap are [kz=2 | kz=1 | kz=0] x cout
+        std::vector<uint16_t> zf(n);
+        for (int t9 = 0; t9 < 9; ++t9)
+          for (int kzr = 0; kzr < 3; ++kzr)
+            for (int co = 0; co < sp.cout; ++co)
+              for (int ci = 0; ci < sp.cin; ++ci)
+                zf[(((size_t)t9 * 3 + kzr) * sp.cout + co) * sp.cin + ci] =
+                    pk[((size_t)((2 - kzr) * 9 + t9) * sp.cout + co) * sp.cin + ci];
+        EXA_CUDA(cudaMalloc(&L.w_zfold, n * 2));
+        EXA_CUDA(cudaMemcpy(L.w_zfold, zf.data(), n * 2, cudaMemcpyHostToDevice));
+      }
     } else {
       std::vector<float> pk(n);  // [tap][cin][cout]
       for (int tap = 0; tap < 27; ++tap)
@@ -464,6 +482,8 @@ Status Engine::conv(const ConvLayer& L, const Act& in, const Act& out, const Hea
                     cudaStream_t s) {
   if (precision_ == EXA_PRECISION_BF16) {
     Scope sc(this, CAT_CONV, s);
+    if (use_zfold_ && L.w_zfold && conv_zfold_supported(in, L.cout))
+      return launch_conv_zfold(in, out, L.w_zfold, L.bias, head, nullptr, num_sms_, s);
     return launch_conv_umma(in, out, L.w_bf16, L.bias, head, num_sms_, s);
   }
   {

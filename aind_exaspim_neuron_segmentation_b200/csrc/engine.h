@@ -23,6 +23,7 @@ struct ConvLayer {
   std::string conv_key, bn_key;
   int cin = 0, cout = 0;
   __nv_bfloat16* w_bf16 = nullptr;  // [27][cout][cin]   (tcgen05 path)
+  __nv_bfloat16* w_zfold = nullptr; // [9 (ky,kx)][3 (kz=2,1,0)][cout][cin]  (z-folded path)
   float* w_f32 = nullptr;           // [27][cin][cout]   (fp32 validation path)
   float* bias = nullptr;            // [cout] folded
 };
@@ -89,6 +90,7 @@ class Engine {
     Scope(Engine* eng, int cat, cudaStream_t st);
     ~Scope();
   };
+  bool use_zfold_ = true;  // EXA_NO_ZFOLD=1 selects the plain per-tap kernel everywhere (A/B tests)
   bool prof_on_ = false;
   std::vector<ProfRec> prof_;
 

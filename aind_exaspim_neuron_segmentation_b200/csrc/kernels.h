@@ -69,6 +69,14 @@ struct StitchArgs {
 Status launch_stem(const PatchSource& src, const StemWeights& w, const Act& out, cudaStream_t s);
 Status launch_conv_umma(const Act& in, const Act& out, const __nv_bfloat16* w_packed,
                         const float* bias, const HeadParams* head, int num_sms, cudaStream_t s);
+// Output sub-box [lo, hi) (z, y, x) a conv has to produce; voxels outside are left untouched.
+struct ConvRegion {
+  int lo[3], hi[3];
+};
+bool conv_zfold_supported(const Act& in, int cout);
+Status launch_conv_zfold(const Act& in, const Act& out, const __nv_bfloat16* w_zfold,
+                         const float* bias, const HeadParams* head, const ConvRegion* region,
+                         int num_sms, cudaStream_t s);
 Status launch_conv_fp32(const Act& in, const Act& out, const float* w_packed, const float* bias,
                         cudaStream_t s);
 Status launch_head_fp32(const Act& in, const HeadParams& head, cudaStream_t s);
