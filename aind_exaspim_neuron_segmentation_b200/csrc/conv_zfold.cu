@@ -33,7 +33,7 @@ bool conv_zfold_supported(const Act& in, int cout) {
 // w_zfold: bf16 [9 taps (ky,kx)][3 (kz = 2,1,0)][Cout][Cin]
 Status launch_conv_zfold(const Act& in, const Act& out, const __nv_bfloat16* w_zfold,
                          const float* bias, const HeadParams* head, const ConvRegion* region,
-                         int num_sms, cudaStream_t s) {
+                         const Act* pool_out, int num_sms, cudaStream_t s) {
   const int Cin = in.C, Cout = head ? 32 : out.C;
   EXA_CHECK(conv_zfold_supported(in, Cout), "conv_zfold: unsupported layer shape");
   ZfArgs a{};
@@ -63,6 +63,16 @@ Status launch_conv_zfold(const Act& in, const Act& out, const __nv_bfloat16* w_z
               "conv_zfold: output shape mismatch");
     EXA_CHECK((out.cstride % 8) == 0 && (out.coff % 8) == 0, "conv_zfold: output alignment");
     a.out = (__nv_bfloat16*)out.ptr; a.out_cstride = out.cstride; a.out_coff = out.coff;
+    if (pool_out) {
+      EXA_CHECK(!region, "conv_zfold: fused pool needs the full output region");
+      EXA_CHECK(in.D % 2 == 0 && pool_out->D * 2 == in.D && pool_out->H * 2 == in.H &&
+                    pool_out->W * 2 == in.W && pool_out->B == in.B && pool_out->C == Cout &&
+                    !pool_out->fp32 && pool_out->cstride % 8 == 0 && pool_out->coff % 8 == 0,
+                "conv_zfold: fused pool output shape mismatch");
+      a.pool_out = (__nv_bfloat16*)pool_out->ptr;
+      a.pool_cstride = pool_out->cstride;
+      a.pool_coff = pool_out->coff;
+    }
   }
 
   CUtensorMap tx, tw;

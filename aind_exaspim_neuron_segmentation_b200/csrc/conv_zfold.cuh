@@ -32,6 +32,8 @@ struct ZfArgs {
   const float* bias;         // [Cout] folded BN bias
   __nv_bfloat16* out;        // EPI_STORE: NDHWC bf16 output
   int out_cstride, out_coff;
+  __nv_bfloat16* pool_out;   // optional fused MaxPool3d(2) output (unet3d.py:195), NDHWC at half res
+  int pool_cstride, pool_coff;
   const float* head_w;       // EPI_HEAD: [head_c][32]
   const float* head_b;       // [head_c]
   float* head_out;           // [B][head_c][D-2t][H-2t][W-2t]
@@ -257,6 +259,9 @@ conv3x3_zfold_kernel(const __grid_constant__ CUtensorMap tmap_x,
 #pragma unroll
     for (int j = 0; j < 32; ++j) bias[j] = __ldg(p.bias + n0 + j);
     uint32_t gbase = 0;
+    uint32_t prev[16];  // previous (even) plane, packed bf16x2, for the fused 2x2x2 max-pool
+#pragma unroll
+    for (int j = 0; j < 16; ++j) prev[j] = 0u;
     for (int tile = cta_in_class; tile < p.tiles_total; tile += ctas_per_class) {
       const int b = tile / tiles_per_b;
       const int r = tile - b * tiles_per_b;
@@ -278,17 +283,44 @@ conv3x3_zfold_kernel(const __grid_constant__ CUtensorMap tmap_x,
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = leaky_relu(__uint_as_float(acc[j]) + bias[j]);
         if constexpr (EPI == EPI_STORE) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
           if (in_xy) {
             const size_t vox = (((size_t)b * p.D + po) * p.H + y) * p.W + x;
             uint4* dst = reinterpret_cast<uint4*>(p.out + vox * p.out_cstride + p.out_coff + n0);
 #pragma unroll
-            for (int gq = 0; gq < 4; ++gq) {
-              uint4 o;
-              o.x = pack_bf16x2(v[8 * gq + 0], v[8 * gq + 1]);
-              o.y = pack_bf16x2(v[8 * gq + 2], v[8 * gq + 3]);
-              o.z = pack_bf16x2(v[8 * gq + 4], v[8 * gq + 5]);
-              o.w = pack_bf16x2(v[8 * gq + 6], v[8 * gq + 7]);
-              dst[gq] = o;
+            for (int gq = 0; gq < 4; ++gq)
+              dst[gq] = make_uint4(pk[4 * gq], pk[4 * gq + 1], pk[4 * gq + 2], pk[4 * gq + 3]);
+          }
+          if (p.pool_out != nullptr) {
+            // max over the z pair (this thread), the x pair (lane ^ 1) and the y pair (lane ^ 8);
+            // max commutes with the bf16 rounding, so this equals pooling the stored tensor
+            if (((po - p.oz) & 1) == 0) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) prev[j] = pk[j];
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                __nv_bfloat162 m = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&pk[j]),
+                                           *reinterpret_cast<__nv_bfloat162*>(&prev[j]));
+                uint32_t mu = *reinterpret_cast<uint32_t*>(&m);
+                uint32_t o1 = __shfl_xor_sync(0xffffffffu, mu, 1);
+                m = __hmax2(m, *reinterpret_cast<__nv_bfloat162*>(&o1));
+                mu = *reinterpret_cast<uint32_t*>(&m);
+                uint32_t o8 = __shfl_xor_sync(0xffffffffu, mu, 8);
+                m = __hmax2(m, *reinterpret_cast<__nv_bfloat162*>(&o8));
+                pk[j] = *reinterpret_cast<uint32_t*>(&m);
+              }
+              if (in_xy && (lane & 9) == 0) {
+                const size_t pvox = (((size_t)b * (p.D >> 1) + (po >> 1)) * (p.H >> 1) + (y >> 1)) *
+                                        (p.W >> 1) + (x >> 1);
+                uint4* dst = reinterpret_cast<uint4*>(p.pool_out + pvox * p.pool_cstride +
+                                                      p.pool_coff + n0);
+#pragma unroll
+                for (int gq = 0; gq < 4; ++gq)
+                  dst[gq] = make_uint4(pk[4 * gq], pk[4 * gq + 1], pk[4 * gq + 2], pk[4 * gq + 3]);
+              }
             }
           }
         } else {

@@ -159,6 +159,10 @@ Engine::~Engine() {
   free_dev(probs_);
   free_dev(starts_dev_);
   free_dev(hist_dev_);
+  free_dev(seed_);
+  free_dev(vol_stage_);
+  free_dev(out_stage_);
+  if (copy_stream_) cudaStreamDestroy(copy_stream_);
 }
 
 Status Engine::init() {
@@ -479,12 +483,26 @@ Status Engine::ensure_workspace(int batch, int pz, int py, int px) {
 }
 
 Status Engine::conv(const ConvLayer& L, const Act& in, const Act& out, const HeadParams* head,
-                    cudaStream_t s) {
+                    const ConvRegion* region, const Act* pool_out, cudaStream_t s) {
   if (precision_ == EXA_PRECISION_BF16) {
-    Scope sc(this, CAT_CONV, s);
-    if (use_zfold_ && L.w_zfold && conv_zfold_supported(in, L.cout))
-      return launch_conv_zfold(in, out, L.w_zfold, L.bias, head, nullptr, num_sms_, s);
-    return launch_conv_umma(in, out, L.w_bf16, L.bias, head, num_sms_, s);
+    const bool zf = use_zfold_ && L.w_zfold && conv_zfold_supported(in, L.cout);
+    {
+      Scope sc(this, CAT_CONV, s);
+      if (zf) {
+        // z-folded kernel: optional output sub-box and fused 2x2x2 max-pool
+        const bool fuse_pool = pool_out && in.D % 2 == 0;
+        EXA_TRY(launch_conv_zfold(in, out, L.w_zfold, L.bias, head, region,
+                                  fuse_pool ? pool_out : nullptr, num_sms_, s));
+        if (fuse_pool) return Status::OK();
+      } else {
+        EXA_TRY(launch_conv_umma(in, out, L.w_bf16, L.bias, head, num_sms_, s));
+      }
+    }
+    if (pool_out) {
+      Scope sc(this, CAT_POOL, s);
+      EXA_TRY(launch_maxpool(out, *pool_out, s));
+    }
+    return Status::OK();
   }
   {
     Scope sc(this, CAT_CONV, s);
@@ -493,6 +511,10 @@ Status Engine::conv(const ConvLayer& L, const Act& in, const Act& out, const Hea
   if (head) {
     Scope sc(this, CAT_HEAD, s);
     EXA_TRY(launch_head_fp32(out, *head, s));
+  }
+  if (pool_out) {
+    Scope sc(this, CAT_POOL, s);
+    EXA_TRY(launch_maxpool(out, *pool_out, s));
   }
   return Status::OK();
 }
@@ -539,44 +561,55 @@ Status Engine::run_network(const PatchSource& src, int batch, int pz, int py, in
   // fp32 mode needs a real buffer for the last conv's activations before the head
   const Act u4 = act(L.cat4, 0, 32, 32, 0);  // cat4 is dead once up4.0 has run
 
-  auto pool = [&](const Act& i, const Act& o) {
-    Scope sc(this, CAT_POOL, s);
-    return launch_maxpool(i, o, s);
-  };
-  auto up = [&](const Act& i, const Act& o) {
+  auto up = [&](const Act& i, const Act& o, const ConvRegion* rg) {
     Scope sc(this, CAT_UPSAMPLE, s);
-    return launch_upsample(i, o, s);
+    return launch_upsample(i, o, rg, s);
   };
+  // Only the inner [trim, P-trim) box of the last conv is ever read (inference.py:161-162), so
+  // the last two convs and the last upsample are restricted to that box grown by their
+  // receptive field.  Everything upstream feeds the pooled path and stays full.
+  ConvRegion r_last, r_up40, r_ups;
+  const ConvRegion *p_last = nullptr, *p_up40 = nullptr, *p_ups = nullptr;
+  if (!f32 && head.trim > 0) {
+    const int dims[3] = {pz, py, px};
+    for (int i = 0; i < 3; ++i) {
+      r_last.lo[i] = head.trim;
+      r_last.hi[i] = dims[i] - head.trim;
+      r_up40.lo[i] = std::max(r_last.lo[i] - 1, 0);
+      r_up40.hi[i] = std::min(r_last.hi[i] + 1, dims[i]);
+      r_ups.lo[i] = std::max(r_up40.lo[i] - 1, 0);
+      r_ups.hi[i] = std::min(r_up40.hi[i] + 1, dims[i]);
+    }
+    p_last = &r_last;
+    p_up40 = &r_up40;
+    p_ups = &r_ups;
+  }
 
   {
     Scope sc(this, CAT_STEM, s);
     EXA_TRY(launch_stem(src, stem_, a0, s));                // inc.0 (+gather/normalise)
   }
-  EXA_TRY(conv(layers_[1], a0, x1, nullptr, s));            // inc.3 -> skip slot of CAT4
-  EXA_TRY(pool(x1, p1));
-  EXA_TRY(conv(layers_[2], p1, d1a, nullptr, s));
-  EXA_TRY(conv(layers_[3], d1a, x2, nullptr, s));
-  EXA_TRY(pool(x2, p2));
-  EXA_TRY(conv(layers_[4], p2, d2a, nullptr, s));
-  EXA_TRY(conv(layers_[5], d2a, x3, nullptr, s));
-  EXA_TRY(pool(x3, p3));
-  EXA_TRY(conv(layers_[6], p3, d3a, nullptr, s));
-  EXA_TRY(conv(layers_[7], d3a, x4, nullptr, s));
-  EXA_TRY(pool(x4, p4));
-  EXA_TRY(conv(layers_[8], p4, d4a, nullptr, s));
-  EXA_TRY(conv(layers_[9], d4a, x5, nullptr, s));
-  EXA_TRY(up(x5, up1_slot));                                // cat([x4, up(x5)])  unet3d.py:288
-  EXA_TRY(conv(layers_[10], cat1, u1a, nullptr, s));
-  EXA_TRY(conv(layers_[11], u1a, u1, nullptr, s));
-  EXA_TRY(up(u1, up2_slot));
-  EXA_TRY(conv(layers_[12], cat2, u2a, nullptr, s));
-  EXA_TRY(conv(layers_[13], u2a, u2, nullptr, s));
-  EXA_TRY(up(u2, up3_slot));
-  EXA_TRY(conv(layers_[14], cat3, u3a, nullptr, s));
-  EXA_TRY(conv(layers_[15], u3a, u3, nullptr, s));
-  EXA_TRY(up(u3, up4_slot));
-  EXA_TRY(conv(layers_[16], cat4, u4a, nullptr, s));
-  EXA_TRY(conv(layers_[17], u4a, u4, &head, s));            // + 1x1x1 head (+sigmoid, trim)
+  EXA_TRY(conv(layers_[1], a0, x1, nullptr, nullptr, &p1, s));   // inc.3 -> skip slot of CAT4 (+pool)
+  EXA_TRY(conv(layers_[2], p1, d1a, nullptr, nullptr, nullptr, s));
+  EXA_TRY(conv(layers_[3], d1a, x2, nullptr, nullptr, &p2, s));
+  EXA_TRY(conv(layers_[4], p2, d2a, nullptr, nullptr, nullptr, s));
+  EXA_TRY(conv(layers_[5], d2a, x3, nullptr, nullptr, &p3, s));
+  EXA_TRY(conv(layers_[6], p3, d3a, nullptr, nullptr, nullptr, s));
+  EXA_TRY(conv(layers_[7], d3a, x4, nullptr, nullptr, &p4, s));
+  EXA_TRY(conv(layers_[8], p4, d4a, nullptr, nullptr, nullptr, s));
+  EXA_TRY(conv(layers_[9], d4a, x5, nullptr, nullptr, nullptr, s));
+  EXA_TRY(up(x5, up1_slot, nullptr));                       // cat([x4, up(x5)])  unet3d.py:288
+  EXA_TRY(conv(layers_[10], cat1, u1a, nullptr, nullptr, nullptr, s));
+  EXA_TRY(conv(layers_[11], u1a, u1, nullptr, nullptr, nullptr, s));
+  EXA_TRY(up(u1, up2_slot, nullptr));
+  EXA_TRY(conv(layers_[12], cat2, u2a, nullptr, nullptr, nullptr, s));
+  EXA_TRY(conv(layers_[13], u2a, u2, nullptr, nullptr, nullptr, s));
+  EXA_TRY(up(u2, up3_slot, nullptr));
+  EXA_TRY(conv(layers_[14], cat3, u3a, nullptr, nullptr, nullptr, s));
+  EXA_TRY(conv(layers_[15], u3a, u3, nullptr, nullptr, nullptr, s));
+  EXA_TRY(up(u3, up4_slot, p_ups));
+  EXA_TRY(conv(layers_[16], cat4, u4a, nullptr, p_up40, nullptr, s));
+  EXA_TRY(conv(layers_[17], u4a, u4, &head, p_last, nullptr, s));  // + 1x1x1 head, sigmoid, trim
   return Status::OK();
 }
 
@@ -667,7 +700,8 @@ Status Engine::slab_run(const uint16_t* slab_dev, int D, int H, int W, const exa
     probs_bytes_ = need;
   }
   // patch starts of this slab in the reference's order (inference.py:394-397)
-  std::vector<int> starts((size_t)n_slab * 3);
+  std::vector<int>& starts = starts_host_;  // member: must outlive the async copy below
+  starts.resize((size_t)n_slab * 3);
   {
     size_t i = 0;
     for (int kz = row_begin; kz < row_end; ++kz)
@@ -687,7 +721,7 @@ Status Engine::slab_run(const uint16_t* slab_dev, int D, int H, int W, const exa
   }
   EXA_CUDA(cudaMemcpyAsync(starts_dev_, starts.data(), starts.size() * sizeof(int),
                            cudaMemcpyHostToDevice, s));
-  EXA_CUDA(cudaStreamSynchronize(s));  // `starts` is a stack-lifetime host buffer
+  // (pageable source: the runtime stages the data before cudaMemcpyAsync returns)
 
   int batch = p.batch > 0 ? p.batch : 32;
   batch = std::min(batch, n_slab);
@@ -750,12 +784,21 @@ Status Engine::slab_stitch(const float* seed_dev, float* out_dev, cudaStream_t s
   EXA_CHECK(job_ready_, "slab_stitch: no slab job (call exa_slab_run first)");
   const int nz = slab_.out_z1 - slab_.out_z0;
   if (nz <= 0) return Status::OK();
+  return stitch_planes(seed_dev, out_dev, (size_t)nz * plan_.H * plan_.W, slab_.out_z0,
+                       slab_.out_z1, s);
+}
+
+// finished planes [z0, z1) of the current slab job -> out (plane z0 first), channel stride given
+Status Engine::stitch_planes(const float* seed_dev, float* out_dev, size_t out_cstride, int z0,
+                             int z1, cudaStream_t s) {
+  EXA_CHECK(job_ready_, "stitch: no slab job");
+  if (z1 <= z0) return Status::OK();
   EXA_CHECK(out_dev != nullptr, "slab_stitch: null buffer");
   StitchArgs a = stitch_base(plan_, probs_, out_channels_, row_begin_, row_end_);
-  a.z_begin = slab_.out_z0;
-  a.z_end = slab_.out_z1;
+  a.z_begin = z0;
+  a.z_end = z1;
   a.out = out_dev;
-  a.out_cstride = (size_t)nz * plan_.H * plan_.W;
+  a.out_cstride = out_cstride;
   a.finalize = 1;
   if (seed_dev != nullptr && slab_.seed_z1 > slab_.seed_z0) {
     a.seed = seed_dev;
@@ -766,15 +809,19 @@ Status Engine::slab_stitch(const float* seed_dev, float* out_dev, cudaStream_t s
   return launch_stitch(a, s);
 }
 
-Status Engine::predict_device(const uint16_t* vol_dev, int D, int H, int W,
-                              const exa_predict_params& p, float* out_dev, cudaStream_t s) {
-  EXA_CUDA(cudaSetDevice(device_));
-  EXA_CHECK(vol_dev && out_dev, "predict: null buffer");
+// Whole volume in groups of z patch-rows.  Each group is a slab job: run its patches, stitch the
+// planes it owns (seeded with the previous group's partial sums for the shared planes, so the
+// fp32 summation order is the reference's), hand partial sums to the next group.  Finished
+// planes are copied to the host on a second stream while the next group computes.
+Status Engine::predict_pipeline(const uint16_t* vol_dev, int D, int H, int W,
+                                const exa_predict_params& p, float* out_dev, float* out_host,
+                                cudaStream_t s) {
   Plan plan;
   EXA_TRY(make_plan(D, H, W, p, &plan));
   const int bins = p.brightness_clip + 1;
+  const size_t plane = (size_t)H * W, nvox = plane * D;
   if (!hist_dev_) EXA_CUDA(cudaMalloc(&hist_dev_, sizeof(unsigned long long) * 65536));
-  EXA_TRY(histogram(vol_dev, (int64_t)D * H * W, p.brightness_clip, (uint64_t*)hist_dev_, s));
+  EXA_TRY(histogram(vol_dev, (int64_t)nvox, p.brightness_clip, (uint64_t*)hist_dev_, s));
   std::vector<uint64_t> hist(bins);
   EXA_CUDA(cudaMemcpyAsync(hist.data(), hist_dev_, sizeof(uint64_t) * bins, cudaMemcpyDeviceToHost,
                            s));
@@ -782,12 +829,74 @@ Status Engine::predict_device(const uint16_t* vol_dev, int D, int H, int W,
   double mn = 0, mx = 0;
   EXA_TRY(percentiles_from_hist(hist.data(), bins, p.pct_lo, p.pct_hi, &mn, &mx));
   EXA_TRY(set_normalization(mn, mx, p.brightness_clip));
-  EXA_TRY(slab_run(vol_dev, D, H, W, p, 0, plan.az.n, s));
   if (plan.n_patches == 0) {  // volume smaller than one stride: the reference returns zeros
-    EXA_CUDA(cudaMemsetAsync(out_dev, 0, sizeof(float) * out_channels_ * (size_t)D * H * W, s));
+    EXA_CUDA(cudaMemsetAsync(out_dev, 0, sizeof(float) * out_channels_ * nvox, s));
+    if (out_host) {
+      EXA_CUDA(cudaMemcpyAsync(out_host, out_dev, sizeof(float) * out_channels_ * nvox,
+                               cudaMemcpyDeviceToHost, s));
+    }
     return Status::OK();
   }
-  return slab_stitch(nullptr, out_dev, s);
+  // group size: at least one wave of patches per group; a single group when planes can be
+  // covered by more than two rows (no pairwise hand-over possible)
+  const int per_row = plan.ay.n * plan.ax.n;
+  const int batch = p.batch > 0 ? p.batch : 32;
+  int rows_per_group = std::max(1, ceil_div(batch, per_row));
+  const int keep = plan.az.patch - 2 * plan.az.trim;
+  if (keep > 2 * plan.az.stride) rows_per_group = plan.az.n;
+  if (out_host && !copy_stream_) {
+    EXA_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+  }
+  const size_t seed_elems = (size_t)out_channels_ * keep * plane;  // upper bound on shared planes
+  if (rows_per_group < plan.az.n && seed_elems * sizeof(float) > seed_bytes_) {
+    free_dev(seed_);
+    seed_ = nullptr;
+    seed_bytes_ = 0;
+    EXA_CUDA(cudaMalloc(&seed_, seed_elems * sizeof(float)));
+    seed_bytes_ = seed_elems * sizeof(float);
+  }
+  std::vector<cudaEvent_t> events;
+  Status st = Status::OK();
+  bool have_seed = false;
+  for (int r0 = 0; r0 < plan.az.n && st.ok; r0 += rows_per_group) {
+    const int r1 = std::min(r0 + rows_per_group, plan.az.n);
+    st = slab_run(vol_dev + (size_t)(r0 * plan.az.stride) * plane, D, H, W, p, r0, r1, s);
+    if (!st.ok) break;
+    const int z0 = slab_.out_z0, z1 = slab_.out_z1;
+    st = stitch_planes(have_seed ? seed_ : nullptr, out_dev + (size_t)z0 * plane, nvox, z0, z1, s);
+    if (!st.ok) break;
+    have_seed = slab_.halo_z1 > slab_.halo_z0;
+    if (have_seed) {
+      st = slab_partial(seed_, s);  // after the stitch above has consumed the previous seed
+      if (!st.ok) break;
+    }
+    if (out_host && z1 > z0) {
+      cudaEvent_t ev;
+      EXA_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      events.push_back(ev);
+      EXA_CUDA(cudaEventRecord(ev, s));
+      EXA_CUDA(cudaStreamWaitEvent(copy_stream_, ev, 0));
+      for (int c = 0; c < out_channels_; ++c) {
+        const size_t off = (size_t)c * nvox + (size_t)z0 * plane;
+        EXA_CUDA(cudaMemcpyAsync(out_host + off, out_dev + off, (size_t)(z1 - z0) * plane * 4,
+                                 cudaMemcpyDeviceToHost, copy_stream_));
+      }
+    }
+  }
+  if (out_host) {
+    cudaError_t e = cudaStreamSynchronize(copy_stream_);
+    if (e != cudaSuccess && st.ok)
+      st = Status::Err(std::string("predict: D2H failed: ") + cudaGetErrorString(e));
+  }
+  for (cudaEvent_t ev : events) cudaEventDestroy(ev);
+  return st;
+}
+
+Status Engine::predict_device(const uint16_t* vol_dev, int D, int H, int W,
+                              const exa_predict_params& p, float* out_dev, cudaStream_t s) {
+  EXA_CUDA(cudaSetDevice(device_));
+  EXA_CHECK(vol_dev && out_dev, "predict: null buffer");
+  return predict_pipeline(vol_dev, D, H, W, p, out_dev, nullptr, s);
 }
 
 Status Engine::predict_host(const uint16_t* vol, int D, int H, int W, const exa_predict_params& p,
@@ -798,31 +907,26 @@ Status Engine::predict_host(const uint16_t* vol, int D, int H, int W, const exa_
   EXA_TRY(check_params(p));
   EXA_CHECK(D > 0 && H > 0 && W > 0, "volume dims must be positive");
   const size_t nvox = (size_t)D * H * W;
-  uint16_t* vol_dev = nullptr;
-  float* out_dev = nullptr;
-  Status st = Status::OK();
+  // device staging buffers are kept between calls (re-allocated only when they must grow)
+  if (nvox * 2 + 16 > vol_stage_bytes_) {
+    free_dev(vol_stage_);
+    vol_stage_ = nullptr;
+    vol_stage_bytes_ = 0;
+    EXA_CUDA(cudaMalloc(&vol_stage_, nvox * 2 + 16));
+    vol_stage_bytes_ = nvox * 2 + 16;
+  }
+  if (nvox * 4 * out_channels_ > out_stage_bytes_) {
+    free_dev(out_stage_);
+    out_stage_ = nullptr;
+    out_stage_bytes_ = 0;
+    EXA_CUDA(cudaMalloc(&out_stage_, nvox * 4 * out_channels_));
+    out_stage_bytes_ = nvox * 4 * out_channels_;
+  }
   cudaStream_t s = nullptr;
-  do {
-    if (cudaMalloc(&vol_dev, nvox * 2 + 16) != cudaSuccess ||
-        cudaMalloc(&out_dev, nvox * 4 * out_channels_) != cudaSuccess) {
-      st = Status::Err(std::string("predict: device allocation failed: ") +
-                       cudaGetErrorString(cudaGetLastError()));
-      break;
-    }
-    if (cudaMemcpyAsync(vol_dev, vol, nvox * 2, cudaMemcpyHostToDevice, s) != cudaSuccess) {
-      st = Status::Err("predict: H2D copy failed");
-      break;
-    }
-    st = predict_device(vol_dev, D, H, W, p, out_dev, s);
-    if (!st.ok) break;
-    cudaError_t e =
-        cudaMemcpyAsync(out, out_dev, nvox * 4 * out_channels_, cudaMemcpyDeviceToHost, s);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-    if (e != cudaSuccess) st = Status::Err(std::string("predict: D2H failed: ") + cudaGetErrorString(e));
-  } while (0);
-  free_dev(vol_dev);
-  free_dev(out_dev);
-  return st;
+  EXA_CUDA(cudaMemcpyAsync(vol_stage_, vol, nvox * 2, cudaMemcpyHostToDevice, s));
+  EXA_TRY(predict_pipeline((const uint16_t*)vol_stage_, D, H, W, p, (float*)out_stage_, out, s));
+  EXA_CUDA(cudaStreamSynchronize(s));
+  return Status::OK();
 }
 
 }  // namespace exa

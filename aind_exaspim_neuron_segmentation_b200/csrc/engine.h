@@ -74,10 +74,14 @@ class Engine {
 
  private:
   Status ensure_workspace(int batch, int pz, int py, int px);
+  Status predict_pipeline(const uint16_t* vol_dev, int D, int H, int W, const exa_predict_params& p,
+                          float* out_dev, float* out_host, cudaStream_t s);
+  Status stitch_planes(const float* seed_dev, float* out_dev, size_t out_cstride, int z0, int z1,
+                       cudaStream_t s);
   Status run_network(const PatchSource& src, int batch, int pz, int py, int px,
                      const HeadParams& head, cudaStream_t s);
   Status conv(const ConvLayer& L, const Act& in, const Act& out, const HeadParams* head,
-              cudaStream_t s);
+              const ConvRegion* region, const Act* pool_out, cudaStream_t s);
 
   struct ProfRec {
     int cat;
@@ -119,9 +123,18 @@ class Engine {
   bool job_ready_ = false;
   float* probs_ = nullptr;
   size_t probs_bytes_ = 0;
+  std::vector<int> starts_host_;
   int* starts_dev_ = nullptr;
   size_t starts_cap_ = 0;
   unsigned long long* hist_dev_ = nullptr;
+  // row-group pipeline (predict_pipeline)
+  float* seed_ = nullptr;
+  size_t seed_bytes_ = 0;
+  void* vol_stage_ = nullptr;
+  size_t vol_stage_bytes_ = 0;
+  void* out_stage_ = nullptr;
+  size_t out_stage_bytes_ = 0;
+  cudaStream_t copy_stream_ = nullptr;
 };
 
 }  // namespace exa

@@ -76,12 +76,13 @@ struct ConvRegion {
 bool conv_zfold_supported(const Act& in, int cout);
 Status launch_conv_zfold(const Act& in, const Act& out, const __nv_bfloat16* w_zfold,
                          const float* bias, const HeadParams* head, const ConvRegion* region,
-                         int num_sms, cudaStream_t s);
+                         const Act* pool_out, int num_sms, cudaStream_t s);
 Status launch_conv_fp32(const Act& in, const Act& out, const float* w_packed, const float* bias,
                         cudaStream_t s);
 Status launch_head_fp32(const Act& in, const HeadParams& head, cudaStream_t s);
 Status launch_maxpool(const Act& in, const Act& out, cudaStream_t s);
-Status launch_upsample(const Act& in, const Act& out, cudaStream_t s);
+// region (optional): only output voxels inside the box are produced
+Status launch_upsample(const Act& in, const Act& out, const ConvRegion* region, cudaStream_t s);
 Status launch_histogram(const uint16_t* vol, size_t n, int clip, unsigned long long* hist,
                         cudaStream_t s);
 Status launch_stitch(const StitchArgs& a, cudaStream_t s);

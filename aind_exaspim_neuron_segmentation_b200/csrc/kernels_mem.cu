@@ -255,18 +255,16 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 maxpool_kernel(const T* __restrict__ in, int in_cstride, int in_coff, T* __restrict__ out,
                int out_cstride, int out_coff, int B, int Do, int Ho, int Wo, int C) {
-  const int cv = C / 8;
-  const size_t total = (size_t)B * Do * Ho * Wo * cv;
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
+  // grid: x covers (yo, xo, c8) of one output plane, y = zo, z = b -> 32-bit index math only
+  const unsigned cv = (unsigned)C / 8;
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (unsigned)Ho * Wo * cv) return;
   const int c8 = (int)(i % cv);
-  size_t v = i / cv;
-  const int xo = (int)(v % Wo);
-  v /= Wo;
-  const int yo = (int)(v % Ho);
-  v /= Ho;
-  const int zo = (int)(v % Do);
-  const int b = (int)(v / Do);
+  const unsigned v = i / cv;
+  const int xo = (int)(v % (unsigned)Wo);
+  const int yo = (int)(v / (unsigned)Wo);
+  const int zo = blockIdx.y;
+  const int b = blockIdx.z;
   const int Di = 2 * Do, Hi = 2 * Ho, Wi = 2 * Wo;
   float m[8];
 #pragma unroll
@@ -295,8 +293,9 @@ Status launch_maxpool(const Act& in, const Act& out, cudaStream_t s) {
   EXA_CHECK(in.fp32 == out.fp32 && in.C == out.C && in.C % 8 == 0, "maxpool: type/channel mismatch");
   EXA_CHECK(in.D == 2 * out.D && in.H == 2 * out.H && in.W == 2 * out.W && in.B == out.B,
             "maxpool: shape mismatch");
-  const size_t total = out.voxels() * (out.C / 8);
-  const int blocks = (int)ceil_div64((int64_t)total, 256);
+  EXA_CHECK(out.B <= 65535 && out.D <= 65535, "maxpool: batch/depth too large for the grid");
+  const dim3 blocks((unsigned)ceil_div(out.H * out.W * (out.C / 8), 256), (unsigned)out.D,
+                    (unsigned)out.B);
   if (in.fp32)
     maxpool_kernel<float><<<blocks, 256, 0, s>>>((const float*)in.ptr, in.cstride, in.coff,
                                                   (float*)out.ptr, out.cstride, out.coff, out.B,
@@ -315,20 +314,21 @@ Status launch_maxpool(const Act& in, const Act& out, cudaStream_t s) {
 template <typename T>
 __global__ void __launch_bounds__(256)
 upsample_kernel(const T* __restrict__ in, int in_cstride, int in_coff, T* __restrict__ out,
-                int out_cstride, int out_coff, int B, int Di, int Hi, int Wi, int C) {
+                int out_cstride, int out_coff, int B, int Di, int Hi, int Wi, int C,
+                const ConvRegion rg) {
   const int Do = 2 * Di, Ho = 2 * Hi, Wo = 2 * Wi;
-  const int cv = C / 8;
-  const size_t total = (size_t)B * Do * Ho * Wo * cv;
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
+  // grid: x covers (yo, xo, c8) of one plane of the output region, y = zo, z = b
+  // -> 32-bit index math only
+  const unsigned cv = (unsigned)C / 8;
+  const unsigned rw = (unsigned)(rg.hi[2] - rg.lo[2]), rh = (unsigned)(rg.hi[1] - rg.lo[1]);
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rh * rw * cv) return;
   const int c8 = (int)(i % cv);
-  size_t v = i / cv;
-  const int xo = (int)(v % Wo);
-  v /= Wo;
-  const int yo = (int)(v % Ho);
-  v /= Ho;
-  const int zo = (int)(v % Do);
-  const int b = (int)(v / Do);
+  const unsigned v = i / cv;
+  const int xo = rg.lo[2] + (int)(v % rw);
+  const int yo = rg.lo[1] + (int)(v / rw);
+  const int zo = rg.lo[0] + blockIdx.y;
+  const int b = blockIdx.z;
   // src = dst * (in-1)/(out-1), computed in fp32 like ATen's area_pixel_compute_source_index
   const float sz = (Do > 1) ? (float)(Di - 1) / (float)(Do - 1) : 0.f;
   const float sy = (Ho > 1) ? (float)(Hi - 1) / (float)(Ho - 1) : 0.f;
@@ -365,20 +365,158 @@ upsample_kernel(const T* __restrict__ in, int in_cstride, int in_coff, T* __rest
   o.store(out + ovox * out_cstride + out_coff + 8 * c8);
 }
 
-Status launch_upsample(const Act& in, const Act& out, cudaStream_t s) {
+// bf16 fast path: one thread produces a 2x2x2 output block for 8 channels from the 3x3x3 input
+// window [j-1, j+1] (clamped), separably: 27 vector loads per 8 outputs instead of 64.
+// Per axis, output o has taps (i0, i1) with weights (1-l, l), l = o*(n-1)/(2n-1) - i0, expressed
+// as 3 coefficients over the window so that the two outputs of a block share the loads.
+struct AxisTaps {
+  int w[3];        // window indices (clamped)
+  float ca[3];     // coefficients of output 2j
+  float cb[3];     // coefficients of output 2j+1
+};
+__device__ __forceinline__ AxisTaps axis_taps(int j, int n) {
+  AxisTaps t;
+  const int w0 = max(j - 1, 0);
+  t.w[0] = w0;
+  t.w[1] = min(w0 + 1, n - 1);
+  t.w[2] = min(w0 + 2, n - 1);
+  const float scale = (2 * n > 1) ? (float)(n - 1) / (float)(2 * n - 1) : 0.f;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const float src = scale * (float)(2 * j + h);
+    const int i0 = (int)src;
+    const int i1 = i0 + (i0 < n - 1 ? 1 : 0);
+    const float l1 = src - (float)i0, l0 = 1.f - l1;
+    float* c = h == 0 ? t.ca : t.cb;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) c[k] = (k == i0 - w0 ? l0 : 0.f) + (k == i1 - w0 ? l1 : 0.f);
+  }
+  return t;
+}
+
+__global__ void __launch_bounds__(128)
+upsample2_bf16_kernel(const __nv_bfloat16* __restrict__ in, int in_cstride, int in_coff,
+                      __nv_bfloat16* __restrict__ out, int out_cstride, int out_coff, int Di, int Hi,
+                      int Wi, int C, const ConvRegion rg, int jz0, int jy0, int jx0, int njy,
+                      int njx) {
+  const unsigned cv = (unsigned)C / 8;
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (unsigned)njy * njx * cv) return;
+  const int c8 = (int)(i % cv);
+  const unsigned v = i / cv;
+  const int xj = jx0 + (int)(v % (unsigned)njx);
+  const int yj = jy0 + (int)(v / (unsigned)njx);
+  const int zj = jz0 + blockIdx.y;
+  const int b = blockIdx.z;
+  const AxisTaps tz = axis_taps(zj, Di), ty = axis_taps(yj, Hi), tx = axis_taps(xj, Wi);
+
+  float acc[2][2][2][8];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int bb = 0; bb < 2; ++bb)
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[a][bb][c][j] = 0.f;
+
+  const __nv_bfloat16* base = in + in_coff + 8 * c8;
+#pragma unroll
+  for (int dz = 0; dz < 3; ++dz) {
+    float py[2][2][8];  // [y out][x out]
+#pragma unroll
+    for (int bb = 0; bb < 2; ++bb)
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) py[bb][c][j] = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const size_t rowv = (((size_t)b * Di + tz.w[dz]) * Hi + ty.w[dy]) * Wi;
+      float pxa[8], pxb[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) pxa[j] = pxb[j] = 0.f;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        Vec8<__nv_bfloat16> q;
+        q.load(base + (rowv + tx.w[dx]) * in_cstride);
+        float f[8];
+        q.to_float(f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          pxa[j] = fmaf(tx.ca[dx], f[j], pxa[j]);
+          pxb[j] = fmaf(tx.cb[dx], f[j], pxb[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        py[0][0][j] = fmaf(ty.ca[dy], pxa[j], py[0][0][j]);
+        py[0][1][j] = fmaf(ty.ca[dy], pxb[j], py[0][1][j]);
+        py[1][0][j] = fmaf(ty.cb[dy], pxa[j], py[1][0][j]);
+        py[1][1][j] = fmaf(ty.cb[dy], pxb[j], py[1][1][j]);
+      }
+    }
+#pragma unroll
+    for (int bb = 0; bb < 2; ++bb)
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[0][bb][c][j] = fmaf(tz.ca[dz], py[bb][c][j], acc[0][bb][c][j]);
+          acc[1][bb][c][j] = fmaf(tz.cb[dz], py[bb][c][j], acc[1][bb][c][j]);
+        }
+  }
+  const int Ho = 2 * Hi, Wo = 2 * Wi, Do = 2 * Di;
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int bb = 0; bb < 2; ++bb)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int zo = 2 * zj + a, yo = 2 * yj + bb, xo = 2 * xj + c;
+        if (zo >= rg.lo[0] && zo < rg.hi[0] && yo >= rg.lo[1] && yo < rg.hi[1] && xo >= rg.lo[2] &&
+            xo < rg.hi[2]) {
+          const size_t ovox = (((size_t)b * Do + zo) * Ho + yo) * Wo + xo;
+          Vec8<__nv_bfloat16> o;
+          o.from_float(acc[a][bb][c]);
+          o.store(out + ovox * out_cstride + out_coff + 8 * c8);
+        }
+      }
+}
+
+Status launch_upsample(const Act& in, const Act& out, const ConvRegion* region, cudaStream_t s) {
   EXA_CHECK(in.fp32 == out.fp32 && in.C == out.C && in.C % 8 == 0, "upsample: type/channel mismatch");
   EXA_CHECK(out.D == 2 * in.D && out.H == 2 * in.H && out.W == 2 * in.W && in.B == out.B,
             "upsample: shape mismatch");
-  const size_t total = out.voxels() * (out.C / 8);
-  const int blocks = (int)ceil_div64((int64_t)total, 256);
-  if (in.fp32)
+  EXA_CHECK(out.B <= 65535 && out.D <= 65535, "upsample: batch/depth too large for the grid");
+  ConvRegion rg;
+  rg.lo[0] = rg.lo[1] = rg.lo[2] = 0;
+  rg.hi[0] = out.D; rg.hi[1] = out.H; rg.hi[2] = out.W;
+  if (region) {
+    rg = *region;
+    EXA_CHECK(rg.lo[0] >= 0 && rg.lo[1] >= 0 && rg.lo[2] >= 0 && rg.hi[0] <= out.D &&
+                  rg.hi[1] <= out.H && rg.hi[2] <= out.W && rg.lo[0] < rg.hi[0] &&
+                  rg.lo[1] < rg.hi[1] && rg.lo[2] < rg.hi[2],
+              "upsample: bad output region");
+  }
+  const dim3 blocks(
+      (unsigned)ceil_div((rg.hi[1] - rg.lo[1]) * (rg.hi[2] - rg.lo[2]) * (out.C / 8), 256),
+      (unsigned)(rg.hi[0] - rg.lo[0]), (unsigned)out.B);
+  if (in.fp32) {
     upsample_kernel<float><<<blocks, 256, 0, s>>>((const float*)in.ptr, in.cstride, in.coff,
                                                    (float*)out.ptr, out.cstride, out.coff, in.B,
-                                                   in.D, in.H, in.W, in.C);
-  else
-    upsample_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(
+                                                   in.D, in.H, in.W, in.C, rg);
+  } else {
+    // 2x2x2 output blocks: block index ranges covering the region
+    const int jz0 = rg.lo[0] / 2, jy0 = rg.lo[1] / 2, jx0 = rg.lo[2] / 2;
+    const int njz = (rg.hi[0] + 1) / 2 - jz0, njy = (rg.hi[1] + 1) / 2 - jy0,
+              njx = (rg.hi[2] + 1) / 2 - jx0;
+    const dim3 blocks2((unsigned)ceil_div(njy * njx * (out.C / 8), 128), (unsigned)njz,
+                       (unsigned)out.B);
+    upsample2_bf16_kernel<<<blocks2, 128, 0, s>>>(
         (const __nv_bfloat16*)in.ptr, in.cstride, in.coff, (__nv_bfloat16*)out.ptr, out.cstride,
-        out.coff, in.B, in.D, in.H, in.W, in.C);
+        out.coff, in.D, in.H, in.W, in.C, rg, jz0, jy0, jx0, njy, njx);
+  }
   EXA_CUDA(cudaGetLastError());
   return Status::OK();
 }
@@ -451,13 +589,12 @@ __device__ __forceinline__ void cover_range(const AxisGeom& g, int p, int& k_lo,
 __global__ void __launch_bounds__(256)
 stitch_kernel(const StitchArgs a) {
   const int H = a.ay.dim, W = a.ax.dim;
-  const int nz = a.z_end - a.z_begin;
-  const size_t total = (size_t)nz * H * W;
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int x = (int)(i % W);
-  const int y = (int)((i / W) % H);
-  const int zl = (int)(i / ((size_t)W * H));
+  // grid: x covers one (y, x) plane, y = plane index -> 32-bit index math only
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (unsigned)H * W) return;
+  const int x = (int)(i % (unsigned)W);
+  const int y = (int)(i / (unsigned)W);
+  const int zl = blockIdx.y;
   const int z = a.z_begin + zl;
 
   int kz0, kz1, ky0, ky1, kx0, kx1;
@@ -495,9 +632,10 @@ stitch_kernel(const StitchArgs a) {
 }
 
 Status launch_stitch(const StitchArgs& a, cudaStream_t s) {
-  const size_t total = (size_t)(a.z_end - a.z_begin) * a.ay.dim * a.ax.dim;
-  if (total == 0) return Status::OK();
-  const int blocks = (int)ceil_div64((int64_t)total, 256);
+  const int nz = a.z_end - a.z_begin;
+  if (nz <= 0 || a.ay.dim <= 0 || a.ax.dim <= 0) return Status::OK();
+  EXA_CHECK(nz <= 65535, "stitch: too many planes for one launch");
+  const dim3 blocks((unsigned)ceil_div64((int64_t)a.ay.dim * a.ax.dim, 256), (unsigned)nz);
   stitch_kernel<<<blocks, 256, 0, s>>>(a);
   EXA_CUDA(cudaGetLastError());
   return Status::OK();

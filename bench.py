@@ -40,7 +40,13 @@ TRIM = 8
 F_PATCH_96 = 370_145_230_848          # 2*MACs of the 19 convs per 96^3 patch
 F_STEM_96 = 2 * 96 ** 3 * 32 * 27     # inc.double_conv.0 (SIMT stem kernel)
 F_HEAD_96 = 2 * 96 ** 3 * 3 * 32      # outc (fused into the last conv's epilogue)
-F_CONV_96 = F_PATCH_96 - F_STEM_96 - F_HEAD_96  # executed by the tcgen05 conv kernels
+# Work skipped because its results are trimmed away (inference.py:161-162): the last conv is
+# evaluated on the kept 80^3 box only and up4.0 on that box grown by one voxel (82^3).  Only
+# EXECUTED MACs are counted (no tile padding).
+F_UP40_FULL = 2 * 96 ** 3 * 32 * 27 * 64
+F_UP43_FULL = 2 * 96 ** 3 * 32 * 27 * 32
+F_TRIM_SAVED = (F_UP40_FULL - 2 * 82 ** 3 * 32 * 27 * 64) + (F_UP43_FULL - 2 * 80 ** 3 * 32 * 27 * 32)
+F_CONV_96 = F_PATCH_96 - F_STEM_96 - F_HEAD_96 - F_TRIM_SAVED  # executed by the tcgen05 convs
 
 
 def volume_shape(n_gpus):
@@ -271,7 +277,14 @@ def run_b200(args):
     def step_device():
         return job.run(slab, gather=True)
 
+    from aind_exaspim_neuron_segmentation_b200 import predict
+
     def step_e2e():
+        if n == 1:
+            # the public call a user makes: host uint16 volume in, host float32 affinities out
+            # (pinned buffers; H2D, all kernels and the row-pipelined D2H inside the call)
+            return predict(host.numpy(), model, verbose=False, patch_shape=PATCH, overlap=OVERLAP,
+                           trim=TRIM, batch_size=args.batch, out=host_out.numpy())
         s = host.to(dev, non_blocking=True)
         own = job.run(s, gather=False)
         host_out.copy_(own, non_blocking=True)
@@ -344,7 +357,9 @@ def run_b200(args):
             "e2e": {"value": voxels / (e2e_ms * 1e-3), "unit": "voxels/s",
                     "h2d_bytes_per_step": int(h2d.item()), "d2h_bytes_per_step": int(d2h.item()),
                     "ms_per_step": e2e_ms,
-                    "note": "pinned uint16 slab H2D + owned fp32 planes D2H per step, every rank"},
+                    "note": ("predict(host uint16, out=pinned float32): H2D + kernels + row-pipelined D2H"
+                             if n == 1 else
+                             "pinned uint16 slab H2D + owned fp32 planes D2H per step, every rank")},
             "gpu_launches": int(launches),
             "roofline": {
                 "kernel": "conv3x3_umma_kernel (17 launches per wave of patches; rank 0)",
@@ -352,7 +367,7 @@ def run_b200(args):
                 "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
                 "peak_source": peaks["source"], "traffic": ncu_traffic(),
                 "launches": conv_launches, "avg_launch_ms": conv_ms / max(conv_launches, 1),
-                "flops_per_patch": F_CONV_96,
+                "flops_per_patch": F_CONV_96, "flops_per_patch_untrimmed": F_PATCH_96,
                 "share_of_step": conv_ms / (ms_step * args.steps),
             },
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
