@@ -212,6 +212,26 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
          | ((uint32_t)(M >> 4) << 24);  // M
 }
 
+// ---- packed fp32 math (sm_100 FFMA2: two fp32 FMAs per issued instruction) -------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2_pack(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+// two bf16 (packed in 32 bits) -> two fp32 (exact)
+__device__ __forceinline__ f32x2 bf16x2_to_f2(uint32_t v) {
+  return f2_pack(__uint_as_float(v << 16), __uint_as_float(v & 0xFFFF0000u));
+}
+
 // ---- misc -----------------------------------------------------------------
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

@@ -194,31 +194,50 @@ stem_kernel(const __grid_constant__ StemWeights wt, const StemArgs a) {
 
   const int tx = threadIdx.x % ST_TX, ty = threadIdx.x / ST_TX;
   T* outp = reinterpret_cast<T*>(a.out);
+  // Two output planes per pass, channel pairs in packed fp32 (FFMA2): the weight pairs come
+  // from the constant bank through uniform registers and are shared by both planes.
+  const f32x2* wpair = reinterpret_cast<const f32x2*>(&wt.w[0][0]);
+  const f32x2* bpair = reinterpret_cast<const f32x2*>(&wt.b[0]);
 #pragma unroll 1
-  for (int tz = 0; tz < ST_TZ; ++tz) {
-    float acc[32];
+  for (int tz = 0; tz < ST_TZ; tz += 2) {
+    f32x2 acc0[16], acc1[16];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) acc[c] = wt.b[c];
+    for (int c = 0; c < 16; ++c) acc0[c] = acc1[c] = bpair[c];
 #pragma unroll
     for (int kz = 0; kz < 3; ++kz)
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
-          const float v = tile[tz + kz][ty + ky][tx + kx];
+          const float v0 = tile[tz + kz][ty + ky][tx + kx];
+          const float v1 = tile[tz + 1 + kz][ty + ky][tx + kx];
+          const f32x2 vv0 = f2_pack(v0, v0), vv1 = f2_pack(v1, v1);
 #pragma unroll
-          for (int c = 0; c < 32; ++c) acc[c] = fmaf(v, wt.w[kz * 9 + ky * 3 + kx][c], acc[c]);
+          for (int c = 0; c < 16; ++c) {
+            const f32x2 w = wpair[(kz * 9 + ky * 3 + kx) * 16 + c];
+            acc0[c] = f2_fma(vv0, w, acc0[c]);
+            acc1[c] = f2_fma(vv1, w, acc1[c]);
+          }
         }
-    const size_t vox = (((size_t)b * a.Pz + (z0 + tz)) * a.Py + (y0 + ty)) * a.Px + (x0 + tx);
-    T* dst = outp + vox * 32;
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      float f[8];
+    for (int h = 0; h < 2; ++h) {
+      const size_t vox =
+          (((size_t)b * a.Pz + (z0 + tz + h)) * a.Py + (y0 + ty)) * a.Px + (x0 + tx);
+      T* dst = outp + vox * 32;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = leaky_relu(acc[8 * g + j]);
-      Vec8<T> o;
-      o.from_float(f);
-      o.store(dst + 8 * g);
+      for (int g = 0; g < 4; ++g) {
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float lo, hi;
+          f2_unpack(h == 0 ? acc0[4 * g + j] : acc1[4 * g + j], lo, hi);
+          f[2 * j] = leaky_relu(lo);
+          f[2 * j + 1] = leaky_relu(hi);
+        }
+        Vec8<T> o;
+        o.from_float(f);
+        o.store(dst + 8 * g);
+      }
     }
   }
 }
@@ -366,31 +385,26 @@ upsample_kernel(const T* __restrict__ in, int in_cstride, int in_coff, T* __rest
 }
 
 // bf16 fast path: one thread produces a 2x2x2 output block for 8 channels from the 3x3x3 input
-// window [j-1, j+1] (clamped), separably: 27 vector loads per 8 outputs instead of 64.
-// Per axis, output o has taps (i0, i1) with weights (1-l, l), l = o*(n-1)/(2n-1) - i0, expressed
-// as 3 coefficients over the window so that the two outputs of a block share the loads.
+// window w = (max(j-1,0), j, min(j+1,n-1)), separably: 27 vector loads per 8 outputs instead
+// of 64.  With align_corners=True and scale (n-1)/(2n-1), output 2j interpolates window
+// elements (w0, w1) and output 2j+1 elements (w1, w2); l = src - floor index.  Channel pairs
+// are processed as packed fp32 (FFMA2).
 struct AxisTaps {
-  int w[3];        // window indices (clamped)
-  float ca[3];     // coefficients of output 2j
-  float cb[3];     // coefficients of output 2j+1
+  int w[3];
+  float a0, a1;  // output 2j   = a0*in[w0] + a1*in[w1]
+  float b0, b1;  // output 2j+1 = b0*in[w1] + b1*in[w2]
 };
 __device__ __forceinline__ AxisTaps axis_taps(int j, int n) {
   AxisTaps t;
-  const int w0 = max(j - 1, 0);
-  t.w[0] = w0;
-  t.w[1] = min(w0 + 1, n - 1);
-  t.w[2] = min(w0 + 2, n - 1);
-  const float scale = (2 * n > 1) ? (float)(n - 1) / (float)(2 * n - 1) : 0.f;
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const float src = scale * (float)(2 * j + h);
-    const int i0 = (int)src;
-    const int i1 = i0 + (i0 < n - 1 ? 1 : 0);
-    const float l1 = src - (float)i0, l0 = 1.f - l1;
-    float* c = h == 0 ? t.ca : t.cb;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) c[k] = (k == i0 - w0 ? l0 : 0.f) + (k == i1 - w0 ? l1 : 0.f);
-  }
+  t.w[0] = max(j - 1, 0);
+  t.w[1] = j;
+  t.w[2] = min(j + 1, n - 1);
+  const float scale = (float)(n - 1) / (float)(2 * n - 1);
+  const float sa = scale * (float)(2 * j), sb = scale * (float)(2 * j + 1);
+  t.a1 = sa - (float)t.w[0];   // j = 0: sa = 0 and w0 = w1 = 0, any split of the weight is exact
+  t.a0 = 1.f - t.a1;
+  t.b1 = sb - (float)j;
+  t.b0 = 1.f - t.b1;
   return t;
 }
 
@@ -409,8 +423,11 @@ upsample2_bf16_kernel(const __nv_bfloat16* __restrict__ in, int in_cstride, int 
   const int zj = jz0 + blockIdx.y;
   const int b = blockIdx.z;
   const AxisTaps tz = axis_taps(zj, Di), ty = axis_taps(yj, Hi), tx = axis_taps(xj, Wi);
+  const f32x2 xa0 = f2_pack(tx.a0, tx.a0), xa1 = f2_pack(tx.a1, tx.a1);
+  const f32x2 xb0 = f2_pack(tx.b0, tx.b0), xb1 = f2_pack(tx.b1, tx.b1);
+  const f32x2 zero = f2_pack(0.f, 0.f);
 
-  float acc[2][2][2][8];
+  f32x2 acc[2][2][2][4];  // [z out][y out][x out][channel pair]
 #pragma unroll
   for (int a = 0; a < 2; ++a)
 #pragma unroll
@@ -418,52 +435,63 @@ upsample2_bf16_kernel(const __nv_bfloat16* __restrict__ in, int in_cstride, int 
 #pragma unroll
       for (int c = 0; c < 2; ++c)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[a][bb][c][j] = 0.f;
+        for (int j = 0; j < 4; ++j) acc[a][bb][c][j] = zero;
 
   const __nv_bfloat16* base = in + in_coff + 8 * c8;
 #pragma unroll
   for (int dz = 0; dz < 3; ++dz) {
-    float py[2][2][8];  // [y out][x out]
+    f32x2 py[2][2][4];  // [y out][x out]
 #pragma unroll
     for (int bb = 0; bb < 2; ++bb)
 #pragma unroll
       for (int c = 0; c < 2; ++c)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) py[bb][c][j] = 0.f;
+        for (int j = 0; j < 4; ++j) py[bb][c][j] = zero;
 #pragma unroll
     for (int dy = 0; dy < 3; ++dy) {
       const size_t rowv = (((size_t)b * Di + tz.w[dz]) * Hi + ty.w[dy]) * Wi;
-      float pxa[8], pxb[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) pxa[j] = pxb[j] = 0.f;
+      f32x2 f[3][4];
 #pragma unroll
       for (int dx = 0; dx < 3; ++dx) {
-        Vec8<__nv_bfloat16> q;
-        q.load(base + (rowv + tx.w[dx]) * in_cstride);
-        float f[8];
-        q.to_float(f);
+        const uint4 q = *reinterpret_cast<const uint4*>(base + (rowv + tx.w[dx]) * in_cstride);
+        f[dx][0] = bf16x2_to_f2(q.x);
+        f[dx][1] = bf16x2_to_f2(q.y);
+        f[dx][2] = bf16x2_to_f2(q.z);
+        f[dx][3] = bf16x2_to_f2(q.w);
+      }
+      f32x2 pxa[4], pxb[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          pxa[j] = fmaf(tx.ca[dx], f[j], pxa[j]);
-          pxb[j] = fmaf(tx.cb[dx], f[j], pxb[j]);
+      for (int j = 0; j < 4; ++j) {
+        pxa[j] = f2_fma(xa1, f[1][j], f2_fma(xa0, f[0][j], zero));
+        pxb[j] = f2_fma(xb1, f[2][j], f2_fma(xb0, f[1][j], zero));
+      }
+      // y pass: output 2yj uses window rows (0,1), output 2yj+1 rows (1,2)
+      const float ca = dy == 0 ? ty.a0 : (dy == 1 ? ty.a1 : 0.f);
+      const float cb = dy == 1 ? ty.b0 : (dy == 2 ? ty.b1 : 0.f);
+      const f32x2 ca2 = f2_pack(ca, ca), cb2 = f2_pack(cb, cb);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (dy < 2) {
+          py[0][0][j] = f2_fma(ca2, pxa[j], py[0][0][j]);
+          py[0][1][j] = f2_fma(ca2, pxb[j], py[0][1][j]);
+        }
+        if (dy > 0) {
+          py[1][0][j] = f2_fma(cb2, pxa[j], py[1][0][j]);
+          py[1][1][j] = f2_fma(cb2, pxb[j], py[1][1][j]);
         }
       }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        py[0][0][j] = fmaf(ty.ca[dy], pxa[j], py[0][0][j]);
-        py[0][1][j] = fmaf(ty.ca[dy], pxb[j], py[0][1][j]);
-        py[1][0][j] = fmaf(ty.cb[dy], pxa[j], py[1][0][j]);
-        py[1][1][j] = fmaf(ty.cb[dy], pxb[j], py[1][1][j]);
-      }
     }
+    const float za = dz == 0 ? tz.a0 : (dz == 1 ? tz.a1 : 0.f);
+    const float zb = dz == 1 ? tz.b0 : (dz == 2 ? tz.b1 : 0.f);
+    const f32x2 za2 = f2_pack(za, za), zb2 = f2_pack(zb, zb);
 #pragma unroll
     for (int bb = 0; bb < 2; ++bb)
 #pragma unroll
       for (int c = 0; c < 2; ++c)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          acc[0][bb][c][j] = fmaf(tz.ca[dz], py[bb][c][j], acc[0][bb][c][j]);
-          acc[1][bb][c][j] = fmaf(tz.cb[dz], py[bb][c][j], acc[1][bb][c][j]);
+        for (int j = 0; j < 4; ++j) {
+          if (dz < 2) acc[0][bb][c][j] = f2_fma(za2, py[bb][c][j], acc[0][bb][c][j]);
+          if (dz > 0) acc[1][bb][c][j] = f2_fma(zb2, py[bb][c][j], acc[1][bb][c][j]);
         }
   }
   const int Ho = 2 * Hi, Wo = 2 * Wi, Do = 2 * Di;
@@ -477,9 +505,13 @@ upsample2_bf16_kernel(const __nv_bfloat16* __restrict__ in, int in_cstride, int 
         if (zo >= rg.lo[0] && zo < rg.hi[0] && yo >= rg.lo[1] && yo < rg.hi[1] && xo >= rg.lo[2] &&
             xo < rg.hi[2]) {
           const size_t ovox = (((size_t)b * Do + zo) * Ho + yo) * Wo + xo;
-          Vec8<__nv_bfloat16> o;
-          o.from_float(acc[a][bb][c]);
-          o.store(out + ovox * out_cstride + out_coff + 8 * c8);
+          uint4 o;
+          float lo, hi;
+          f2_unpack(acc[a][bb][c][0], lo, hi); o.x = pack_bf16x2(lo, hi);
+          f2_unpack(acc[a][bb][c][1], lo, hi); o.y = pack_bf16x2(lo, hi);
+          f2_unpack(acc[a][bb][c][2], lo, hi); o.z = pack_bf16x2(lo, hi);
+          f2_unpack(acc[a][bb][c][3], lo, hi); o.w = pack_bf16x2(lo, hi);
+          *reinterpret_cast<uint4*>(out + ovox * out_cstride + out_coff + 8 * c8) = o;
         }
       }
 }
