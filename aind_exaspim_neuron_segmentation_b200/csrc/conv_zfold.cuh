@@ -38,6 +38,7 @@ struct ZfArgs {
   const float* head_b;       // [head_c]
   float* head_out;           // [B][head_c][D-2t][H-2t][W-2t]
   int head_c, trim, apply_sigmoid;
+  long long* dbg;            // optional [gridDim.x][8] cycle counters (EXA_ZF_DEBUG=1), else nullptr
 };
 
 template <int CIN>
@@ -150,11 +151,24 @@ conv3x3_zfold_kernel(const __grid_constant__ CUtensorMap tmap_x,
       mbar_wait(smem_u32(w_bar), 0);
       tc_fence_after();
       const uint32_t w_base = smem_u32(smem_w);
-      int stage = 0;
-      uint32_t phase = 0;
+      // Flattened loop over (tile, input plane).  The barrier probes for iteration it+1 are
+      // issued BEFORE the MMAs of iteration it ("peek") and only consumed afterwards: an
+      // mbarrier probe whose result is needed immediately costs 200-550 cycles, during which the
+      // tensor pipe (which queues almost nothing) would drain.
+      const int nin = zin1 - zin0;
+      const int my_tiles = cta_in_class < p.tiles_total
+                               ? (p.tiles_total - cta_in_class + ctas_per_class - 1) / ctas_per_class
+                               : 0;
+      const int total_it = my_tiles * nin;
+      long long d_tempty = 0, d_full = 0, d_issue = 0, d_commit = 0, d_planes = 0;
+      bool tok_full = false, tok_fresh = false;
+      int zi = zin0;
       uint32_t gbase = 0;  // running count of output planes handled by this CTA
-      for (int tile = cta_in_class; tile < p.tiles_total; tile += ctas_per_class) {
-        for (int zi = zin0; zi < zin1; ++zi) {
+      for (int it = 0; it < total_it; ++it) {
+        {
+          const int stage = it % STAGES;
+          const uint32_t phase = (uint32_t)(it / STAGES) & 1u;
+          const long long c0 = p.dbg ? clock64() : 0;
           // Output planes fed by input plane zi: po = zi - 1 + kzr (kzr = 0..2 <-> B rows
           // [32*kzr, 32*kzr+32)).  Everything below is kept in scalar registers and the tap loop
           // is fully unrolled: a single thread issues every MMA, so its instruction count per
@@ -173,7 +187,9 @@ conv3x3_zfold_kernel(const __grid_constant__ CUtensorMap tmap_x,
             f_col[kzr] = slot * 32u;
             f_acc[kzr] = fresh ? 0u : 1u;
             if (valid) {
-              if (fresh) {  // first touch of this ring slot: the epilogue must have drained it
+              // first touch of this ring slot: the epilogue must have drained it.  The slot of
+              // plane zi+1 was peeked during the previous iteration.
+              if (fresh && !(kzr == 2 && tok_fresh)) {
                 mbar_wait(smem_u32(&tempty_bar[slot]), ((g / ZF_RING) & 1u) ^ 1u);
               }
               if (sa_n == 0) {
@@ -187,9 +203,28 @@ conv3x3_zfold_kernel(const __grid_constant__ CUtensorMap tmap_x,
               }
             }
           }
-          tc_fence_after();
-          mbar_wait(smem_u32(&full_bar[stage]), phase);
-          tc_fence_after();
+          const long long c1 = p.dbg ? clock64() : 0;
+          if (!tok_full) mbar_wait(smem_u32(&full_bar[stage]), phase);
+          const long long c2 = p.dbg ? clock64() : 0;
+          // ---- peek the barriers of the next iteration ----
+          int zi_next = zi + 1;
+          uint32_t gbase_next = gbase;
+          if (zi_next == zin1) {
+            zi_next = zin0;
+            gbase_next += (uint32_t)p.nzp;
+          }
+          tok_full = false;
+          tok_fresh = false;
+          if (it + 1 < total_it) {
+            const int nstage = (it + 1) % STAGES;
+            tok_full = mbar_test_wait(smem_u32(&full_bar[nstage]), (uint32_t)((it + 1) / STAGES) & 1u);
+            const int pf = zi_next + 1;  // the plane first touched by the next iteration (kzr = 2)
+            if (pf >= p.oz && pf < p.oz + p.nzp) {
+              const uint32_t gn = gbase_next + (uint32_t)(pf - p.oz);
+              tok_fresh = mbar_test_wait(smem_u32(&tempty_bar[gn % ZF_RING]),
+                                         ((gn / ZF_RING) & 1u) ^ 1u);
+            }
+          }
           const uint32_t a_base = smem_u32(smem_a + stage * S::A_STAGE);
           // halo view: 8-row groups are 10 rows apart; tap (ky,kx) shifts the start by ky*10+kx rows
           uint64_t adesc0 = umma_smem_desc<ROWB>(a_base);
@@ -233,19 +268,26 @@ conv3x3_zfold_kernel(const __grid_constant__ CUtensorMap tmap_x,
               }
             }
           }
+          const long long c3 = p.dbg ? clock64() : 0;
           umma_commit(smem_u32(&empty_bar[stage]));
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1u;
-          }
           // completed output planes: zi-1 always; zi too when it is the last input plane
           const int pc = zi - 1;
           if (pc >= p.oz && pc < p.oz + p.nzp)
             umma_commit(smem_u32(&tfull_bar[(gbase + (uint32_t)(pc - p.oz)) % ZF_RING]));
           if (zi == zin1 - 1 && zi >= p.oz && zi < p.oz + p.nzp)
             umma_commit(smem_u32(&tfull_bar[(gbase + (uint32_t)(zi - p.oz)) % ZF_RING]));
+          if (p.dbg) {
+            const long long c4 = clock64();
+            d_tempty += c1 - c0; d_full += c2 - c1; d_issue += c3 - c2; d_commit += c4 - c3;
+            ++d_planes;
+          }
+          zi = zi_next;
+          gbase = gbase_next;
         }
-        gbase += (uint32_t)p.nzp;
+      }
+      if (p.dbg) {
+        long long* d = p.dbg + (size_t)blockIdx.x * 8;
+        d[0] = d_tempty; d[1] = d_full; d[2] = d_issue; d[3] = d_commit; d[4] = d_planes;
       }
     }
     __syncwarp();
@@ -259,6 +301,7 @@ conv3x3_zfold_kernel(const __grid_constant__ CUtensorMap tmap_x,
 #pragma unroll
     for (int j = 0; j < 32; ++j) bias[j] = __ldg(p.bias + n0 + j);
     uint32_t gbase = 0;
+    long long e_wait = 0, e_ld = 0, e_rest = 0;
     uint32_t prev[16];  // previous (even) plane, packed bf16x2, for the fused 2x2x2 max-pool
 #pragma unroll
     for (int j = 0; j < 16; ++j) prev[j] = 0u;
@@ -271,14 +314,17 @@ conv3x3_zfold_kernel(const __grid_constant__ CUtensorMap tmap_x,
       for (int po = p.oz; po < p.oz + p.nzp; ++po) {
         const uint32_t g = gbase + (uint32_t)(po - p.oz);
         const uint32_t slot = g % ZF_RING;
+        const long long e0 = p.dbg ? clock64() : 0;
         mbar_wait(smem_u32(&tfull_bar[slot]), (g / ZF_RING) & 1u);
         tc_fence_after();
+        const long long e1 = p.dbg ? clock64() : 0;
         uint32_t acc[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + slot * 32u, acc);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[slot]));  // slot is in registers now
+        const long long e2 = p.dbg ? clock64() : 0;
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = leaky_relu(__uint_as_float(acc[j]) + bias[j]);
@@ -340,8 +386,16 @@ conv3x3_zfold_kernel(const __grid_constant__ CUtensorMap tmap_x,
             }
           }
         }
+        if (p.dbg) {
+          const long long e3 = clock64();
+          e_wait += e1 - e0; e_ld += e2 - e1; e_rest += e3 - e2;
+        }
       }
       gbase += (uint32_t)p.nzp;
+    }
+    if (p.dbg && warp == 4 && lane == 0) {
+      long long* d = p.dbg + (size_t)blockIdx.x * 8;
+      d[5] = e_wait; d[6] = e_ld; d[7] = e_rest;
     }
   }
 

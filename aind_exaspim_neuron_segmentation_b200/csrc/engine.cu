@@ -3,6 +3,7 @@
 #include "engine.h"
 
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -194,6 +195,7 @@ Engine::Scope::Scope(Engine* eng, int cat, cudaStream_t st) : e(eng), s(st) {
   if (!e->prof_on_) return;
   ProfRec r;
   r.cat = cat;
+  r.tag = cat == CAT_CONV ? e->cur_tag_ : -1;
   if (cudaEventCreate(&r.start) != cudaSuccess || cudaEventCreate(&r.stop) != cudaSuccess) return;
   cudaEventRecord(r.start, s);
   stop = r.stop;
@@ -223,6 +225,8 @@ Status Engine::profile_end(double* ms_by_cat, int64_t* launches_by_cat, int n) {
     launches_by_cat[i] = 0;
   }
   Status st = Status::OK();
+  double layer_ms[18] = {0};
+  int layer_n[18] = {0};
   for (auto& r : prof_) {
     float ms = 0.f;
     cudaError_t e = cudaEventSynchronize(r.stop);
@@ -230,10 +234,21 @@ Status Engine::profile_end(double* ms_by_cat, int64_t* launches_by_cat, int n) {
     if (e != cudaSuccess && st.ok) st = Status::Err(std::string("cudaEventElapsedTime: ") + cudaGetErrorString(e));
     ms_by_cat[r.cat] += ms;
     launches_by_cat[r.cat] += 1;
+    if (r.tag >= 0 && r.tag < 18) {
+      layer_ms[r.tag] += ms;
+      layer_n[r.tag] += 1;
+    }
     cudaEventDestroy(r.start);
     cudaEventDestroy(r.stop);
   }
   prof_.clear();
+  if (getenv("EXA_LAYER_PROF")) {
+    for (int i = 0; i < 18; ++i)
+      if (layer_n[i])
+        fprintf(stderr, "[layer %2d %-36s %3d->%3d] %4d launches, %.3f ms total, %.4f ms/launch\n", i,
+                layers_[i].conv_key.c_str(), layers_[i].cin, layers_[i].cout, layer_n[i],
+                layer_ms[i], layer_ms[i] / layer_n[i]);
+  }
   return st;
 }
 
@@ -484,6 +499,7 @@ Status Engine::ensure_workspace(int batch, int pz, int py, int px) {
 
 Status Engine::conv(const ConvLayer& L, const Act& in, const Act& out, const HeadParams* head,
                     const ConvRegion* region, const Act* pool_out, cudaStream_t s) {
+  cur_tag_ = (int)(&L - layers_);
   if (precision_ == EXA_PRECISION_BF16) {
     const bool zf = use_zfold_ && L.w_zfold && conv_zfold_supported(in, L.cout);
     {

@@ -85,8 +85,10 @@ class Engine {
 
   struct ProfRec {
     int cat;
+    int tag;  // conv: layer index 1..17; other categories: -1 (EXA_LAYER_PROF=1 prints per-tag sums)
     cudaEvent_t start, stop;
   };
+  int cur_tag_ = -1;
   struct Scope {  // counts the launch and, when profiling, brackets it with two events
     Engine* e;
     cudaStream_t s;

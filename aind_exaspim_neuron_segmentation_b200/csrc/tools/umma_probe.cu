@@ -161,6 +161,185 @@ rate_kernel(int iters, long long* cycles) {
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
+// Same, but A descriptors are the nine "halo views" of the z-folded conv kernel: start address
+// shifted by (ky*10+kx) rows, 8-row groups 10 rows apart (unaligned swizzle atoms), or -- with
+// ALIGNED -- the 3-copy layout (x-shifted copies with pitch 8: start ky*8 rows, SBO 8 rows).
+template <int N, int ROWB, bool ALIGNED>
+__global__ void __launch_bounds__(128, 1)
+rate_halo_kernel(int iters, long long* cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + 196608);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 4);
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 196608 / 16; i += blockDim.x) ((uint4*)smem)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bars[0]), 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), 512);
+    tmem_relinquish();
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int warp_u = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  if (warp_u == 0) {
+    constexpr uint32_t idesc = umma_idesc_bf16(128, N);
+    uint64_t a0 = umma_smem_desc<ROWB>(smem_u32(smem));
+    if (!ALIGNED) {
+      a0 &= ~((uint64_t)0x3FFF << 32);
+      a0 |= (uint64_t)((10 * ROWB) >> 4) << 32;
+    }
+    const uint64_t b0 = umma_smem_desc<ROWB>(smem_u32(smem) + 98304);
+    long long t0 = clock64();
+    if (elect_one()) {
+      for (int it = 0; it < iters; it += 36) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int kk = k % (ROWB / 32);
+            const int rows = ALIGNED ? ((t % 3) * 144 + (t / 3) * 8) : ((t / 3) * 10 + (t % 3));
+            const uint64_t adesc = a0 + (uint64_t)((rows * ROWB + kk * 32) >> 4);
+            const uint64_t bdesc = b0 + (uint64_t)(((t % 2) * N * ROWB + kk * 32) >> 4);  // stays inside smem
+            umma_bf16(tmem, adesc, bdesc, idesc, 1);
+          }
+        }
+      }
+      umma_commit(smem_u32(&bars[0]));
+    }
+    __syncwarp();
+    mbar_wait(smem_u32(&bars[0]), 0);
+    long long t1 = clock64();
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+template <int N, int ROWB, bool ALIGNED>
+static void run_rate_halo(int sms, long long* dcyc) {
+  const size_t smem_bytes = 196608 + 64 + 1024;
+  CK(cudaFuncSetAttribute(rate_halo_kernel<N, ROWB, ALIGNED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  const int iters = 36 * 256;
+  rate_halo_kernel<N, ROWB, ALIGNED><<<sms, 128, smem_bytes>>>(iters, dcyc);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("rate halo kernel error %s\n", cudaGetErrorString(e)); exit(3); }
+  std::vector<long long> h(sms);
+  CK(cudaMemcpy(h.data(), dcyc, sizeof(long long) * sms, cudaMemcpyDeviceToHost));
+  long long mx = 0;
+  for (auto v : h) mx = v > mx ? v : mx;
+  double cyc = (double)mx / iters;
+  printf("RATE-HALO N=%3d rowbytes=%3d %-9s : %.2f cyc/MMA (ideal %.1f) -> %.1f%% of tensor peak\n", N, ROWB,
+         ALIGNED ? "aligned" : "unaligned", cyc, N / 2.0, 100.0 * (N / 2.0) / cyc);
+}
+
+
+// ---- issuer-loop emulation --------------------------------------------------------------
+// One "plane" = 9 taps x KSTEPS halo-view MMAs (N=96) as in conv_zfold.cuh, plus the barrier
+// traffic the real issuer thread has per plane.  Answers: what do tcgen05.commit and mbarrier
+// probes cost when interleaved with the MMA stream of the single issuing thread?
+//  MODE 0 MMAs only | 1 +1 commit | 2 +2 commits | 3 +2 commits +1 blocking try_wait (complete
+//  barrier) | 4 +2 commits +2 try_waits | 5 +2 commits +2 test_wait peeks consumed next plane |
+//  6 MODE 0 with the first k-step split in three N=32 MMAs | 7 MODE 2 + split first k-step
+template <int ROWB, int MODE>
+__global__ void __launch_bounds__(128, 1)
+loop_kernel(int planes, long long* cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + 196608);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 6);
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 196608 / 16; i += blockDim.x) ((uint4*)smem)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 5; ++i) mbar_init(smem_u32(&bars[i]), 1);
+    mbar_fence_init();
+    mbar_arrive(smem_u32(&bars[3]));  // phase 0 of bars[3], bars[4] complete for good
+    mbar_arrive(smem_u32(&bars[4]));
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), 512);
+    tmem_relinquish();
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int warp_u = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  constexpr int KSTEPS = ROWB / 32;
+  if (warp_u == 0) {
+    uint64_t a0 = umma_smem_desc<ROWB>(smem_u32(smem));
+    a0 &= ~((uint64_t)0x3FFF << 32);
+    a0 |= (uint64_t)((10 * ROWB) >> 4) << 32;
+    const uint64_t b0 = umma_smem_desc<ROWB>(smem_u32(smem) + 98304);
+    long long t0 = clock64();
+    if (elect_one()) {
+      bool tok0 = true, tok1 = true;
+      for (int pl = 0; pl < planes; ++pl) {
+        const uint32_t col = (uint32_t)((pl & 3) * 96);
+        const uint64_t astage = a0 + (uint64_t)(((pl & 3) * 12288) >> 4);
+        if (MODE == 3 || MODE == 4) mbar_wait(smem_u32(&bars[3]), 0);
+        if (MODE == 4) mbar_wait(smem_u32(&bars[4]), 0);
+        if (MODE == 5) {
+          if (!tok0) mbar_wait(smem_u32(&bars[3]), 0);
+          if (!tok1) mbar_wait(smem_u32(&bars[4]), 0);
+          tok0 = mbar_test_wait(smem_u32(&bars[3]), 0);
+          tok1 = mbar_test_wait(smem_u32(&bars[4]), 0);
+        }
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+#pragma unroll
+          for (int k = 0; k < KSTEPS; ++k) {
+            const uint64_t aoff = (uint64_t)((((t / 3) * 10 + (t % 3)) * ROWB + k * 32) >> 4);
+            const uint64_t boff = (uint64_t)((t * 96 * ROWB + k * 32) >> 4);
+            if ((MODE == 6 || MODE == 7) && t == 0 && k == 0) {
+#pragma unroll
+              for (int z = 0; z < 3; ++z)
+                umma_bf16(tmem + col + z * 32, astage, b0 + (uint64_t)((z * 32 * ROWB) >> 4),
+                          umma_idesc_bf16(128, 32), z == 2 ? 0u : 1u);
+            } else {
+              umma_bf16(tmem + col, astage + aoff, b0 + boff, umma_idesc_bf16(128, 96), 1u);
+            }
+          }
+        }
+        if (MODE >= 1 && MODE != 6) umma_commit(smem_u32(&bars[1]));
+        if ((MODE >= 2 && MODE != 6)) umma_commit(smem_u32(&bars[2]));
+      }
+      umma_commit(smem_u32(&bars[0]));
+    }
+    __syncwarp();
+    mbar_wait(smem_u32(&bars[0]), 0);
+    long long t1 = clock64();
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+template <int ROWB, int MODE>
+static void run_loop(int sms, long long* dcyc) {
+  const size_t smem_bytes = 196608 + 64 + 1024;
+  CK(cudaFuncSetAttribute(loop_kernel<ROWB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  const int planes = 2048;
+  loop_kernel<ROWB, MODE><<<sms, 128, smem_bytes>>>(planes, dcyc);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("loop kernel error %s\n", cudaGetErrorString(e)); exit(3); }
+  std::vector<long long> h(sms);
+  CK(cudaMemcpy(h.data(), dcyc, sizeof(long long) * sms, cudaMemcpyDeviceToHost));
+  long long mx = 0;
+  for (auto v : h) mx = v > mx ? v : mx;
+  const int mmas = 9 * (ROWB / 32);
+  printf("LOOP rowbytes=%3d mode=%d : %.1f cyc/plane (%d MMAs; N=96 floor %d, smem-bound %d)\n", ROWB, MODE,
+         (double)mx / planes, mmas, mmas * 48, mmas * 56);
+}
+
 template <int N, int ACCS>
 static void run_rate(int sms, long long* dcyc) {
   const size_t smem_bytes = 196608 + 64 + 1024;
@@ -197,6 +376,7 @@ int main() {
   const int D = 3, H = 24, W = 16, NW = 256;
   int failures = 0;
   for (int rb : {128, 64}) {
+    if (getenv("PROBE_RATE_ONLY")) break;
     const int C = rb / 2;
     std::vector<uint16_t> hx((size_t)D * H * W * C), hw((size_t)27 * NW * C);
     uint32_t s = 12345u + rb;
@@ -292,6 +472,13 @@ int main() {
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     long long* dcyc;
     CK(cudaMalloc(&dcyc, sizeof(long long) * sms));
+    run_rate_halo<96, 128, false>(sms, dcyc); run_rate_halo<96, 128, true>(sms, dcyc);
+    run_rate_halo<96, 64, false>(sms, dcyc);  run_rate_halo<96, 64, true>(sms, dcyc);
+    run_rate_halo<192, 128, false>(sms, dcyc); run_rate_halo<192, 128, true>(sms, dcyc);
+    run_loop<64, 0>(sms, dcyc); run_loop<64, 1>(sms, dcyc); run_loop<64, 2>(sms, dcyc); run_loop<64, 3>(sms, dcyc);
+    run_loop<64, 4>(sms, dcyc); run_loop<64, 5>(sms, dcyc); run_loop<64, 6>(sms, dcyc); run_loop<64, 7>(sms, dcyc);
+    run_loop<128, 0>(sms, dcyc); run_loop<128, 2>(sms, dcyc); run_loop<128, 4>(sms, dcyc); run_loop<128, 5>(sms, dcyc);
+    if (getenv("PROBE_RATE_ONLY")) { printf("PROBE DONE (rate only)\n"); return 0; }
     run_rate<32, 1>(sms, dcyc);  run_rate<32, 4>(sms, dcyc);
     run_rate<64, 1>(sms, dcyc);  run_rate<64, 4>(sms, dcyc);
     run_rate<96, 1>(sms, dcyc);  run_rate<96, 4>(sms, dcyc);
