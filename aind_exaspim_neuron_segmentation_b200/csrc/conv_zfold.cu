@@ -1,7 +1,6 @@
 // Host launcher for the z-folded halo-tile tcgen05 conv (kernel in conv_zfold.cuh).
 #include "conv_zfold.cuh"
 
-#include <stdio.h>
 #include <stdlib.h>
 
 #include "kernels.h"
@@ -21,7 +20,7 @@ Status launch_zf(const CUtensorMap& tx, const CUtensorMap& tw, const ZfArgs& a, 
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     configured = true;
   }
-  conv3x3_zfold_kernel<CIN, EPI><<<grid, 256, S::TOTAL, s>>>(tx, tw, a);
+  conv3x3_zfold_kernel<CIN, EPI><<<grid, ZF_THREADS, S::TOTAL, s>>>(tx, tw, a);
   EXA_CUDA(cudaGetLastError());
   return Status::OK();
 }
@@ -99,28 +98,10 @@ Status launch_conv_zfold(const Act& in, const Act& out, const __nv_bfloat16* w_z
   }
   int grid = num_sms - num_sms % a.n_halves;
   if (grid > a.tiles_total * a.n_halves) grid = a.tiles_total * a.n_halves;
-  static const bool debug = getenv("EXA_ZF_DEBUG") != nullptr;
-  static long long* dbg_dev = nullptr;
-  if (debug) {
-    if (!dbg_dev) EXA_CUDA(cudaMalloc(&dbg_dev, sizeof(long long) * 8 * 1024));
-    EXA_CUDA(cudaMemsetAsync(dbg_dev, 0, sizeof(long long) * 8 * 1024, s));
-    a.dbg = dbg_dev;
+  {
+    static const char* dbg_env = getenv("EXA_ZF_DBG");  // development-only timing experiments
+    a.dbg = dbg_env ? atoi(dbg_env) : 0;
   }
-  struct DbgPrint {
-    bool on; int grid, cin, cout, head; cudaStream_t s; long long* dev;
-    ~DbgPrint() {
-      if (!on) return;
-      cudaStreamSynchronize(s);
-      static long long h[8 * 1024];
-      cudaMemcpy(h, dev, sizeof(long long) * 8 * grid, cudaMemcpyDeviceToHost);
-      double t[8] = {0};
-      for (int i = 0; i < grid; ++i) for (int j = 0; j < 8; ++j) t[j] += (double)h[i * 8 + j];
-      const double pl = t[4] > 0 ? t[4] : 1;
-      fprintf(stderr, "[zfold cin=%d cout=%d head=%d grid=%d] per plane (cycles): issuer tempty %.0f full %.0f issue %.0f commit %.0f | epilogue(w4) wait %.0f ld %.0f rest %.0f | planes/cta %.0f\n",
-              cin, cout, head, grid, t[0] / pl, t[1] / pl, t[2] / pl, t[3] / pl, t[5] / pl, t[6] / pl, t[7] / pl, pl / grid);
-    }
-  } dbg_print{debug, grid, Cin, Cout, head != nullptr, s, dbg_dev};
-
   if (Cin == 32) {
     if (head) return launch_zf<32, EPI_HEAD>(tx, tw, a, grid, s);
     return launch_zf<32, EPI_STORE>(tx, tw, a, grid, s);

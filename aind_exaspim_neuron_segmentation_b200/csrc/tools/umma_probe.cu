@@ -249,13 +249,21 @@ static void run_rate_halo(int sms, long long* dcyc) {
 //  6 MODE 0 with the first k-step split in three N=32 MMAs | 7 MODE 2 + split first k-step
 template <int ROWB, int MODE>
 __global__ void __launch_bounds__(128, 1)
-loop_kernel(int planes, long long* cycles) {
+loop_kernel(int planes, long long* cycles, int fill) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = (uint64_t*)(smem + 196608);
   uint32_t* tmem_slot = (uint32_t*)(bars + 6);
   const int warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < 196608 / 16; i += blockDim.x) ((uint4*)smem)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < 196608 / 16; i += blockDim.x) {
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (fill) {  // pseudo-random bf16 values in (-2, 2): realistic operand toggling
+      uint32_t h = (uint32_t)i * 2654435761u + blockIdx.x * 40503u;
+      auto nxt = [&]() { h = h * 1664525u + 1013904223u; return ((h >> 9) & 0x807F807Fu) | 0x3F003F00u; };
+      v = make_uint4(nxt(), nxt(), nxt(), nxt());
+    }
+    ((uint4*)smem)[i] = v;
+  }
   if (threadIdx.x == 0) {
     for (int i = 0; i < 5; ++i) mbar_init(smem_u32(&bars[i]), 1);
     mbar_fence_init();
@@ -277,13 +285,21 @@ loop_kernel(int planes, long long* cycles) {
     uint64_t a0 = umma_smem_desc<ROWB>(smem_u32(smem));
     a0 &= ~((uint64_t)0x3FFF << 32);
     a0 |= (uint64_t)((10 * ROWB) >> 4) << 32;
-    const uint64_t b0 = umma_smem_desc<ROWB>(smem_u32(smem) + 98304);
+    const uint64_t b0 = umma_smem_desc<ROWB>(smem_u32(smem) + (ROWB == 64 ? 98304 : 65536));
     long long t0 = clock64();
     if (elect_one()) {
       bool tok0 = true, tok1 = true;
+      uint32_t wring = 0;
+#pragma unroll 1
       for (int pl = 0; pl < planes; ++pl) {
-        const uint32_t col = (uint32_t)((pl & 3) * 96);
-        const uint64_t astage = a0 + (uint64_t)(((pl & 3) * 12288) >> 4);
+        // MODE 8/9: the TMEM column operand is a loop-carried value in ONE register that is
+        // rewritten every plane (MODE 9 also commits twice per plane)
+        uint32_t col = (uint32_t)((pl & 3) * 96);
+        if (MODE == 8 || MODE == 9) {
+          col = wring * 32u;
+          wring = wring == 12u ? 0u : wring + 1u;
+        }
+        const uint64_t astage = a0 + (uint64_t)((ROWB == 64 ? (pl & 3) * 12288 : (pl & 1) * 24576) >> 4);
         if (MODE == 3 || MODE == 4) mbar_wait(smem_u32(&bars[3]), 0);
         if (MODE == 4) mbar_wait(smem_u32(&bars[4]), 0);
         if (MODE == 5) {
@@ -308,8 +324,8 @@ loop_kernel(int planes, long long* cycles) {
             }
           }
         }
-        if (MODE >= 1 && MODE != 6) umma_commit(smem_u32(&bars[1]));
-        if ((MODE >= 2 && MODE != 6)) umma_commit(smem_u32(&bars[2]));
+        if (MODE >= 1 && MODE != 6 && MODE != 8) umma_commit(smem_u32(&bars[1]));
+        if ((MODE >= 2 && MODE != 6 && MODE != 8)) umma_commit(smem_u32(&bars[2]));
       }
       umma_commit(smem_u32(&bars[0]));
     }
@@ -328,7 +344,8 @@ static void run_loop(int sms, long long* dcyc) {
   const size_t smem_bytes = 196608 + 64 + 1024;
   CK(cudaFuncSetAttribute(loop_kernel<ROWB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   const int planes = 2048;
-  loop_kernel<ROWB, MODE><<<sms, 128, smem_bytes>>>(planes, dcyc);
+  for (int fill = 0; fill < 2; ++fill) {
+  loop_kernel<ROWB, MODE><<<sms, 128, smem_bytes>>>(planes, dcyc, fill);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("loop kernel error %s\n", cudaGetErrorString(e)); exit(3); }
   std::vector<long long> h(sms);
@@ -336,8 +353,205 @@ static void run_loop(int sms, long long* dcyc) {
   long long mx = 0;
   for (auto v : h) mx = v > mx ? v : mx;
   const int mmas = 9 * (ROWB / 32);
-  printf("LOOP rowbytes=%3d mode=%d : %.1f cyc/plane (%d MMAs; N=96 floor %d, smem-bound %d)\n", ROWB, MODE,
-         (double)mx / planes, mmas, mmas * 48, mmas * 56);
+  printf("LOOP rowbytes=%3d mode=%d fill=%s : %.1f cyc/plane (%d MMAs; N=96 floor %d, smem-bound %d)\n", ROWB, MODE,
+         fill ? "random" : "zeros", (double)mx / planes, mmas, mmas * 48, mmas * 56);
+  }
+}
+
+
+// ---- shared-memory port contention --------------------------------------------------------
+// The MMA stream of loop_kernel<64,0> (18 N=96 MMAs per plane, operand reads ~125 B/cycle) runs
+// while a second warp writes into an unrelated shared-memory region by
+//   bg=1 TMA halo boxes with 64 B rows | bg=2 TMA halo boxes with 128 B rows |
+//   bg=3 cp.async 16 B per thread (64 threads) | bg=4 st.shared.v4 (32 threads) | bg=0 nothing.
+// Reports MMA cycles/plane and background bytes written per plane.
+__global__ void __launch_bounds__(128, 1)
+contend_kernel(const __grid_constant__ CUtensorMap tmap64, const __grid_constant__ CUtensorMap tmap128,
+               const uint4* gsrc, int planes, int bg, long long* cycles, long long* bgbytes) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + 196608);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 12);
+  volatile uint32_t* done_flag = (volatile uint32_t*)(bars + 13);
+  uint8_t* scratch = smem + 155648;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 196608 / 16; i += blockDim.x) ((uint4*)smem)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 12; ++i) mbar_init(smem_u32(&bars[i]), 1);
+    mbar_fence_init();
+    *done_flag = 0;
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), 512);
+    tmem_relinquish();
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int warp_u = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  constexpr int ROWB = 64;
+  if (warp_u == 0) {
+    uint64_t a0 = umma_smem_desc<ROWB>(smem_u32(smem));
+    a0 &= ~((uint64_t)0x3FFF << 32);
+    a0 |= (uint64_t)((10 * ROWB) >> 4) << 32;
+    const uint64_t b0 = umma_smem_desc<ROWB>(smem_u32(smem) + 98304);
+    long long t0 = clock64();
+    if (elect_one()) {
+      for (int pl = 0; pl < planes; ++pl) {
+        const uint32_t col = (uint32_t)((pl & 3) * 96);
+        const uint64_t astage = a0 + (uint64_t)(((pl & 3) * 12288) >> 4);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const uint64_t aoff = (uint64_t)((((t / 3) * 10 + (t % 3)) * ROWB + k * 32) >> 4);
+            const uint64_t boff = (uint64_t)((t * 96 * ROWB + k * 32) >> 4);
+            umma_bf16(tmem + col, astage + aoff, b0 + boff, umma_idesc_bf16(128, 96), 1u);
+          }
+        }
+      }
+      umma_commit(smem_u32(&bars[0]));
+    }
+    __syncwarp();
+    mbar_wait(smem_u32(&bars[0]), 0);
+    long long t1 = clock64();
+    if (threadIdx.x == 0) {
+      cycles[blockIdx.x] = t1 - t0;
+      *done_flag = 1;
+    }
+  } else if (warp_u == 2 || warp_u == 3) {
+    long long bytes = 0;
+    if (bg == 1 || bg == 2) {
+      if (warp_u == 2 && elect_one()) {
+        const CUtensorMap* tm = bg == 1 ? &tmap64 : &tmap128;
+        const uint32_t box_bytes = bg == 1 ? 180 * 64 : 180 * 128;
+        // 4 boxes in flight, round robin over 4 barriers
+        uint32_t ph[4] = {0, 0, 0, 0};
+        int issued = 0;
+        for (int i = 0; i < 4; ++i) {
+          mbar_expect_tx(smem_u32(&bars[4 + i]), box_bytes);
+          tma_load_5d(smem_u32(scratch), tm, smem_u32(&bars[4 + i]), 0, -1, -1, i % 3, 0);
+          ++issued;
+        }
+        int i = 0;
+        while (!*done_flag) {
+          mbar_wait(smem_u32(&bars[4 + i]), ph[i]);
+          ph[i] ^= 1u;
+          bytes += box_bytes;
+          mbar_expect_tx(smem_u32(&bars[4 + i]), box_bytes);
+          tma_load_5d(smem_u32(scratch), tm, smem_u32(&bars[4 + i]), 0, -1, -1, issued % 3, 0);
+          ++issued;
+          i = (i + 1) & 3;
+        }
+        for (int j = 0; j < 4; ++j) {  // drain
+          mbar_wait(smem_u32(&bars[4 + i]), ph[i]);
+          i = (i + 1) & 3;
+        }
+        bgbytes[blockIdx.x] = bytes;
+      }
+    } else if (bg == 3) {
+      const int tid = threadIdx.x - 64;  // 0..63
+      const uint32_t dst = smem_u32(scratch) + tid * 16;
+      int it = 0;
+      while (!*done_flag) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)(u * 1024)),
+                       "l"(gsrc + ((it * 8 + u) & 1023) * 64 + tid)
+                       : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 2;" ::: "memory");
+        bytes += 8 * 16;
+        ++it;
+      }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      atomicAdd((unsigned long long*)&bgbytes[blockIdx.x], (unsigned long long)bytes);
+    } else if (bg == 5 || bg == 6) {
+      // tcgen05.ld stream from this warp's TMEM lane quarter: back to back (5) or one 16-column
+      // load per ~250 cycles (6), the real epilogue's rate
+      uint32_t acc = 0;
+      const uint32_t taddr = tmem + ((uint32_t)(warp_u * 32) << 16);
+      while (!*done_flag) {
+        uint32_t r[16];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+              "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+              "=r"(r[14]), "=r"(r[15])
+            : "r"(taddr + ((uint32_t)bytes & 0x1F0u))
+            : "memory");
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc += r[j];
+        bytes += 16 * 4 * 32;
+        if (bg == 6) __nanosleep(100);
+      }
+      if (acc == 0x12345u) printf("x");
+      if ((threadIdx.x & 31) == 0) atomicAdd((unsigned long long*)&bgbytes[blockIdx.x], (unsigned long long)bytes);
+    } else if (bg == 4) {
+      if (warp_u == 2) {
+        const uint32_t dst = smem_u32(scratch) + (threadIdx.x & 31) * 16;
+        uint32_t v = threadIdx.x;
+        while (!*done_flag) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst + (uint32_t)(u * 512)), "r"(v) : "memory");
+          bytes += 8 * 16;
+          ++v;
+        }
+        atomicAdd((unsigned long long*)&bgbytes[blockIdx.x], (unsigned long long)bytes);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+static void run_contend(int sms, long long* dcyc) {
+  // small global tensors for the TMA background stream (L2 resident)
+  const int D = 3, H = 24, W = 16;
+  uint16_t *d64, *d128;
+  uint4* gsrc;
+  long long* dbytes;
+  CK(cudaMalloc(&d64, (size_t)D * H * W * 32 * 2));
+  CK(cudaMalloc(&d128, (size_t)D * H * W * 64 * 2));
+  CK(cudaMalloc(&gsrc, 1024 * 64 * 16));
+  CK(cudaMalloc(&dbytes, sizeof(long long) * sms));
+  CK(cudaMemset(d64, 0, (size_t)D * H * W * 32 * 2));
+  CK(cudaMemset(d128, 0, (size_t)D * H * W * 64 * 2));
+  CK(cudaMemset(gsrc, 0, 1024 * 64 * 16));
+  CUtensorMap t64, t128;
+  for (int C : {32, 64}) {
+    uint64_t dims[5] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)D, 1};
+    uint64_t str[4] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2, (uint64_t)D * H * W * C * 2};
+    uint32_t box[5] = {(uint32_t)C, 10, 18, 1, 1};
+    Status st = make_tmap_bf16(C == 32 ? &t64 : &t128, C == 32 ? (void*)d64 : (void*)d128, 5, dims, str, box, C * 2);
+    if (!st.ok) { printf("tmap contend: %s\n", st.msg.c_str()); exit(2); }
+  }
+  const size_t smem_bytes = 196608 + 128 + 1024;
+  CK(cudaFuncSetAttribute(contend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  const int planes = 2048;
+  for (int bg = 0; bg <= 6; ++bg) {
+    CK(cudaMemset(dbytes, 0, sizeof(long long) * sms));
+    contend_kernel<<<sms, 128, smem_bytes>>>(t64, t128, gsrc, planes, bg, dcyc, dbytes);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("contend kernel error %s\n", cudaGetErrorString(e)); exit(3); }
+    std::vector<long long> h(sms), hb(sms);
+    CK(cudaMemcpy(h.data(), dcyc, sizeof(long long) * sms, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hb.data(), dbytes, sizeof(long long) * sms, cudaMemcpyDeviceToHost));
+    long long mx = 0; double bsum = 0;
+    for (auto v : h) mx = v > mx ? v : mx;
+    for (auto v : hb) bsum += (double)v;
+    const char* names[7] = {"none", "TMA 64B rows", "TMA 128B rows", "cp.async 16B", "st.shared.v4", "tcgen05.ld b2b", "tcgen05.ld paced"};
+    const double cyc = (double)mx / planes, bpp = bsum / sms / planes;
+    printf("CONTEND bg=%-14s : %.1f cyc/plane (alone 1008), background %.0f B/plane -> %.1f B per stolen cycle\n",
+           names[bg], cyc, bpp, cyc > 1009 ? bpp / (cyc - 1008.2) : 0.0);
+  }
 }
 
 template <int N, int ACCS>
@@ -475,9 +689,10 @@ int main() {
     run_rate_halo<96, 128, false>(sms, dcyc); run_rate_halo<96, 128, true>(sms, dcyc);
     run_rate_halo<96, 64, false>(sms, dcyc);  run_rate_halo<96, 64, true>(sms, dcyc);
     run_rate_halo<192, 128, false>(sms, dcyc); run_rate_halo<192, 128, true>(sms, dcyc);
-    run_loop<64, 0>(sms, dcyc); run_loop<64, 1>(sms, dcyc); run_loop<64, 2>(sms, dcyc); run_loop<64, 3>(sms, dcyc);
-    run_loop<64, 4>(sms, dcyc); run_loop<64, 5>(sms, dcyc); run_loop<64, 6>(sms, dcyc); run_loop<64, 7>(sms, dcyc);
-    run_loop<128, 0>(sms, dcyc); run_loop<128, 2>(sms, dcyc); run_loop<128, 4>(sms, dcyc); run_loop<128, 5>(sms, dcyc);
+    run_contend(sms, dcyc);
+    run_loop<64, 0>(sms, dcyc); run_loop<64, 2>(sms, dcyc); run_loop<64, 5>(sms, dcyc); run_loop<64, 7>(sms, dcyc);
+    run_loop<64, 8>(sms, dcyc); run_loop<64, 9>(sms, dcyc);
+    run_loop<128, 0>(sms, dcyc); run_loop<128, 5>(sms, dcyc);
     if (getenv("PROBE_RATE_ONLY")) { printf("PROBE DONE (rate only)\n"); return 0; }
     run_rate<32, 1>(sms, dcyc);  run_rate<32, 4>(sms, dcyc);
     run_rate<64, 1>(sms, dcyc);  run_rate<64, 4>(sms, dcyc);
