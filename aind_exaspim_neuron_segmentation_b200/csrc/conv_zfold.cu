@@ -1,6 +1,7 @@
 // Host launcher for the z-folded halo-tile tcgen05 conv (kernel in conv_zfold.cuh).
 #include "conv_zfold.cuh"
 
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "kernels.h"
@@ -102,6 +103,29 @@ Status launch_conv_zfold(const Act& in, const Act& out, const __nv_bfloat16* w_z
     static const char* dbg_env = getenv("EXA_ZF_DBG");  // development-only timing experiments
     a.dbg = dbg_env ? atoi(dbg_env) : 0;
   }
+  static long long* dbg_dev = nullptr;
+  if (a.dbg & 8) {
+    if (!dbg_dev) EXA_CUDA(cudaMalloc(&dbg_dev, sizeof(long long) * 4 * 1024));
+    EXA_CUDA(cudaMemsetAsync(dbg_dev, 0, sizeof(long long) * 4 * 1024, s));
+    a.dbg_out = dbg_dev;
+  }
+  struct DbgPrint {  // prints after the launch below (synchronises: development only)
+    bool on; int grid, cin, cout, head; cudaStream_t s; long long* dev;
+    ~DbgPrint() {
+      if (!on) return;
+      cudaStreamSynchronize(s);
+      static long long h[4 * 1024];
+      cudaMemcpy(h, dev, sizeof(long long) * 4 * grid, cudaMemcpyDeviceToHost);
+      double cyc = 0, ns = 0, pl = 0, mx = 0;
+      for (int i = 0; i < grid; ++i) {
+        cyc += (double)h[i * 4]; ns += (double)h[i * 4 + 1]; pl += (double)h[i * 4 + 2];
+        if ((double)h[i * 4] > mx) mx = (double)h[i * 4];
+      }
+      fprintf(stderr, "[zfold cin=%d cout=%d head=%d grid=%d] issuer: %.0f cycles/plane, %.0f planes/cta, "
+              "SM clock %.0f MHz, longest cta %.3f ms\n", cin, cout, head, grid, cyc / pl, pl / grid,
+              1e3 * cyc / ns, mx / (1e3 * cyc / ns) * 1e-3);
+    }
+  } dbg_print{(a.dbg & 8) != 0, grid, Cin, Cout, head != nullptr, s, dbg_dev};
   if (Cin == 32) {
     if (head) return launch_zf<32, EPI_HEAD>(tx, tw, a, grid, s);
     return launch_zf<32, EPI_STORE>(tx, tw, a, grid, s);

@@ -48,6 +48,7 @@ struct ZfArgs {
   float* head_out;           // [B][head_c][D-2t][H-2t][W-2t]
   int head_c, trim, apply_sigmoid;
   int dbg;                   // development only (EXA_ZF_DBG): timing experiments, wrong results
+  long long* dbg_out;        // dbg & 8: [gridDim.x][4] issuer {cycles, ns, planes, 0}
 };
 
 template <int CIN>
@@ -63,10 +64,10 @@ struct ZfSmem {
   static constexpr int TOTAL = W_BYTES + STAGES * A_STAGE + BAR_BYTES + 1024;
 };
 
-constexpr int ZF_RING = 16;      // TMEM slots of 32 fp32 columns
+constexpr int ZF_GROUPS = 5;     // TMEM accumulator groups of 3 x 32 fp32 columns (480 of 512)
 constexpr int ZF_THREADS = 384;  // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..11 epilogue
 
-// ---- UMMA shared-memory descriptors split in (lo, hi) words: only `lo` ever changes ------
+// ---- UMMA shared-memory descriptors: (lo, hi) words; only the start-address field changes --
 template <int ROWB>
 __device__ __forceinline__ constexpr uint32_t zf_desc_hi(int sbo_rows) {
   return (uint32_t)((sbo_rows * ROWB) >> 4)      // SBO             [32,46)
@@ -82,80 +83,24 @@ __device__ __forceinline__ uint64_t zf_join(uint32_t lo, uint32_t hi) {
   return d;
 }
 
-// All MMAs of one steady-state input plane (planes zi-1, zi, zi+1 all valid; zi+1 is touched
-// for the first time).  w = ring slot of plane zi-1.
-//   V == 0 (w <= 13): one N=96 group at column 32*w;
-//   V == 1 (w == 14): slots (14, 15 | 0);   V == 2 (w == 15): slots (15 | 0, 1).
-template <int CIN, int V>
-__device__ __forceinline__ void zf_issue_steady(uint32_t tmem_base, uint32_t w, uint32_t a_lo,
-                                                uint32_t w_lo) {
-  using S = ZfSmem<CIN>;
-  constexpr int ROWB = S::ROWB;
-  constexpr int KSTEPS = CIN / 16;
-  constexpr uint32_t A_HI = zf_desc_hi<ROWB>(10);  // halo view: 8-row groups are 10 rows apart
-  constexpr uint32_t B_HI = zf_desc_hi<ROWB>(8);
-  constexpr uint32_t I32 = umma_idesc_bf16(128, 32), I64 = umma_idesc_bf16(128, 64),
-                     I96 = umma_idesc_bf16(128, 96);
-  constexpr uint32_t BROW = (32 * ROWB) >> 4;  // descriptor units per 32 B rows (one kz block)
-  const uint32_t d0 = tmem_base + (V == 0 ? w * 32u : (V == 1 ? 448u : 480u));
-#pragma unroll
-  for (int t = 0; t < 9; ++t) {
-#pragma unroll
-    for (int k = 0; k < KSTEPS; ++k) {
-      const bool first = (t == 0 && k == 0);
-      // tap (ky,kx) shifts the halo view's start by ky*10+kx rows
-      const uint64_t ad = zf_join(a_lo + (uint32_t)((((t / 3) * 10 + (t % 3)) * ROWB + k * 32) >> 4), A_HI);
-      const uint32_t b = w_lo + (uint32_t)((t * S::W_TAP + k * 32) >> 4);
-      if (V == 0) {
-        if (first) {
-          umma_bf16(d0, ad, zf_join(b, B_HI), I64, 1u);
-          umma_bf16(d0 + 64u, ad, zf_join(b + 2 * BROW, B_HI), I32, 0u);
-        } else {
-          umma_bf16(d0, ad, zf_join(b, B_HI), I96, 1u);
-        }
-      } else if (V == 1) {
-        umma_bf16(d0, ad, zf_join(b, B_HI), I64, 1u);
-        umma_bf16(tmem_base, ad, zf_join(b + 2 * BROW, B_HI), I32, first ? 0u : 1u);
-      } else {
-        umma_bf16(d0, ad, zf_join(b, B_HI), I32, 1u);
-        if (first) {
-          umma_bf16(tmem_base, ad, zf_join(b + BROW, B_HI), I32, 1u);
-          umma_bf16(tmem_base + 32u, ad, zf_join(b + 2 * BROW, B_HI), I32, 0u);
-        } else {
-          umma_bf16(tmem_base, ad, zf_join(b + BROW, B_HI), I64, 1u);
-        }
-      }
-    }
-  }
-}
-
-// Edge planes of a column (first/last input planes: some of zi-1, zi, zi+1 are outside the
-// output range): one N=32 MMA per valid z tap.  Four planes per column, so speed is secondary.
+// All MMAs of one input plane: 9 taps x CIN/16 k-steps, each M=128, N=96, into the plane's own
+// accumulator group (columns d0 .. d0+95 = partial sums of output planes z-1, z, z+1).  The first
+// MMA overwrites, so groups need no zeroing and no plane is special.
 template <int CIN>
-__device__ __noinline__ void zf_issue_edge(uint32_t tmem_base, uint32_t a_lo, uint32_t w_lo,
-                                           uint32_t col0, uint32_t col1, uint32_t col2,
-                                           uint32_t flags) {
+__device__ __forceinline__ void zf_issue_plane(uint32_t d0, uint64_t a_desc, uint64_t w_desc) {
   using S = ZfSmem<CIN>;
   constexpr int ROWB = S::ROWB;
   constexpr int KSTEPS = CIN / 16;
-  constexpr uint32_t A_HI = zf_desc_hi<ROWB>(10);
-  constexpr uint32_t B_HI = zf_desc_hi<ROWB>(8);
-  constexpr uint32_t I32 = umma_idesc_bf16(128, 32);
-  constexpr uint32_t BROW = (32 * ROWB) >> 4;
-  const uint32_t col[3] = {col0, col1, col2};
-#pragma unroll 1
+  constexpr uint32_t I96 = umma_idesc_bf16(128, 96);
+#pragma unroll
   for (int t = 0; t < 9; ++t) {
 #pragma unroll
     for (int k = 0; k < KSTEPS; ++k) {
-      const uint64_t ad = zf_join(a_lo + (uint32_t)((((t / 3) * 10 + (t % 3)) * ROWB + k * 32) >> 4), A_HI);
-      const uint32_t b = w_lo + (uint32_t)((t * S::W_TAP + k * 32) >> 4);
-#pragma unroll
-      for (int kzr = 0; kzr < 3; ++kzr) {
-        if (flags & (1u << kzr)) {  // valid
-          const uint32_t acc = (t == 0 && k == 0 && (flags & (8u << kzr))) ? 0u : 1u;  // fresh
-          umma_bf16(tmem_base + col[kzr], ad, zf_join(b + kzr * BROW, B_HI), I32, acc);
-        }
-      }
+      // tap (ky,kx) shifts the halo view's start by ky*10+kx rows; the start-address field never
+      // carries out of its 14 bits, so plain 64-bit adds of small immediates are exact
+      const uint64_t ad = a_desc + (uint64_t)((((t / 3) * 10 + (t % 3)) * ROWB + k * 32) >> 4);
+      const uint64_t bd = w_desc + (uint64_t)((t * S::W_TAP + k * 32) >> 4);
+      umma_bf16(d0, ad, bd, I96, (t == 0 && k == 0) ? 0u : 1u);
     }
   }
 }
@@ -183,20 +128,19 @@ conv3x3_zfold_kernel(const __grid_constant__ CUtensorMap tmap_x,
                      const __grid_constant__ CUtensorMap tmap_w, const ZfArgs p) {
   using S = ZfSmem<CIN>;
   constexpr int STAGES = S::STAGES;
-  // epilogue arrivals per TMEM slot: EPI_STORE splits the 32 columns over two warps per lane
-  // quarter (8 warps touch every plane); EPI_HEAD alternates planes between the two warp sets
-  constexpr uint32_t TEMPTY_COUNT = EPI == EPI_STORE ? 8 : 4;
+  // every epilogue warp releases every accumulator group once per use
+  constexpr uint32_t TEMPTY_COUNT = 8;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_w = smem;
   uint8_t* smem_a = smem + S::W_BYTES;
   uint64_t* bars = (uint64_t*)(smem_a + STAGES * S::A_STAGE);
-  uint64_t* full_bar = bars;                          // [STAGES] TMA -> MMA
-  uint64_t* empty_bar = bars + STAGES;                // [STAGES] MMA -> TMA
-  uint64_t* tfull_bar = bars + 2 * STAGES;            // [16] MMA -> epilogue (slot complete)
-  uint64_t* tempty_bar = bars + 2 * STAGES + ZF_RING; // [16] epilogue -> TMA producer (slot drained)
-  uint64_t* w_bar = bars + 2 * STAGES + 2 * ZF_RING;  // weights resident
+  uint64_t* full_bar = bars;                             // [STAGES] TMA -> MMA
+  uint64_t* empty_bar = bars + STAGES;                   // [STAGES] MMA -> TMA
+  uint64_t* tfull_bar = bars + 2 * STAGES;               // [5] MMA -> epilogue (group complete)
+  uint64_t* tempty_bar = bars + 2 * STAGES + ZF_GROUPS;  // [5] epilogue -> MMA (group drained)
+  uint64_t* w_bar = bars + 2 * STAGES + 2 * ZF_GROUPS;   // weights resident
   uint32_t* tmem_slot = (uint32_t*)(w_bar + 1);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -209,7 +153,7 @@ conv3x3_zfold_kernel(const __grid_constant__ CUtensorMap tmap_x,
       mbar_init(smem_u32(&full_bar[s]), 1);
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
-    for (int s = 0; s < ZF_RING; ++s) {
+    for (int s = 0; s < ZF_GROUPS; ++s) {
       mbar_init(smem_u32(&tfull_bar[s]), 1);
       mbar_init(smem_u32(&tempty_bar[s]), TEMPTY_COUNT);
     }
@@ -231,9 +175,15 @@ conv3x3_zfold_kernel(const __grid_constant__ CUtensorMap tmap_x,
   const int cta_in_class = blockIdx.x / p.n_halves;
   const int ctas_per_class = gridDim.x / p.n_halves;
   const int tiles_per_b = p.nty * p.ntx;
-  const int zin0 = max(p.oz - 1, 0);
-  const int zin1 = min(p.oz + p.nzp + 1, p.D);
+  const int zin0 = max(p.oz - 1, 0);               // input planes [zin0, zin1) feed the
+  const int zin1 = min(p.oz + p.nzp + 1, p.D);     // output planes [oz, oz + nzp)
+  const int nin = zin1 - zin0;
   const int zend = p.oz + p.nzp;
+  const int my_tiles = cta_in_class < p.tiles_total
+                           ? (p.tiles_total - cta_in_class + ctas_per_class - 1) / ctas_per_class
+                           : 0;
+  // Input planes of this CTA are numbered consecutively across its tiles: gi = tile * nin +
+  // (z - zin0).  Plane gi uses shared-memory stage gi % STAGES and accumulator group gi % 5.
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -250,26 +200,12 @@ conv3x3_zfold_kernel(const __grid_constant__ CUtensorMap tmap_x,
       }
       int stage = 0;
       uint32_t phase = 0;
-      uint32_t gbase = 0;  // running count of output planes handled by this CTA
       for (int tile = cta_in_class; tile < p.tiles_total; tile += ctas_per_class) {
         const int b = tile / tiles_per_b;
         const int r = tile - b * tiles_per_b;
         const int ty = r / p.ntx, tx = r - ty * p.ntx;
         const int x0 = p.ox + tx * 8, y0 = p.oy + ty * 16;
         for (int zi = zin0; zi < zin1; ++zi) {
-          // TMEM slots first touched by the MMAs of input plane zi (plane zi+1; at the first
-          // input plane also plane zi) must have been drained by the epilogue.  Doing this
-          // hand-shake here keeps it off the MMA issuer's critical path.
-          if (!(p.dbg & 4)) {
-            if (zi == zin0 && zi >= p.oz) {
-              const uint32_t g = gbase + (uint32_t)(zi - p.oz);
-              mbar_wait(smem_u32(&tempty_bar[g % ZF_RING]), ((g / ZF_RING) & 1u) ^ 1u);
-            }
-            if (zi + 1 >= p.oz && zi + 1 < zend) {
-              const uint32_t g = gbase + (uint32_t)(zi + 1 - p.oz);
-              mbar_wait(smem_u32(&tempty_bar[g % ZF_RING]), ((g / ZF_RING) & 1u) ^ 1u);
-            }
-          }
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
           const uint32_t fb = smem_u32(&full_bar[stage]);
           mbar_expect_tx(fb, (uint32_t)S::A_TX_BYTES);
@@ -279,111 +215,95 @@ conv3x3_zfold_kernel(const __grid_constant__ CUtensorMap tmap_x,
             phase ^= 1u;
           }
         }
-        gbase += (uint32_t)p.nzp;
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    // Two disjoint sets of loop-carried variables: the descriptor / TMEM column / commit-address
-    // chain (`a_lo`, `ea`, `w`: add + wrap, nothing derived from the barrier variables) and the
-    // mbarrier probe chain (`fa`, `phase`); the probe result is consumed one plane later.
+    // Every input plane is the same straight-line sequence.  Two disjoint sets of loop-carried
+    // variables: the descriptor / TMEM column / commit-address chain (`a_desc`, `ea`, `d0`, `tfa`:
+    // add + wrap) and the mbarrier probe chains (`fa`, `fph`: TMA data; `ta`, `tph`: accumulator
+    // group drained); each probe result is consumed one plane later.
     if (elect_one()) {
       mbar_wait(smem_u32(w_bar), 0);
       tc_fence_after();
-      const uint32_t w_lo_c = zf_desc_lo(smem_u32(smem_w));
-      const uint32_t a_lo0 = zf_desc_lo(smem_u32(smem_a));
-      const uint32_t a_lo_end = a_lo0 + (uint32_t)STAGES * (uint32_t)(S::A_STAGE >> 4);
+      constexpr int ROWB = S::ROWB;
+      // halo view: 8-row groups are 10 rows apart (A); weights: plain 8-row groups (B)
+      const uint64_t w_desc_c = zf_join(zf_desc_lo(smem_u32(smem_w)), zf_desc_hi<ROWB>(8));
+      const uint64_t a_desc0 = zf_join(zf_desc_lo(smem_u32(smem_a)), zf_desc_hi<ROWB>(10));
+      const uint64_t a_desc_end = a_desc0 + (uint64_t)STAGES * (uint64_t)(S::A_STAGE >> 4);
       const uint32_t bar0 = smem_u32(bars);
-      const uint32_t fa_end = bar0 + (uint32_t)STAGES * 8u;        // == &empty_bar[0]
-      const uint32_t ea_end = bar0 + 2u * (uint32_t)STAGES * 8u;   // == &tfull_bar[0]
-      const uint32_t tfull0 = ea_end;
-      const int my_tiles = cta_in_class < p.tiles_total
-                               ? (p.tiles_total - cta_in_class + ctas_per_class - 1) / ctas_per_class
-                               : 0;
-      const int oz = p.oz, nzp = p.nzp;
-      const int n_steady = nzp - 2;
+      const uint32_t empty0 = bar0 + (uint32_t)STAGES * 8u;
+      const uint32_t tfull0 = bar0 + 2u * (uint32_t)STAGES * 8u;
+      const uint32_t tempty0 = tfull0 + (uint32_t)ZF_GROUPS * 8u;
+      const uint32_t tempty_end = tempty0 + (uint32_t)ZF_GROUPS * 8u;
       const bool nowait = (p.dbg & 2) != 0;
-      uint32_t a_lo = a_lo0;    // descriptor word of the current A stage        (uniform chain)
-      uint32_t ea = fa_end;     // empty_bar of the current stage                (uniform chain)
-      uint32_t w = 15u;         // ring slot of plane zi-1                       (uniform chain)
-      uint32_t fa = bar0;       // full_bar of the current stage                 (probe chain)
-      uint32_t phase = 0;       //                                               (probe chain)
-      bool tok = false;         // full_bar of the current stage already seen complete (peeked)
+      uint64_t a_desc = a_desc0;     // descriptor of the current A stage
+      uint32_t ea = empty0;          // empty_bar of the current stage
+      uint32_t d0 = tmem_base;       // first column of the current accumulator group
+      uint32_t tfa = tfull0;         // tfull_bar of the current group
+      uint32_t fa = bar0, fph = 0;   // probe chain: full_bar of the current stage
+      uint32_t ta = tempty0, tph = 1;  // probe chain: tempty_bar of the current group (first
+                                       // round: parity 1 passes on a fresh barrier)
+      bool ftok = false, ttok = false;  // already seen complete (probed one plane ahead)
 
-      // wait for the TMA data of the current stage; probe the next stage now and consume the
-      // answer one plane later
-      auto acquire = [&]() {
-        if (!tok && !nowait) mbar_wait(fa, phase);
+      long long dbg_c0 = 0, dbg_t0 = 0;
+      if (p.dbg & 8) {
+        dbg_c0 = clock64();
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
+      }
+      const int total = my_tiles * nin;
+      for (int it = 0; it < total; ++it) {
+        if (!ftok && !nowait) mbar_wait(fa, fph);
+        if (!ttok && !nowait) mbar_wait(ta, tph);
+        // probe the next plane's barriers now, consume the answers one plane later
         fa += 8u;
-        if (fa == fa_end) {
+        if (fa == empty0) {
           fa = bar0;
-          phase ^= 1u;
+          fph ^= 1u;
         }
-        tok = mbar_test_wait(fa, phase);
+        ta += 8u;
+        if (ta == tempty_end) {
+          ta = tempty0;
+          tph ^= 1u;
+        }
+        ftok = mbar_test_wait(fa, fph);
+        ttok = mbar_test_wait(ta, tph);
         tc_fence_after();
-      };
-      auto next_stage = [&]() {
-        umma_commit(ea);  // stage consumed once the MMAs issued so far retire
+        // keep the 18..36 weight descriptors `base + immediate` instead of letting the compiler
+        // hoist them into dozens of loop-invariant registers
+        uint64_t w_desc = w_desc_c;
+        asm volatile("" : "+l"(w_desc));
+        zf_issue_plane<CIN>(d0, a_desc, w_desc);
+        umma_commit(ea);   // shared-memory stage consumed once these MMAs retire
+        umma_commit(tfa);  // accumulator group complete
         ea += 8u;
-        a_lo += (uint32_t)(S::A_STAGE >> 4);
-        if (a_lo == a_lo_end) {
-          a_lo = a_lo0;
-          ea = fa_end;
+        a_desc += (uint64_t)(S::A_STAGE >> 4);
+        if (a_desc == a_desc_end) {
+          a_desc = a_desc0;
+          ea = empty0;
         }
-      };
-      // first/last input planes of a column: some of zi-1, zi, zi+1 are not output planes
-      auto edge_plane = [&](int zi) {
-        acquire();
-        uint32_t w_lo = w_lo_c;
-        asm volatile("" : "+r"(w_lo));
-        uint32_t flags = 0;
-#pragma unroll
-        for (int kzr = 0; kzr < 3; ++kzr) {
-          const int po = zi - 1 + kzr;
-          if (po >= oz && po < zend) {
-            flags |= 1u << kzr;
-            if (zi == max(po - 1, zin0)) flags |= 8u << kzr;  // first touch of this slot
-          }
+        tfa += 8u;
+        d0 += 96u;
+        if (tfa == tempty0) {
+          tfa = tfull0;
+          d0 = tmem_base;
         }
-        zf_issue_edge<CIN>(tmem_base, a_lo, w_lo, w * 32u, ((w + 1u) % ZF_RING) * 32u,
-                           ((w + 2u) % ZF_RING) * 32u, flags);
-        next_stage();
-        // completed output planes: zi-1 always; zi too when it is the last input plane
-        if (zi > oz && zi - 1 < zend) umma_commit(tfull0 + w * 8u);
-        if (zi == zin1 - 1 && zi >= oz && zi < zend) umma_commit(tfull0 + ((w + 1u) % ZF_RING) * 8u);
-        w = (w + 1u) % ZF_RING;
-      };
-
-      for (int tl = 0; tl < my_tiles; ++tl) {
-        // ring slot of plane zin0-1: plane oz sits at slot (tl*nzp) % 16
-        w = ((uint32_t)tl * (uint32_t)nzp + (uint32_t)(zin0 - 1 - oz)) % ZF_RING;
-        int zi = zin0;
-        for (; zi <= oz && zi < zin1; ++zi) edge_plane(zi);
-        for (int i = 0; i < n_steady; ++i) {
-          acquire();
-          // keep the 18..36 weight descriptors `base + immediate` instead of letting the
-          // compiler hoist them into dozens of loop-invariant registers
-          uint32_t w_lo = w_lo_c;
-          asm volatile("" : "+r"(w_lo));
-          if (w <= 13u) {
-            zf_issue_steady<CIN, 0>(tmem_base, w, a_lo, w_lo);
-          } else if (w == 14u) {
-            zf_issue_steady<CIN, 1>(tmem_base, w, a_lo, w_lo);
-          } else {
-            zf_issue_steady<CIN, 2>(tmem_base, w, a_lo, w_lo);
-          }
-          next_stage();
-          umma_commit(tfull0 + w * 8u);  // plane zi-1 is complete
-          w = (w + 1u) % ZF_RING;
-        }
-        zi += n_steady > 0 ? n_steady : 0;
-        for (; zi < zin1; ++zi) edge_plane(zi);
+      }
+      if (p.dbg & 8) {
+        long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        long long* d = p.dbg_out + (size_t)blockIdx.x * 4;
+        d[0] = clock64() - dbg_c0;
+        d[1] = t1 - dbg_t0;
+        d[2] = (long long)total;
       }
     }
     __syncwarp();
   } else if (warp >= 4) {
     // ===================== epilogue: 8 warps, two per TMEM lane quarter =====================
+    // Output plane po = sum of up to three partials: columns [64,96) of input plane po-1's group,
+    // [32,64) of plane po's and [0,32) of plane po+1's.
     const int q = warp & 3;          // TMEM lane quarter this warp may access
     const int hs = (warp - 4) >> 2;  // 0/1: column half (EPI_STORE) or plane parity (EPI_HEAD)
     const int row = q * 32 + lane;
@@ -391,8 +311,58 @@ conv3x3_zfold_kernel(const __grid_constant__ CUtensorMap tmap_x,
     const uint32_t tfull0 = smem_u32(tfull_bar), tempty0 = smem_u32(tempty_bar);
     const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     const bool skip = (p.dbg & 1) != 0;
-    uint32_t gbase = 0;
+    constexpr int NC = EPI == EPI_STORE ? 16 : 32;    // accumulator columns per thread
+    const uint32_t col_off = EPI == EPI_STORE ? (uint32_t)(hs * 16) : 0u;
 
+    // wait for the partials of output plane po and sum them into v[]  (gi0 = number of this
+    // tile's first input plane)
+    auto gather_plane = [&](uint32_t gi0, int po, float (&v)[NC]) {
+      const int zl = po + 1 < zin1 ? po + 1 : po;  // latest contributing input plane
+      {
+        const uint32_t gi = gi0 + (uint32_t)(zl - zin0);
+        mbar_wait(tfull0 + (gi % ZF_GROUPS) * 8u, (gi / ZF_GROUPS) & 1u);
+        tc_fence_after();
+      }
+#pragma unroll
+      for (int j = 0; j < NC; ++j) v[j] = 0.f;
+      if (!skip) {
+#pragma unroll
+        for (int dz = -1; dz <= 1; ++dz) {
+          const int z = po + dz;
+          if (z >= zin0 && z < zin1) {
+            const uint32_t gi = gi0 + (uint32_t)(z - zin0);
+            const uint32_t taddr =
+                tmem_lane + (gi % ZF_GROUPS) * 96u + (uint32_t)((1 - dz) * 32) + col_off;
+            uint32_t acc[NC];
+            if constexpr (NC == 16) tmem_ld_32x16(taddr, acc);
+            else tmem_ld_32x32(taddr, acc);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < NC; ++j) v[j] += __uint_as_float(acc[j]);
+          }
+        }
+      }
+      tc_fence_before();
+    };
+    // Release rule, executed by EVERY epilogue warp for EVERY output plane po in order (also for
+    // planes whose partials the warp does not read): after plane po this warp will not read the
+    // group of input plane po-1 again; after the column's last plane nor those of planes po, po+1.
+    auto release_plane = [&](uint32_t gi0, int po) {
+      __syncwarp();
+      if (lane == 0) {
+        if (po - 1 >= zin0) {
+          const uint32_t gi = gi0 + (uint32_t)(po - 1 - zin0);
+          mbar_arrive(tempty0 + (gi % ZF_GROUPS) * 8u);
+        }
+        if (po == zend - 1) {
+          const uint32_t gi = gi0 + (uint32_t)(po - zin0);
+          mbar_arrive(tempty0 + (gi % ZF_GROUPS) * 8u);
+          if (po + 1 < zin1) mbar_arrive(tempty0 + ((gi + 1u) % ZF_GROUPS) * 8u);
+        }
+      }
+    };
+
+    uint32_t gi0 = 0;  // number of this tile's first input plane
     if constexpr (EPI == EPI_STORE) {
       const int n0 = half * 32 + hs * 16;
       float bias[16];
@@ -401,31 +371,18 @@ conv3x3_zfold_kernel(const __grid_constant__ CUtensorMap tmap_x,
       const size_t plane_elems = (size_t)p.H * p.W * p.out_cstride;
       const bool pool = p.pool_out != nullptr;
 
-      // one plane: TMEM -> registers -> bias + LeakyReLU -> bf16 -> one 32 B store per voxel
-      auto do_plane = [&](uint32_t g, __nv_bfloat16* dst, bool in_xy, uint32_t (&pk)[8]) {
-        const uint32_t slot = g % ZF_RING;
-        mbar_wait(tfull0 + slot * 8u, (g / ZF_RING) & 1u);
-        tc_fence_after();
-        if (skip) {
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tempty0 + slot * 8u);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) pk[j] = 0;
-          return;
-        }
-        uint32_t acc[16];
-        tmem_ld_32x16(tmem_lane + slot * 32u + (uint32_t)(hs * 16), acc);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty0 + slot * 8u);  // slot is in registers now
+      // one plane: partial sums -> bias + LeakyReLU -> bf16 -> one 32 B store per voxel
+      auto do_plane = [&](int po, __nv_bfloat16* dst, bool in_xy, uint32_t (&pk)[8]) {
+        float v[16];
+        gather_plane(gi0, po, v);
+        release_plane(gi0, po);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float a = leaky_relu(__uint_as_float(acc[2 * j]) + bias[2 * j]);
-          const float c = leaky_relu(__uint_as_float(acc[2 * j + 1]) + bias[2 * j + 1]);
+          const float a = leaky_relu(v[2 * j] + bias[2 * j]);
+          const float c = leaky_relu(v[2 * j + 1] + bias[2 * j + 1]);
           pk[j] = pack_bf16x2(a, c);
         }
-        if (in_xy) st_global_256(dst, pk);
+        if (in_xy && !skip) st_global_256(dst, pk);
       };
 
       for (int tile = cta_in_class; tile < p.tiles_total; tile += ctas_per_class) {
@@ -437,9 +394,9 @@ conv3x3_zfold_kernel(const __grid_constant__ CUtensorMap tmap_x,
         __nv_bfloat16* dst = p.out + ((((size_t)b * p.D + p.oz) * p.H + y) * p.W + x) * p.out_cstride +
                              p.out_coff + n0;
         if (!pool) {
-          for (int i = 0; i < p.nzp; ++i) {
+          for (int po = p.oz; po < zend; ++po) {
             uint32_t pk[8];
-            do_plane(gbase + (uint32_t)i, dst, in_xy, pk);
+            do_plane(po, dst, in_xy, pk);
             dst += plane_elems;
           }
         } else {
@@ -451,11 +408,11 @@ conv3x3_zfold_kernel(const __grid_constant__ CUtensorMap tmap_x,
                   p.pool_cstride +
               p.pool_coff + n0;
           const size_t pplane = (size_t)(p.H >> 1) * (p.W >> 1) * p.pool_cstride;
-          for (int i = 0; i < p.nzp; i += 2) {
+          for (int po = p.oz; po < zend; po += 2) {
             uint32_t pa[8], pb[8];
-            do_plane(gbase + (uint32_t)i, dst, in_xy, pa);
+            do_plane(po, dst, in_xy, pa);
             dst += plane_elems;
-            do_plane(gbase + (uint32_t)i + 1u, dst, in_xy, pb);
+            do_plane(po + 1, dst, in_xy, pb);
             dst += plane_elems;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -473,7 +430,7 @@ conv3x3_zfold_kernel(const __grid_constant__ CUtensorMap tmap_x,
             pdst += pplane;
           }
         }
-        gbase += (uint32_t)p.nzp;
+        gi0 += (uint32_t)nin;
       }
     } else {
       // fused 1x1x1 head (+sigmoid) and trim: every thread needs all 32 channels of its voxel,
@@ -490,24 +447,17 @@ conv3x3_zfold_kernel(const __grid_constant__ CUtensorMap tmap_x,
         const int ty = r / p.ntx, tx = r - ty * p.ntx;
         const int x = p.ox + tx * 8 + rx, y = p.oy + ty * 16 + ry;
         const bool keep_xy = x >= t && x < p.W - t && y >= t && y < p.H - t;
-        for (int i = hs; i < p.nzp; i += 2) {
-          const uint32_t g = gbase + (uint32_t)i;
-          const uint32_t slot = g % ZF_RING;
-          const int po = p.oz + i;
-          mbar_wait(tfull0 + slot * 8u, (g / ZF_RING) & 1u);
-          tc_fence_after();
-          uint32_t acc[32];
-          if (!skip) {
-            tmem_ld_32x32(tmem_lane + slot * 32u, acc);
-            tmem_ld_wait();
+        for (int po = p.oz; po < zend; ++po) {
+          if (((po - p.oz) & 1) != hs) {  // the other warp set's plane
+            release_plane(gi0, po);
+            continue;
           }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tempty0 + slot * 8u);
+          float v[32];
+          gather_plane(gi0, po, v);
+          release_plane(gi0, po);
           if (!skip && keep_xy && po >= t && po < p.D - t) {
-            float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = leaky_relu(__uint_as_float(acc[j]) + bias[j]);
+            for (int j = 0; j < 32; ++j) v[j] = leaky_relu(v[j] + bias[j]);
             float* o = p.head_out + (size_t)b * p.head_c * cstride +
                        ((size_t)(po - t) * Hy + (y - t)) * Wx + (x - t);
             for (int oc = 0; oc < p.head_c; ++oc) {
@@ -519,7 +469,7 @@ conv3x3_zfold_kernel(const __grid_constant__ CUtensorMap tmap_x,
             }
           }
         }
-        gbase += (uint32_t)p.nzp;
+        gi0 += (uint32_t)nin;
       }
     }
   }

@@ -38,6 +38,7 @@ struct ProbeArgs {
   int use_base_offset;
   int b_row_off;    // B descriptor starts at this row (multiple of 8)
   float* out;       // [128][n]
+  int dcol;         // first accumulator column (TMEM wrap-around test when dcol + n > 512)
 };
 
 template <int ROW_BYTES>
@@ -59,7 +60,7 @@ probe_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
     mbar_fence_init();
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(tmem_slot), 256);
+    tmem_alloc(smem_u32(tmem_slot), 512);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -91,7 +92,7 @@ probe_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
     }
     uint64_t bdesc = umma_smem_desc<ROW_BYTES>(smem_u32(sB) + a.b_row_off * ROW_BYTES);
     const uint32_t idesc = umma_idesc_bf16(128, a.n);
-    for (int k = 0; k < KC / 16; ++k) umma_bf16(tmem, adesc + 2 * k, bdesc + 2 * k, idesc, k > 0);
+    for (int k = 0; k < KC / 16; ++k) umma_bf16(tmem + (uint32_t)a.dcol, adesc + 2 * k, bdesc + 2 * k, idesc, k > 0);
     umma_commit(smem_u32(&bars[1]));
   }
   __syncwarp();
@@ -100,13 +101,13 @@ probe_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
   const int row = warp * 32 + lane;
   for (int c0 = 0; c0 < a.n; c0 += 32) {
     uint32_t r[32];
-    tmem_ld_32x32(tmem + ((uint32_t)(warp * 32) << 16) + c0, r);
+    tmem_ld_32x32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)((a.dcol + c0) % 512), r);
     tmem_ld_wait();
     for (int j = 0; j < 32; ++j) a.out[row * a.n + c0 + j] = __uint_as_float(r[j]);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 256);
+  if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
 // ---- issue-rate probe ------------------------------------------------------
@@ -631,10 +632,10 @@ int main() {
 
     // tile origin (x0,y0) = (0,0) so the halo box starts at (-1,-1): exercises OOB zero fill,
     // and H=24 > 16+1, W=16 > 8+1 so the far halo is real data.
-    auto run = [&](int halo, int ky, int kx, int z, int n, int use_bo, int b_row_off, const char* name) {
+    auto run = [&](int halo, int ky, int kx, int z, int n, int use_bo, int b_row_off, const char* name, int dcol = 0) {
       ProbeArgs a;
       a.halo = halo; a.ky = ky; a.kx = kx; a.z = z; a.tap = (ky * 3 + kx); a.n = n;
-      a.use_base_offset = use_bo; a.b_row_off = b_row_off; a.out = dout;
+      a.use_base_offset = use_bo; a.b_row_off = b_row_off; a.out = dout; a.dcol = dcol;
       CK(cudaMemset(dout, 0xff, 128 * 256 * 4));
       if (rb == 128) probe_kernel<128><<<1, 128, smem_bytes>>>(halo ? tx_halo : tx_plain, tw, a);
       else probe_kernel<64><<<1, 128, smem_bytes>>>(halo ? tx_halo : tx_plain, tw, a);
@@ -669,6 +670,8 @@ int main() {
     for (int n : {32, 64, 96, 128, 256}) failures += run(0, 1, 1, 1, n, 0, 0, "plain") ? 1 : 0;
     failures += run(0, 0, 0, 0, 32, 0, 0, "plain/oob") ? 1 : 0;
     failures += run(0, 2, 2, 2, 64, 0, 32, "plain/b_row_off") ? 1 : 0;
+    failures += run(0, 1, 1, 1, 96, 0, 0, "plain/dcol=416", 416) ? 1 : 0;
+    { int bad = run(0, 1, 1, 1, 96, 0, 0, "TMEM column wrap dcol=480", 480); printf("[rb=%3d] TMEM accumulator window 480..575 %s\n", rb, bad ? "does NOT wrap to 0..63" : "WRAPS to columns 0..63"); }
     // 2. halo view, base_offset = 0
     int halo_bad0 = 0, halo_bad1 = 0;
     for (int ky = 0; ky < 3; ++ky)
