@@ -1,5 +1,6 @@
 // Host launcher for the z-folded halo-tile tcgen05 conv (kernel in conv_zfold.cuh).
 #include "conv_zfold.cuh"
+#include "conv_zfold2.cuh"
 
 #include <stdio.h>
 #include <stdlib.h>
@@ -26,19 +27,35 @@ Status launch_zf(const CUtensorMap& tx, const CUtensorMap& tw, const ZfArgs& a, 
   return Status::OK();
 }
 
+template <int CIN, int EPI>
+Status launch_zf2(const CUtensorMap& tx, const CUtensorMap& tw, const ZfArgs& a, int grid,
+                  cudaStream_t s) {
+  using S = Zf2Smem<CIN>;
+  static bool configured = false;
+  if (!configured) {
+    EXA_CUDA(cudaFuncSetAttribute(conv3x3_zfold2_kernel<CIN, EPI>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    configured = true;
+  }
+  conv3x3_zfold2_kernel<CIN, EPI><<<grid, ZF_THREADS, S::TOTAL, s>>>(tx, tw, a);  // clusters of 2
+  EXA_CUDA(cudaGetLastError());
+  return Status::OK();
+}
+
 }  // namespace
 
-bool conv_zfold_supported(const Act& in, int cout) {
-  return !in.fp32 && (in.C == 32 || in.C == 64) && (cout == 32 || cout == 64) &&
-         in.W % 8 == 0 && in.H % 16 == 0 && in.D >= 2;
+bool conv_zfold_supported(const Act& in, int cout, bool pair) {
+  const bool cin_ok = in.C == 32 || in.C == 64 || (pair && in.C == 128);
+  return !in.fp32 && cin_ok && (cout == 32 || cout == 64) && in.W % 8 == 0 && in.H % 16 == 0 &&
+         in.D >= 2;
 }
 
 // w_zfold: bf16 [9 taps (ky,kx)][3 (kz = 2,1,0)][Cout][Cin]
 Status launch_conv_zfold(const Act& in, const Act& out, const __nv_bfloat16* w_zfold,
                          const float* bias, const HeadParams* head, const ConvRegion* region,
-                         const Act* pool_out, int num_sms, cudaStream_t s) {
+                         const Act* pool_out, int num_sms, bool pair, cudaStream_t s) {
   const int Cin = in.C, Cout = head ? 32 : out.C;
-  EXA_CHECK(conv_zfold_supported(in, Cout), "conv_zfold: unsupported layer shape");
+  EXA_CHECK(conv_zfold_supported(in, Cout, pair), "conv_zfold: unsupported layer shape");
   ZfArgs a{};
   a.B = in.B; a.D = in.D; a.H = in.H; a.W = in.W;
   int x0 = 0, x1 = in.W, y0 = 0, y1 = in.H, z0 = 0, z1 = in.D;
@@ -59,7 +76,13 @@ Status launch_conv_zfold(const Act& in, const Act& out, const __nv_bfloat16* w_z
   a.bias = bias;
   if (head) {
     EXA_CHECK(Cout == 32, "fused head needs Cout == 32");
-    a.head_w = head->w; a.head_b = head->b; a.head_out = head->out;
+    EXA_CHECK(head->C >= 1 && head->C <= 8 && head->w_host && head->b_host,
+              "conv_zfold: fused head needs 1..8 channels and host weights");
+    for (int oc = 0; oc < head->C; ++oc) {
+      for (int j = 0; j < 32; ++j) a.head_w[oc][j] = head->w_host[oc * 32 + j];
+      a.head_b[oc] = head->b_host[oc];
+    }
+    a.head_out = head->out;
     a.head_c = head->C; a.trim = head->trim; a.apply_sigmoid = head->apply_sigmoid;
   } else {
     EXA_CHECK(!out.fp32 && out.B == in.B && out.D == in.D && out.H == in.H && out.W == in.W,
@@ -79,26 +102,37 @@ Status launch_conv_zfold(const Act& in, const Act& out, const __nv_bfloat16* w_z
   }
 
   CUtensorMap tx, tw;
+  // pair mode (conv_zfold2.cuh): channel boxes of at most 64 (128 B swizzle span), weight rows in
+  // chunks of 16 so that each CTA of a pair can fetch its 48 of the 96 [kz][cout] rows
+  const int cbox = pair && Cin > 64 ? 64 : Cin;
   {
-    // activations: 5-D (C, W, H, D, B), box = (Cin, 10, 18, 1, 1): the halo tile of one plane
+    // activations: 5-D (C, W, H, D, B), box = (cbox, 10, 18, 1, 1): the halo tile of one plane
     const uint64_t cs = (uint64_t)in.cstride * 2;
     uint64_t dims[5] = {(uint64_t)Cin, (uint64_t)in.W, (uint64_t)in.H, (uint64_t)in.D,
                         (uint64_t)in.B};
     uint64_t strides[4] = {cs, cs * in.W, cs * in.W * in.H, cs * in.W * in.H * in.D};
-    uint32_t box[5] = {(uint32_t)Cin, 10, 18, 1, 1};
+    uint32_t box[5] = {(uint32_t)cbox, 10, 18, 1, 1};
     void* base = (void*)((__nv_bfloat16*)in.ptr + in.coff);
-    EXA_TRY(make_tmap_bf16(&tx, base, 5, dims, strides, box, Cin * 2));
+    EXA_TRY(make_tmap_bf16(&tx, base, 5, dims, strides, box, cbox * 2));
   }
   {
-    // weights: 4-D (Cin, Cout, 3, 9), box = (Cin, 32, 3, 1): one tap, one 32-channel slice
+    // weights: 4-D (Cin, Cout, 3, 9); box = (Cin, 32, 3, 1): one tap, one 32-channel slice;
+    // pair mode: box = (cbox, 16, 1, 1)
     uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Cout, 3, 9};
     uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)Cin * Cout * 2,
                            (uint64_t)Cin * Cout * 3 * 2};
-    uint32_t box[4] = {(uint32_t)Cin, 32, 3, 1};
-    EXA_TRY(make_tmap_bf16(&tw, (void*)w_zfold, 4, dims, strides, box, Cin * 2));
+    uint32_t box[4] = {(uint32_t)cbox, pair ? 16u : 32u, pair ? 1u : 3u, 1};
+    EXA_TRY(make_tmap_bf16(&tw, (void*)w_zfold, 4, dims, strides, box, cbox * 2));
   }
-  int grid = num_sms - num_sms % a.n_halves;
-  if (grid > a.tiles_total * a.n_halves) grid = a.tiles_total * a.n_halves;
+  int grid;
+  if (pair) {
+    grid = num_sms - num_sms % (2 * a.n_halves);
+    const int rounds = (a.tiles_total + 1) / 2;
+    if (grid > 2 * rounds * a.n_halves) grid = 2 * rounds * a.n_halves;
+  } else {
+    grid = num_sms - num_sms % a.n_halves;
+    if (grid > a.tiles_total * a.n_halves) grid = a.tiles_total * a.n_halves;
+  }
   {
     static const char* dbg_env = getenv("EXA_ZF_DBG");  // development-only timing experiments
     a.dbg = dbg_env ? atoi(dbg_env) : 0;
@@ -126,6 +160,18 @@ Status launch_conv_zfold(const Act& in, const Act& out, const __nv_bfloat16* w_z
               1e3 * cyc / ns, mx / (1e3 * cyc / ns) * 1e-3);
     }
   } dbg_print{(a.dbg & 8) != 0, grid, Cin, Cout, head != nullptr, s, dbg_dev};
+  if (pair) {
+    if (Cin == 32) {
+      if (head) return launch_zf2<32, EPI_HEAD>(tx, tw, a, grid, s);
+      return launch_zf2<32, EPI_STORE>(tx, tw, a, grid, s);
+    }
+    if (Cin == 64) {
+      if (head) return launch_zf2<64, EPI_HEAD>(tx, tw, a, grid, s);
+      return launch_zf2<64, EPI_STORE>(tx, tw, a, grid, s);
+    }
+    EXA_CHECK(!head, "conv_zfold: fused head needs Cin <= 64");
+    return launch_zf2<128, EPI_STORE>(tx, tw, a, grid, s);
+  }
   if (Cin == 32) {
     if (head) return launch_zf<32, EPI_HEAD>(tx, tw, a, grid, s);
     return launch_zf<32, EPI_STORE>(tx, tw, a, grid, s);

@@ -43,8 +43,8 @@ struct ZfArgs {
   int out_cstride, out_coff;
   __nv_bfloat16* pool_out;   // optional fused MaxPool3d(2) output (unet3d.py:195), NDHWC at half res
   int pool_cstride, pool_coff;
-  const float* head_w;       // EPI_HEAD: [head_c][32]
-  const float* head_b;       // [head_c]
+  float head_w[8][32];       // EPI_HEAD: 1x1x1 head weights/bias as kernel parameters, so that
+  float head_b[8];           // they are constant-bank operands of the FMAs (no loads)
   float* head_out;           // [B][head_c][D-2t][H-2t][W-2t]
   int head_c, trim, apply_sigmoid;
   int dbg;                   // development only (EXA_ZF_DBG): timing experiments, wrong results
@@ -460,12 +460,15 @@ conv3x3_zfold_kernel(const __grid_constant__ CUtensorMap tmap_x,
             for (int j = 0; j < 32; ++j) v[j] = leaky_relu(v[j] + bias[j]);
             float* o = p.head_out + (size_t)b * p.head_c * cstride +
                        ((size_t)(po - t) * Hy + (y - t)) * Wx + (x - t);
-            for (int oc = 0; oc < p.head_c; ++oc) {
-              float s = __ldg(p.head_b + oc);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) s = fmaf(__ldg(p.head_w + oc * 32 + j), v[j], s);
-              if (p.apply_sigmoid) s = 1.f / (1.f + expf(-s));
-              o[(size_t)oc * cstride] = s;
+            for (int oc = 0; oc < 8; ++oc) {
+              if (oc < p.head_c) {  // uniform; weights are immediate constant-bank operands
+                float s = p.head_b[oc];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) s = fmaf(p.head_w[oc][j], v[j], s);
+                if (p.apply_sigmoid) s = __fdividef(1.f, 1.f + __expf(-s));
+                o[(size_t)oc * cstride] = s;
+              }
             }
           }
         }

@@ -184,6 +184,8 @@ Status Engine::init() {
   num_sms_ = prop.multiProcessorCount;
   const char* nz = getenv("EXA_NO_ZFOLD");
   use_zfold_ = !(nz && nz[0] == '1');
+  const char* np = getenv("EXA_NO_PAIR");
+  use_pair_ = !(np && np[0] == '1');
   return Status::OK();
 }
 
@@ -350,6 +352,8 @@ Status Engine::finalize_weights() {
   free_dev(head_w_);
   free_dev(head_b_);
   head_w_ = head_b_ = nullptr;
+  head_w_host_ = hw->f32;
+  head_b_host_ = hb->f32;
   EXA_CUDA(cudaMalloc(&head_w_, sizeof(float) * out_channels_ * 32));
   EXA_CUDA(cudaMalloc(&head_b_, sizeof(float) * out_channels_));
   EXA_CUDA(cudaMemcpy(head_w_, hw->f32.data(), sizeof(float) * out_channels_ * 32,
@@ -411,7 +415,7 @@ Status Engine::finalize_weights() {
             pk[((size_t)tap * sp.cout + co) * sp.cin + ci] = f32_to_bf16_rn((float)wsrc(co, ci, tap));
       EXA_CUDA(cudaMalloc(&L.w_bf16, n * 2));
       EXA_CUDA(cudaMemcpy(L.w_bf16, pk.data(), n * 2, cudaMemcpyHostToDevice));
-      if ((sp.cin == 32 || sp.cin == 64) && (sp.cout == 32 || sp.cout == 64)) {
+      if ((sp.cin == 32 || sp.cin == 64 || sp.cin == 128) && (sp.cout == 32 || sp.cout == 64)) {
         // z-folded layout: B operand rows of one in-plane tap are [kz=2 | kz=1 | kz=0] x cout
         std::vector<uint16_t> zf(n);
         for (int t9 = 0; t9 < 9; ++t9)
@@ -501,14 +505,14 @@ Status Engine::conv(const ConvLayer& L, const Act& in, const Act& out, const Hea
                     const ConvRegion* region, const Act* pool_out, cudaStream_t s) {
   cur_tag_ = (int)(&L - layers_);
   if (precision_ == EXA_PRECISION_BF16) {
-    const bool zf = use_zfold_ && L.w_zfold && conv_zfold_supported(in, L.cout);
+    const bool zf = use_zfold_ && L.w_zfold && conv_zfold_supported(in, L.cout, use_pair_);
     {
       Scope sc(this, CAT_CONV, s);
       if (zf) {
         // z-folded kernel: optional output sub-box and fused 2x2x2 max-pool
         const bool fuse_pool = pool_out && in.D % 2 == 0;
         EXA_TRY(launch_conv_zfold(in, out, L.w_zfold, L.bias, head, region,
-                                  fuse_pool ? pool_out : nullptr, num_sms_, s));
+                                  fuse_pool ? pool_out : nullptr, num_sms_, use_pair_, s));
         if (fuse_pool) return Status::OK();
       } else {
         EXA_TRY(launch_conv_umma(in, out, L.w_bf16, L.bias, head, num_sms_, s));
@@ -643,6 +647,8 @@ Status Engine::forward(const float* x, float* logits, int batch, const int32_t p
   HeadParams head;
   head.w = head_w_;
   head.b = head_b_;
+  head.w_host = head_w_host_.data();
+  head.b_host = head_b_host_.data();
   head.out = logits;
   head.C = out_channels_;
   head.trim = 0;
@@ -756,6 +762,8 @@ Status Engine::slab_run(const uint16_t* slab_dev, int D, int H, int W, const exa
     HeadParams head;
     head.w = head_w_;
     head.b = head_b_;
+    head.w_host = head_w_host_.data();
+    head.b_host = head_b_host_.data();
     head.out = probs_ + (size_t)i0 * per_patch;
     head.C = out_channels_;
     head.trim = t;

@@ -96,6 +96,7 @@ class Engine {
     Scope(Engine* eng, int cat, cudaStream_t st);
     ~Scope();
   };
+  bool use_pair_ = true;   // EXA_NO_PAIR=1: one CTA per MMA (conv_zfold.cuh) instead of CTA pairs
   bool use_zfold_ = true;  // EXA_NO_ZFOLD=1 selects the plain per-tap kernel everywhere (A/B tests)
   bool prof_on_ = false;
   std::vector<ProfRec> prof_;
@@ -109,6 +110,7 @@ class Engine {
   StemWeights stem_{};
   float* head_w_ = nullptr;
   float* head_b_ = nullptr;
+  std::vector<float> head_w_host_, head_b_host_;
 
   // activation workspace
   void* ws_ = nullptr;

@@ -40,8 +40,10 @@ struct PatchSource {
 };
 
 struct HeadParams {
-  const float* w = nullptr;  // [C][32]
-  const float* b = nullptr;  // [C]
+  const float* w = nullptr;  // device [C][32]
+  const float* b = nullptr;  // device [C]
+  const float* w_host = nullptr;  // host copies (passed to K1z as kernel parameters)
+  const float* b_host = nullptr;
   float* out = nullptr;      // [B][C][D-2t][H-2t][W-2t]
   int C = 0;
   int trim = 0;
@@ -73,10 +75,11 @@ Status launch_conv_umma(const Act& in, const Act& out, const __nv_bfloat16* w_pa
 struct ConvRegion {
   int lo[3], hi[3];
 };
-bool conv_zfold_supported(const Act& in, int cout);
+// pair: the cta_group::2 variant (conv_zfold2.cuh), which also takes Cin = 128
+bool conv_zfold_supported(const Act& in, int cout, bool pair);
 Status launch_conv_zfold(const Act& in, const Act& out, const __nv_bfloat16* w_zfold,
                          const float* bias, const HeadParams* head, const ConvRegion* region,
-                         const Act* pool_out, int num_sms, cudaStream_t s);
+                         const Act* pool_out, int num_sms, bool pair, cudaStream_t s);
 Status launch_conv_fp32(const Act& in, const Act& out, const float* w_packed, const float* bias,
                         cudaStream_t s);
 Status launch_head_fp32(const Act& in, const HeadParams& head, cudaStream_t s);
