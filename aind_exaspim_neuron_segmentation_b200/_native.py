@@ -15,8 +15,9 @@ import subprocess
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_PKG_DIR, "csrc")
 LIB_PATH = os.path.join(_PKG_DIR, "libexaspim_b200.so")
-SOURCES = ["capi.cu", "engine.cu", "kernels_mem.cu", "conv_umma.cu", "conv_zfold.cu"]
-HEADERS = ["common.cuh", "conv_umma.cuh", "conv_zfold.cuh", "engine.h", "kernels.h", "tmap.h"]
+SOURCES = ["capi.cu", "engine.cu", "kernels_mem.cu", "conv_umma.cu", "conv_zfold.cu", "conv_stem.cu"]
+HEADERS = ["common.cuh", "conv_umma.cuh", "conv_zfold.cuh", "conv_zfold2.cuh", "conv_stem.cuh", "engine.h",
+           "kernels.h", "tmap.h"]
 
 PRECISION_BF16 = 0
 PRECISION_FP32 = 1

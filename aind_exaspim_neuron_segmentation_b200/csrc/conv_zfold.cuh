@@ -72,7 +72,7 @@ template <int ROWB>
 __device__ __forceinline__ constexpr uint32_t zf_desc_hi(int sbo_rows) {
   return (uint32_t)((sbo_rows * ROWB) >> 4)      // SBO             [32,46)
          | (1u << 14)                            // version (sm_100) bit 46
-         | ((ROWB == 128 ? 2u : 4u) << 29);      // swizzle mode    [61,64)
+         | ((ROWB == 128 ? 2u : (ROWB == 64 ? 4u : 6u)) << 29);  // swizzle mode [61,64): 128/64/32 B
 }
 __device__ __forceinline__ uint32_t zf_desc_lo(uint32_t smem_addr) {
   return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16);  // start address [0,14), LBO (ignored)

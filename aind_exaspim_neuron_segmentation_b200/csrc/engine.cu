@@ -155,6 +155,8 @@ Engine::~Engine() {
   }
   free_dev(head_w_);
   free_dev(head_b_);
+  free_dev(stem_band_);
+  free_dev(stem_bias_);
   free_dev(ws_);
   free_dev(lut_);
   free_dev(probs_);
@@ -184,6 +186,8 @@ Status Engine::init() {
   num_sms_ = prop.multiProcessorCount;
   const char* nz = getenv("EXA_NO_ZFOLD");
   use_zfold_ = !(nz && nz[0] == '1');
+  const char* ns = getenv("EXA_NO_TC_STEM");
+  use_tc_stem_ = !(ns && ns[0] == '1');
   const char* np = getenv("EXA_NO_PAIR");
   use_pair_ = !(np && np[0] == '1');
   return Status::OK();
@@ -404,6 +408,25 @@ Status Engine::finalize_weights() {
       for (int tap = 0; tap < 27; ++tap)
         for (int co = 0; co < 32; ++co) stem_.w[tap][co] = (float)wsrc(co, 0, tap);
       for (int co = 0; co < 32; ++co) stem_.b[co] = bias[co];
+      if (precision_ == EXA_PRECISION_BF16) {
+        // Toeplitz (band) form for the tensor-core stem: B[kz,ky][n = xo*32 + c][k = x'] =
+        // w[c][kz][ky][kx = x' - xo], bf16-rounded once like every other layer's weights
+        std::vector<uint16_t> band((size_t)9 * 256 * 16, 0);
+        for (int t9 = 0; t9 < 9; ++t9)
+          for (int xo = 0; xo < 8; ++xo)
+            for (int c = 0; c < 32; ++c)
+              for (int kx = 0; kx < 3; ++kx)
+                band[((size_t)t9 * 256 + xo * 32 + c) * 16 + xo + kx] =
+                    f32_to_bf16_rn(stem_.w[t9 * 3 + kx][c]);
+        free_dev(stem_band_);
+        free_dev(stem_bias_);
+        stem_band_ = nullptr;
+        stem_bias_ = nullptr;
+        EXA_CUDA(cudaMalloc(&stem_band_, band.size() * 2));
+        EXA_CUDA(cudaMemcpy(stem_band_, band.data(), band.size() * 2, cudaMemcpyHostToDevice));
+        EXA_CUDA(cudaMalloc(&stem_bias_, sizeof(float) * 32));
+        EXA_CUDA(cudaMemcpy(stem_bias_, stem_.b, sizeof(float) * 32, cudaMemcpyHostToDevice));
+      }
       continue;
     }
     const size_t n = (size_t)27 * sp.cin * sp.cout;
@@ -451,7 +474,7 @@ Status Engine::finalize_weights() {
 namespace {
 struct WsLayout {
   // element offsets (in units of the activation element) of every buffer
-  size_t a0, cat4, p1, d1a, cat3, p2, d2a, cat2, p3, d3a, cat1, p4, d4a, x5, u1a, u1, u2a, u2, u3a,
+  size_t xhi, xlo, a0, cat4, p1, d1a, cat3, p2, d2a, cat2, p3, d3a, cat1, p4, d4a, x5, u1a, u1, u2a, u2, u3a,
       u3, total;
 };
 WsLayout layout(int B, int pz, int py, int px) {
@@ -463,6 +486,9 @@ WsLayout layout(int B, int pz, int py, int px) {
     off += (n + 127) / 128 * 128;  // 256-byte alignment for bf16, more for fp32
     return o;
   };
+  // normalised input, bf16 hi / lo parts, rows padded to px + 16 (tensor-core stem)
+  L.xhi = take((size_t)B * pz * py * (px + 16));
+  L.xlo = take((size_t)B * pz * py * (px + 16));
   L.a0 = take(vox(0) * 32);    // inc.0 output; re-used for up4.0 output (A0 is dead by then)
   L.cat4 = take(vox(0) * 64);  // [x1 | up(u3)]
   L.p1 = take(vox(1) * 32);
@@ -605,7 +631,19 @@ Status Engine::run_network(const PatchSource& src, int batch, int pz, int py, in
     p_ups = &r_ups;
   }
 
-  {
+  if (!f32 && use_tc_stem_ && pz % 16 == 0 && py % 8 == 0 && px % 8 == 0) {
+    // inc.0 on the tensor cores: gather/normalise into bf16 hi+lo, then the Toeplitz-form conv
+    __nv_bfloat16* xhi = (__nv_bfloat16*)((char*)ws_ + L.xhi * esz);
+    __nv_bfloat16* xlo = (__nv_bfloat16*)((char*)ws_ + L.xlo * esz);
+    {
+      Scope sc(this, CAT_STEM, s);
+      EXA_TRY(launch_stem_split(src, batch, pz, py, px, xhi, xlo, s));
+    }
+    {
+      Scope sc(this, CAT_STEM, s);
+      EXA_TRY(launch_stem_tc(xhi, xlo, stem_band_, stem_bias_, a0, num_sms_, s));
+    }
+  } else {
     Scope sc(this, CAT_STEM, s);
     EXA_TRY(launch_stem(src, stem_, a0, s));                // inc.0 (+gather/normalise)
   }

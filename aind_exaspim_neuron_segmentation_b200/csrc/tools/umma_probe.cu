@@ -590,7 +590,7 @@ static inline uint16_t f_to_bf16(float f) {
 int main() {
   const int D = 3, H = 24, W = 16, NW = 256;
   int failures = 0;
-  for (int rb : {128, 64}) {
+  for (int rb : {128, 64, 32}) {
     if (getenv("PROBE_RATE_ONLY")) break;
     const int C = rb / 2;
     std::vector<uint16_t> hx((size_t)D * H * W * C), hw((size_t)27 * NW * C);
@@ -628,7 +628,8 @@ int main() {
     }
     const size_t smem_bytes = 32768 + 32768 + 64 + 1024;
     if (rb == 128) CK(cudaFuncSetAttribute(probe_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    else CK(cudaFuncSetAttribute(probe_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    else if (rb == 64) CK(cudaFuncSetAttribute(probe_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    else CK(cudaFuncSetAttribute(probe_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
 
     // tile origin (x0,y0) = (0,0) so the halo box starts at (-1,-1): exercises OOB zero fill,
     // and H=24 > 16+1, W=16 > 8+1 so the far halo is real data.
@@ -638,7 +639,8 @@ int main() {
       a.use_base_offset = use_bo; a.b_row_off = b_row_off; a.out = dout; a.dcol = dcol;
       CK(cudaMemset(dout, 0xff, 128 * 256 * 4));
       if (rb == 128) probe_kernel<128><<<1, 128, smem_bytes>>>(halo ? tx_halo : tx_plain, tw, a);
-      else probe_kernel<64><<<1, 128, smem_bytes>>>(halo ? tx_halo : tx_plain, tw, a);
+      else if (rb == 64) probe_kernel<64><<<1, 128, smem_bytes>>>(halo ? tx_halo : tx_plain, tw, a);
+      else probe_kernel<32><<<1, 128, smem_bytes>>>(halo ? tx_halo : tx_plain, tw, a);
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) {
         printf("[rb=%d] %-28s ky=%d kx=%d n=%d : LAUNCH ERROR %s\n", rb, name, ky, kx, n, cudaGetErrorString(e));
@@ -671,7 +673,7 @@ int main() {
     failures += run(0, 0, 0, 0, 32, 0, 0, "plain/oob") ? 1 : 0;
     failures += run(0, 2, 2, 2, 64, 0, 32, "plain/b_row_off") ? 1 : 0;
     failures += run(0, 1, 1, 1, 96, 0, 0, "plain/dcol=416", 416) ? 1 : 0;
-    { int bad = run(0, 1, 1, 1, 96, 0, 0, "TMEM column wrap dcol=480", 480); printf("[rb=%3d] TMEM accumulator window 480..575 %s\n", rb, bad ? "does NOT wrap to 0..63" : "WRAPS to columns 0..63"); }
+    // (an accumulator window crossing column 512 does not wrap: the launch faults -- measured)
     // 2. halo view, base_offset = 0
     int halo_bad0 = 0, halo_bad1 = 0;
     for (int ky = 0; ky < 3; ++ky)
