@@ -6,8 +6,8 @@ reference's key layout, so it shares no code with either the reference's
 
 ``emulate_bf16=True`` reproduces the *numerics contract* of the CUDA bf16 path
 (DESIGN.md): BatchNorm folded into the conv in fp32, folded weights rounded to
-bf16 once, every layer output rounded to bf16 once, fp32 accumulation, fp32
-stem input, fp32 1x1x1 head.  It is used to separate "rounding noise" from
+bf16 once (including the Cin=1 stem's), every layer output rounded to bf16 once, fp32
+accumulation, stem input kept to ~fp32 accuracy (bf16 hi+lo split), fp32 1x1x1 head.  It is used to separate "rounding noise" from
 "bug" when the GPU result is compared with the fp32 oracle.
 """
 
@@ -47,8 +47,7 @@ def _conv_bn_act(x, sd, prefix, conv_idx, bn_idx, emulate_bf16, round_input=True
     scale = (g.double() / torch.sqrt(var.double() + 1e-5))
     wf = (w.double() * scale.view(-1, 1, 1, 1, 1)).float()
     bf = ((b.double() - mu.double()) * scale + beta.double()).float()
-    if w.shape[1] > 1:  # the Cin=1 stem runs in fp32 on the fp32 normalised input
-        wf = _bf16(wf)
+    wf = _bf16(wf)  # every layer's folded weights are rounded once (the stem input is NOT rounded)
     y = F.leaky_relu(F.conv3d(x, wf, None, padding=1) + bf.view(1, -1, 1, 1, 1), 0.01)
     return y
 
