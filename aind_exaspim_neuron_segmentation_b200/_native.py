@@ -137,6 +137,9 @@ _SIGNATURES = {
     "exa_profile_begin": (ctypes.c_int, [ctypes.c_void_p]),
     "exa_profile_end": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double),
                                        ctypes.POINTER(ctypes.c_int64), ctypes.c_int]),
+    "exa_profile_layers": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double),
+                                          ctypes.POINTER(ctypes.c_int64),
+                                          ctypes.POINTER(ctypes.c_int32), ctypes.c_int]),
     "exa_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),
 }
 

@@ -216,6 +216,10 @@ int exa_profile_end(exa_engine* e, double* ms_by_category, int64_t* launches_by_
   return guarded(e, [&] { return e->impl.profile_end(ms_by_category, launches_by_category, n); });
 }
 
+int exa_profile_layers(exa_engine* e, double* ms, int64_t* launches, int32_t* kind, int n) {
+  return guarded(e, [&] { return e->impl.profile_layers(ms, launches, kind, n); });
+}
+
 int64_t exa_launch_count(const exa_engine* e) { return e ? e->impl.launches : -1; }
 
 }  // extern "C"

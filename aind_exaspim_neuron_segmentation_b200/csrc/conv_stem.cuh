@@ -139,9 +139,19 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constan
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      bool ftok = false, ttok = false;  // next tile's barriers already seen complete (probed early:
+                                        // a probe consumed at once stalls the tensor pipe)
       for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
-        mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1u);
-        mbar_wait(smem_u32(&full_bar[stage]), phase);
+        if (!ttok) mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1u);
+        if (!ftok) mbar_wait(smem_u32(&full_bar[stage]), phase);
+        {
+          const int ns = stage + 1 == STAGES ? 0 : stage + 1;
+          const uint32_t np = stage + 1 == STAGES ? phase ^ 1u : phase;
+          const int na = acc ^ 1;
+          const uint32_t nap = na == 0 ? acc_phase ^ 1u : acc_phase;
+          ftok = mbar_test_wait(smem_u32(&full_bar[ns]), np);
+          ttok = mbar_test_wait(smem_u32(&tempty_bar[na]), nap ^ 1u);
+        }
         tc_fence_after();
         // halo view: rows are (z, y) with y innermost; 8-row groups (8 y of one z) 10 rows apart
         const uint64_t a_desc =

@@ -46,8 +46,10 @@ Status launch_zf2(const CUtensorMap& tx, const CUtensorMap& tw, const ZfArgs& a,
 
 bool conv_zfold_supported(const Act& in, int cout, bool pair) {
   const bool cin_ok = in.C == 32 || in.C == 64 || (pair && in.C == 128);
-  return !in.fp32 && cin_ok && (cout == 32 || cout == 64) && in.W % 8 == 0 && in.H % 16 == 0 &&
-         in.D >= 2;
+  // pair mode tolerates a ragged last tile row (H % 16 != 0: out-of-range rows are zero-filled by
+  // TMA and masked in the epilogue), which admits the 24^3 level (up2.conv.double_conv.3)
+  return !in.fp32 && cin_ok && (cout == 32 || cout == 64) && in.W % 8 == 0 &&
+         (in.H % 16 == 0 || (pair && in.H % 8 == 0)) && in.D >= 2;
 }
 
 // w_zfold: bf16 [9 taps (ky,kx)][3 (kz = 2,1,0)][Cout][Cin]

@@ -302,34 +302,34 @@ conv3x3_zfold2_kernel(const __grid_constant__ CUtensorMap tmap_x,
     const int rx = row & 7, ry = row >> 3;
     const uint32_t tfull0 = smem_u32(tfull_bar), tempty0 = smem_u32(tempty_bar);
     const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-    constexpr int NC = EPI == EPI_STORE ? 16 : 32;
     const uint32_t col_off = EPI == EPI_STORE ? (uint32_t)(hs * 16) : 0u;
 
-    auto gather_plane = [&](uint32_t gi0, int po, float (&v)[NC]) {
-      const int zl = po + 1 < zin1 ? po + 1 : po;
-      {
-        const uint32_t gi = gi0 + (uint32_t)(zl - zin0);
-        mbar_wait(tfull0 + (gi % ZF_GROUPS) * 8u, (gi / ZF_GROUPS) & 1u);
-        tc_fence_after();
-      }
-#pragma unroll
-      for (int j = 0; j < NC; ++j) v[j] = 0.f;
+    // wait until every partial of output plane po is complete
+    auto wait_plane = [&](uint32_t gi0, int po) {
+      const int zl = po + 1 < zin1 ? po + 1 : po;  // latest contributing input plane
+      const uint32_t gi = gi0 + (uint32_t)(zl - zin0);
+      mbar_wait(tfull0 + (gi % ZF_GROUPS) * 8u, (gi / ZF_GROUPS) & 1u);
+      tc_fence_after();
+    };
+    // sum the (up to three) partials of 16 accumulator columns [c0, c0+16) of output plane po:
+    // all loads are issued before the single wait
+    auto gather16 = [&](uint32_t gi0, int po, uint32_t c0, float (&v)[16]) {
+      uint32_t a[3][16];
 #pragma unroll
       for (int dz = -1; dz <= 1; ++dz) {
         const int z = po + dz;
         if (z >= zin0 && z < zin1) {
           const uint32_t gi = gi0 + (uint32_t)(z - zin0);
-          const uint32_t taddr =
-              tmem_lane + (gi % ZF_GROUPS) * 96u + (uint32_t)((1 - dz) * 32) + col_off;
-          uint32_t acc[NC];
-          if constexpr (NC == 16) tmem_ld_32x16(taddr, acc);
-          else tmem_ld_32x32(taddr, acc);
-          tmem_ld_wait();
+          tmem_ld_32x16(tmem_lane + (gi % ZF_GROUPS) * 96u + (uint32_t)((1 - dz) * 32) + c0, a[dz + 1]);
+        } else {
 #pragma unroll
-          for (int j = 0; j < NC; ++j) v[j] += __uint_as_float(acc[j]);
+          for (int j = 0; j < 16; ++j) a[dz + 1][j] = 0u;
         }
       }
-      tc_fence_before();
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        v[j] = (__uint_as_float(a[0][j]) + __uint_as_float(a[1][j])) + __uint_as_float(a[2][j]);
     };
     // same release rule as conv_zfold.cuh, signalled to the leader's barrier
     auto release_plane = [&](uint32_t gi0, int po) {
@@ -358,7 +358,9 @@ conv3x3_zfold2_kernel(const __grid_constant__ CUtensorMap tmap_x,
 
       auto do_plane = [&](int po, __nv_bfloat16* dst, bool in_xy, uint32_t (&pk)[8]) {
         float v[16];
-        gather_plane(gi0, po, v);
+        wait_plane(gi0, po);
+        gather16(gi0, po, col_off, v);
+        tc_fence_before();
         release_plane(gi0, po);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -436,22 +438,37 @@ conv3x3_zfold2_kernel(const __grid_constant__ CUtensorMap tmap_x,
             release_plane(gi0, po);
             continue;
           }
+          wait_plane(gi0, po);
           float v[32];
-          gather_plane(gi0, po, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = bias[j];
+#pragma unroll
+          for (int dz = -1; dz <= 1; ++dz) {  // one 32-column load at a time: 32 + 32 live registers
+            const int z = po + dz;
+            if (z >= zin0 && z < zin1) {
+              const uint32_t gi = gi0 + (uint32_t)(z - zin0);
+              uint32_t acc[32];
+              tmem_ld_32x32(tmem_lane + (gi % ZF_GROUPS) * 96u + (uint32_t)((1 - dz) * 32), acc);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(acc[j]);
+            }
+          }
+          tc_fence_before();
           release_plane(gi0, po);
           if (keep_xy && po >= t && po < p.D - t) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = leaky_relu(v[j] + bias[j]);
+            for (int j = 0; j < 32; ++j) v[j] = leaky_relu(v[j]);
             float* o = p.head_out + (size_t)b * p.head_c * cstride +
                        ((size_t)(po - t) * Hy + (y - t)) * Wx + (x - t);
 #pragma unroll
             for (int oc = 0; oc < 8; ++oc) {
-              if (oc < p.head_c) {
-                float s = p.head_b[oc];
+              if (oc < p.head_c) {  // uniform; weights are immediate constant-bank operands
+                float r = p.head_b[oc];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) s = fmaf(p.head_w[oc][j], v[j], s);
-                if (p.apply_sigmoid) s = __fdividef(1.f, 1.f + __expf(-s));
-                o[(size_t)oc * cstride] = s;
+                for (int j = 0; j < 32; ++j) r = fmaf(p.head_w[oc][j], v[j], r);
+                if (p.apply_sigmoid) r = __fdividef(1.f, 1.f + __expf(-r));
+                o[(size_t)oc * cstride] = r;
               }
             }
           }

@@ -231,8 +231,12 @@ Status Engine::profile_end(double* ms_by_cat, int64_t* launches_by_cat, int n) {
     launches_by_cat[i] = 0;
   }
   Status st = Status::OK();
-  double layer_ms[18] = {0};
-  int layer_n[18] = {0};
+  double* layer_ms = layer_ms_;
+  int64_t* layer_n = layer_n_;
+  for (int i = 0; i < 18; ++i) {
+    layer_ms[i] = 0;
+    layer_n[i] = 0;
+  }
   for (auto& r : prof_) {
     float ms = 0.f;
     cudaError_t e = cudaEventSynchronize(r.stop);
@@ -252,10 +256,20 @@ Status Engine::profile_end(double* ms_by_cat, int64_t* launches_by_cat, int n) {
     for (int i = 0; i < 18; ++i)
       if (layer_n[i])
         fprintf(stderr, "[layer %2d %-36s %3d->%3d] %4d launches, %.3f ms total, %.4f ms/launch\n", i,
-                layers_[i].conv_key.c_str(), layers_[i].cin, layers_[i].cout, layer_n[i],
+                layers_[i].conv_key.c_str(), layers_[i].cin, layers_[i].cout, (int)layer_n[i],
                 layer_ms[i], layer_ms[i] / layer_n[i]);
   }
   return st;
+}
+
+Status Engine::profile_layers(double* ms, int64_t* launches, int32_t* kind, int n) const {
+  EXA_CHECK(ms && launches && kind && n >= 18, "profile_layers: need 18 entries");
+  for (int i = 0; i < 18; ++i) {
+    ms[i] = layer_ms_[i];
+    launches[i] = layer_n_[i];
+    kind[i] = layer_kind_[i];
+  }
+  return Status::OK();
 }
 
 // ---------------------------------------------------------------------------
@@ -532,6 +546,7 @@ Status Engine::conv(const ConvLayer& L, const Act& in, const Act& out, const Hea
   cur_tag_ = (int)(&L - layers_);
   if (precision_ == EXA_PRECISION_BF16) {
     const bool zf = use_zfold_ && L.w_zfold && conv_zfold_supported(in, L.cout, use_pair_);
+    layer_kind_[cur_tag_] = zf ? (use_pair_ ? 3 : 2) : 1;
     {
       Scope sc(this, CAT_CONV, s);
       if (zf) {

@@ -68,6 +68,9 @@ class Engine {
                   CAT_COUNT };
   Status profile_begin();
   Status profile_end(double* ms_by_cat, int64_t* launches_by_cat, int n);
+  // per conv layer (index = position in unet3d.py:64-74 order, 0 = stem) of the last profile_end;
+  // kind: 0 none, 1 K1 (conv_umma), 2 K1z (conv_zfold), 3 K1z2 (conv_zfold2, CTA pairs)
+  Status profile_layers(double* ms, int64_t* launches, int32_t* kind, int n) const;
 
   std::string last_error;
   int64_t launches = 0;
@@ -89,6 +92,9 @@ class Engine {
     cudaEvent_t start, stop;
   };
   int cur_tag_ = -1;
+  double layer_ms_[18] = {0};
+  int64_t layer_n_[18] = {0};
+  int32_t layer_kind_[18] = {0};
   struct Scope {  // counts the launch and, when profiling, brackets it with two events
     Engine* e;
     cudaStream_t s;

@@ -92,6 +92,17 @@ class Engine:
         _native.check(self._lib.exa_profile_end(self._h, ms, cnt, n), self._h, "exa_profile_end")
         return {k: (ms[i], int(cnt[i])) for i, k in enumerate(self.PROFILE_CATEGORIES)}
 
+    LAYER_KERNELS = ("none", "conv3x3_umma_kernel", "conv3x3_zfold_kernel", "conv3x3_zfold2_kernel")
+
+    def profile_layers(self):
+        """-> [(device ms, launches, kernel name)] * 18 per conv layer for the last profile_end."""
+        ms = (ctypes.c_double * 18)()
+        cnt = (ctypes.c_int64 * 18)()
+        kind = (ctypes.c_int32 * 18)()
+        _native.check(self._lib.exa_profile_layers(self._h, ms, cnt, kind, 18), self._h,
+                      "exa_profile_layers")
+        return [(ms[i], int(cnt[i]), self.LAYER_KERNELS[kind[i]]) for i in range(18)]
+
     # -- operator level ----------------------------------------------------------
     def forward(self, x):
         """float32 (B,1,Pz,Py,Px) cuda tensor -> float32 logits (B,C,Pz,Py,Px)."""

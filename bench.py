@@ -5,8 +5,8 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one pass of the whole path over one synthetic uint16 volume:
-histogram -> percentiles -> (gather+normalise+stem, 17 tcgen05 convs, pools, upsamples, fused
-head+sigmoid+trim) per wave of patches -> overlap stitch -> (N>1: halo exchange + all-gather).
+histogram -> percentiles -> (gather+normalise, tensor-core stem, 17 tcgen05 convs, pools, upsamples,
+fused head+sigmoid+trim) per wave of patches -> overlap stitch -> (N>1: halo exchange + all-gather).
 N=1 runs BASELINE config 2 (512^3, patch 96^3 -> 512 patches); N GPUs run N x 512^3 voxels
 (1024x512x512, 1024x1024x512, 1024^3 = BASELINE config 3), sharded by z patch-rows: weak scaling.
 
@@ -14,9 +14,11 @@ N=1 runs BASELINE config 2 (512^3, patch 96^3 -> 512 patches); N GPUs run N x 51
             events), max over ranks.
 `e2e`     : same metric through the public API with HOST buffers: pinned H2D of the slab and
             D2H of the rank's output planes inside the timed region.
-`roofline`: the conv3x3x3 tcgen05 kernels (the dominant kernels), executed FLOPs / summed CUDA
-            event time of their launches inside the timed steps, against the measured dense
-            bf16 peak (MEASURED_PEAKS.json, sustained figure: timed inside a long step).
+`roofline`: the dominant kernel, conv3x3_zfold2_kernel (z-folded tcgen05 conv on CTA pairs; 8 of the
+            17 conv layers, ~2/3 of the step): executed FLOPs of its launches / their summed CUDA
+            event time inside the timed steps, against the measured dense bf16 peak
+            (MEASURED_PEAKS.json, sustained figure: timed inside a long step).  `all_conv_kernels`
+            and `per_layer` give the same for every conv launch.
 `cpu_baseline` / `--impl reference`: the CPU oracle port of the reference path (oracle/),
             all host threads, on a bounded sample (4 patches) of the same workload.
 """
@@ -47,6 +49,23 @@ F_UP40_FULL = 2 * 96 ** 3 * 32 * 27 * 64
 F_UP43_FULL = 2 * 96 ** 3 * 32 * 27 * 32
 F_TRIM_SAVED = (F_UP40_FULL - 2 * 82 ** 3 * 32 * 27 * 64) + (F_UP43_FULL - 2 * 80 ** 3 * 32 * 27 * 32)
 F_CONV_96 = F_PATCH_96 - F_STEM_96 - F_HEAD_96 - F_TRIM_SAVED  # executed by the tcgen05 convs
+
+# (level, Cin, Cout) of conv layers 1..17 in the order of unet3d.py:64-74 (0 = the Cin=1 stem)
+LAYER_SHAPES = {1: (0, 32, 32), 2: (1, 32, 64), 3: (1, 64, 64), 4: (2, 64, 128), 5: (2, 128, 128),
+                6: (3, 128, 256), 7: (3, 256, 256), 8: (4, 256, 256), 9: (4, 256, 256),
+                10: (3, 512, 256), 11: (3, 256, 128), 12: (2, 256, 128), 13: (2, 128, 64),
+                14: (1, 128, 64), 15: (1, 64, 32), 16: (0, 64, 32), 17: (0, 32, 32)}
+
+
+def layer_flops_96(i):
+    """Executed FLOPs (2*MACs) of conv layer i per 96^3 patch; the last two layers only compute the
+    kept box (80^3) and that box grown by one voxel (82^3)."""
+    lvl, cin, cout = LAYER_SHAPES[i]
+    side = {16: 82, 17: 80}.get(i, 96 >> lvl)
+    return 2 * side ** 3 * cout * 27 * cin
+
+
+assert sum(layer_flops_96(i) for i in LAYER_SHAPES) == F_CONV_96
 
 
 def volume_shape(n_gpus):
@@ -311,6 +330,7 @@ def run_b200(args):
     barrier()
     ms = ev0.elapsed_time(ev1)
     prof = engine.profile_end()
+    layers = engine.profile_layers()
     launches = engine.launch_count - launches0
     clocks = sampler.stop() if rank == 0 else None
     checksum = float(out[:, ::37, ::41, ::43].double().sum().item())
@@ -347,7 +367,23 @@ def run_b200(args):
         n_patches_rank = (job.rows[1] - job.rows[0]) * (shape[1] // 64) * (shape[2] // 64)
         conv_ms, conv_launches = prof["conv"]
         conv_flops = n_patches_rank * F_CONV_96 * args.steps
-        achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        achieved_all = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        # the dominant kernel: the z-folded CTA-pair conv (conv_zfold2.cuh)
+        per_layer, dom_ms, dom_flops, dom_launches = {}, 0.0, 0.0, 0
+        dom_name = "conv3x3_zfold2_kernel"
+        for i, (lms, ln, lname) in enumerate(layers):
+            if i == 0 or ln == 0:
+                continue
+            fl = n_patches_rank * layer_flops_96(i) * args.steps
+            per_layer[str(i)] = {"kernel": lname, "cin": LAYER_SHAPES[i][1], "cout": LAYER_SHAPES[i][2],
+                                 "ms_per_launch": lms / ln, "tflops": fl / (lms * 1e-3) / 1e12}
+            if lname == dom_name:
+                dom_ms += lms
+                dom_flops += fl
+                dom_launches += ln
+        if dom_launches == 0:   # pair kernel disabled (EXA_NO_PAIR / EXA_NO_ZFOLD): fall back to all convs
+            dom_name, dom_ms, dom_flops, dom_launches = "conv3x3 kernels (all)", conv_ms, conv_flops, conv_launches
+        achieved = dom_flops / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
         line = {
             "metric": "affinity voxels/sec", "value": voxels / (ms_step * 1e-3), "unit": "voxels/s",
             "n_gpus": n, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -362,13 +398,18 @@ def run_b200(args):
                              "pinned uint16 slab H2D + owned fp32 planes D2H per step, every rank")},
             "gpu_launches": int(launches),
             "roofline": {
-                "kernel": "conv3x3_umma_kernel (17 launches per wave of patches; rank 0)",
+                "kernel": f"{dom_name} ({dom_launches // max(args.steps, 1)} launches per step on rank 0)",
                 "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"],
                 "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
                 "peak_source": peaks["source"], "traffic": ncu_traffic(),
-                "launches": conv_launches, "avg_launch_ms": conv_ms / max(conv_launches, 1),
-                "flops_per_patch": F_CONV_96, "flops_per_patch_untrimmed": F_PATCH_96,
-                "share_of_step": conv_ms / (ms_step * args.steps),
+                "launches": dom_launches, "avg_launch_ms": dom_ms / max(dom_launches, 1),
+                "flops_per_launch": dom_flops / max(dom_launches, 1),
+                "share_of_step": dom_ms / (ms_step * args.steps),
+                "all_conv_kernels": {"achieved": achieved_all, "frac": achieved_all / peaks["bf16_tflops"],
+                                     "launches": conv_launches, "share_of_step": conv_ms / (ms_step * args.steps),
+                                     "flops_per_patch": F_CONV_96,
+                                     "flops_per_patch_untrimmed": F_PATCH_96},
+                "per_layer": per_layer,
             },
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
             "clocks": clocks,

@@ -137,6 +137,12 @@ enum { EXA_PROFILE_CATEGORIES = 7 };
 int exa_profile_begin(exa_engine* e);
 int exa_profile_end(exa_engine* e, double* ms_by_category, int64_t* launches_by_category, int n);
 
+/* Per-layer view of the last exa_profile_end: summed device ms and launches of the 3x3x3 conv
+ * of layer i (i = 1..17 in the order of unet3d.py:64-74; 0 = the stem, reported under category 1)
+ * and the kernel that ran it: 0 none, 1 K1 (per-tap implicit GEMM), 2 K1z (z-folded, one CTA per
+ * MMA), 3 K1z2 (z-folded, CTA pairs).  n >= 18. */
+int exa_profile_layers(exa_engine* e, double* ms, int64_t* launches, int32_t* kind, int n);
+
 /* number of kernel launches issued by this engine since creation (bench bookkeeping) */
 int64_t exa_launch_count(const exa_engine* e);
 
