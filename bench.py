@@ -240,7 +240,7 @@ def run_reference(args):
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(n):
@@ -417,10 +417,32 @@ def run_b200(args):
         }
         if n == 1 and not args.no_cpu:
             line["cpu_baseline"], _ = cpu_baseline(steps=1)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+_JSON_FD = None
+
+
+def capture_stdout():
+    """Keep the real stdout for the ONE JSON line and send everything else written to fd 1 (e.g.
+    NCCL's "NCCL version ..." banner, which goes to stdout) to stderr."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
@@ -438,6 +460,7 @@ def main():
                f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1", "--master-port",
                "29531", os.path.abspath(__file__)] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
+    capture_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
