@@ -1,6 +1,8 @@
 // Host launcher for the tcgen05 implicit-GEMM conv (kernel in conv_umma.cuh).
 #include "conv_umma.cuh"
 
+#include <stdlib.h>
+
 #include "kernels.h"
 #include "tmap.h"
 
@@ -14,17 +16,17 @@ int largest_pow2_divisor_leq(int value, int cap) {
   return t;
 }
 
-template <int N, int KC, int EPI>
+template <int N, int KC, int EPI, int MT = 1>
 Status launch_instance(const CUtensorMap& tx, const CUtensorMap& tw, const ConvArgs& a, int grid,
                        cudaStream_t s) {
-  using S = ConvSmem<N, KC>;
+  using S = ConvSmem<N, KC, MT>;
   static bool configured = false;
   if (!configured) {
-    EXA_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<N, KC, EPI>,
+    EXA_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<N, KC, EPI, MT>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     configured = true;
   }
-  conv3x3_umma_kernel<N, KC, EPI><<<grid, 256, S::TOTAL, s>>>(tx, tw, a);
+  conv3x3_umma_kernel<N, KC, EPI, MT><<<grid, 256, S::TOTAL, s>>>(tx, tw, a);
   EXA_CUDA(cudaGetLastError());
   return Status::OK();
 }
@@ -39,19 +41,33 @@ Status launch_conv_umma(const Act& in, const Act& out, const __nv_bfloat16* w_pa
   EXA_CHECK(Cin % 32 == 0 && Cout % 32 == 0, "conv_umma: channels must be multiples of 32");
   const int KC = (Cin % 64 == 0) ? 64 : 32;
 
+  int N = Cout;
+  if (N > 256) N = 256;
+  // two M tiles per stage share one weight tile when the accumulators fit TMEM twice
+  // (2 sets x 2 tiles x N <= 512) -- halves the weight traffic per MMA
+  static const bool no_mt2 = getenv("EXA_NO_MT2") != nullptr;
+  const int mt_try = (!head && !no_mt2 && KC == 64 && N <= 128 && in.voxels() >= 256) ? 2 : 1;
+
   ConvArgs a{};
   a.B = in.B; a.D = in.D; a.H = in.H; a.W = in.W;
   a.Cin = Cin; a.Cout = Cout;
-  a.tw = largest_pow2_divisor_leq(in.W, 32);
-  a.th = largest_pow2_divisor_leq(in.H, 128 / a.tw);
-  a.td = largest_pow2_divisor_leq(in.D, 128 / (a.tw * a.th));
-  a.tb = 128 / (a.tw * a.th * a.td);
+  int MT = mt_try;
+  for (;;) {
+    const int rows = 128 * MT;
+    a.tw = largest_pow2_divisor_leq(in.W, 32);
+    a.th = largest_pow2_divisor_leq(in.H, rows / a.tw);
+    a.td = largest_pow2_divisor_leq(in.D, rows / (a.tw * a.th));
+    a.tb = rows / (a.tw * a.th * a.td);
+    // fall back to single tiles when the box does not fit or the doubled tiles would leave the
+    // persistent grid with fewer than ~3 rounds (tile quantisation costs more than B traffic)
+    const long long tiles2 = (long long)(in.W / a.tw) * (in.H / a.th) * (in.D / a.td) *
+                             ceil_div(in.B, a.tb) * (Cout / N);
+    if (MT == 1 || (a.tb <= 256 && tiles2 >= 3LL * num_sms)) break;
+    MT = 1;
+  }
   a.ntx = in.W / a.tw; a.nty = in.H / a.th; a.ntz = in.D / a.td;
   a.ntb = ceil_div(in.B, a.tb);
   const int m_tiles = a.ntx * a.nty * a.ntz * a.ntb;
-
-  int N = Cout;
-  if (N > 256) N = 256;
   if (N == 256 && m_tiles < num_sms) N = 128;
   EXA_CHECK(Cout % N == 0, "conv_umma: Cout must be a multiple of the N tile");
   a.n_tiles_n = Cout / N;
@@ -89,6 +105,12 @@ Status launch_conv_umma(const Act& in, const Act& out, const __nv_bfloat16* w_pa
   }
   const int grid = a.num_tiles < num_sms ? a.num_tiles : num_sms;
 
+  if (MT == 2) {
+    if (N == 128) return launch_instance<128, 64, EPI_STORE, 2>(tx, tw_, a, grid, s);
+    if (N == 64) return launch_instance<64, 64, EPI_STORE, 2>(tx, tw_, a, grid, s);
+    if (N == 32) return launch_instance<32, 64, EPI_STORE, 2>(tx, tw_, a, grid, s);
+    return Status::Err("conv_umma: unsupported N for two-tile stages");
+  }
 #define EXA_CONV_CASE(NN, KK)                                                    \
   if (N == NN && KC == KK) {                                                     \
     if (head) return launch_instance<NN, KK, EPI_HEAD>(tx, tw_, a, grid, s);     \

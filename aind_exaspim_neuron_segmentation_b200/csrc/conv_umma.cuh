@@ -41,9 +41,11 @@ struct ConvArgs {
   int apply_sigmoid;
 };
 
-template <int N, int KC>
+// MT = number of 128-row M tiles per pipeline stage that share one B tile (MT = 2 halves the
+// weight traffic per MMA; the kernel is bound by L2 -> shared-memory traffic, not by the MMAs)
+template <int N, int KC, int MT = 1>
 struct ConvSmem {
-  static constexpr int A_BYTES = 128 * KC * 2;
+  static constexpr int A_BYTES = MT * 128 * KC * 2;
   static constexpr int B_BYTES = N * KC * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BUDGET = 200 * 1024;
@@ -54,14 +56,15 @@ struct ConvSmem {
   static_assert(STAGES >= 3, "pipeline too shallow");
 };
 
-template <int N, int KC, int EPI>
+template <int N, int KC, int EPI, int MT = 1>
 __global__ void __launch_bounds__(256, 1)
 conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmap_x,
                     const __grid_constant__ CUtensorMap tmap_w, const ConvArgs p) {
-  using S = ConvSmem<N, KC>;
+  using S = ConvSmem<N, KC, MT>;
   constexpr int STAGES = S::STAGES;
   constexpr int ROW_BYTES = KC * 2;
-  constexpr uint32_t TMEM_COLS = (2 * N < 32) ? 32 : 2 * N;  // two accumulators
+  constexpr uint32_t TMEM_COLS = (2 * MT * N < 32) ? 32 : 2 * MT * N;  // two accumulator sets
+  static_assert(2 * MT * N <= 512, "accumulators exceed TMEM");
   static_assert(EPI == EPI_STORE || N == 32, "fused head needs all 32 channels in one tile");
 
   extern __shared__ uint8_t smem_raw[];
@@ -143,19 +146,31 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmap_x,
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      // A barrier probe whose result is consumed at once costs ~150 cycles of tensor time
+      // (tools/umma_probe.cu), more than half of a 4-MMA stage: every probe is issued one stage
+      // (one tile) ahead and consumed later; the blocking wait only runs when the probe failed.
+      bool ftok = false, ttok = false;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1u);
+        if (!ttok) mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1u);
+        ttok = mbar_test_wait(smem_u32(&tempty_bar[acc ^ 1]), ((acc ^ 1) == 0 ? acc_phase ^ 1u : acc_phase) ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * MT * N);
         for (int it = 0; it < kiters; ++it) {
-          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          if (!ftok) mbar_wait(smem_u32(&full_bar[stage]), phase);
+          {
+            const int ns = stage + 1 == STAGES ? 0 : stage + 1;
+            ftok = mbar_test_wait(smem_u32(&full_bar[ns]), stage + 1 == STAGES ? phase ^ 1u : phase);
+          }
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
           const uint64_t adesc = umma_smem_desc<ROW_BYTES>(sa);
           const uint64_t bdesc = umma_smem_desc<ROW_BYTES>(sa + S::A_BYTES);
 #pragma unroll
           for (int k = 0; k < KC / 16; ++k) {
-            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+#pragma unroll
+            for (int m = 0; m < MT; ++m)
+              umma_bf16(d_tmem + (uint32_t)(m * N), adesc + (uint64_t)((m * 128 * ROW_BYTES) >> 4) + 2 * k,
+                        bdesc + 2 * k, idesc, (it | k) != 0);
           }
           umma_commit(smem_u32(&empty_bar[stage]));
           if (++stage == STAGES) {
@@ -172,69 +187,72 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmap_x,
   } else if (warp >= 4) {
     // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
     const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const int r_tx = row % p.tw;
-    const int r_ty = (row / p.tw) % p.th;
-    const int r_tz = (row / (p.tw * p.th)) % p.td;
-    const int r_tb = row / (p.tw * p.th * p.td);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int nt = tile % p.n_tiles_n;
-      int m = tile / p.n_tiles_n;
-      const int bt = m / tiles_m_per_b;
-      m -= bt * tiles_m_per_b;
-      const int zt = m / (p.ntx * p.nty);
-      m -= zt * (p.ntx * p.nty);
-      const int yt = m / p.ntx;
-      const int xt = m - yt * p.ntx;
-      const int x = xt * p.tw + r_tx, y = yt * p.th + r_ty, z = zt * p.td + r_tz;
-      const int b = bt * p.tb + r_tb;
+      int mt = tile / p.n_tiles_n;
+      const int bt = mt / tiles_m_per_b;
+      mt -= bt * tiles_m_per_b;
+      const int zt = mt / (p.ntx * p.nty);
+      mt -= zt * (p.ntx * p.nty);
+      const int yt = mt / p.ntx;
+      const int xt = mt - yt * p.ntx;
       const int n0 = nt * N;
-      const bool valid = (x < p.W) && (y < p.H) && (z < p.D) && (b < p.B);
 
       mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * N);
 #pragma unroll 1
-      for (int c0 = 0; c0 < N; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(taddr + (uint32_t)c0, r);
-        tmem_ld_wait();
-        float v[32];
+      for (int m = 0; m < MT; ++m) {
+        const int row = m * 128 + q * 32 + lane;  // voxel of the tile box, x fastest
+        const int r_tx = row % p.tw;
+        const int r_ty = (row / p.tw) % p.th;
+        const int r_tz = (row / (p.tw * p.th)) % p.td;
+        const int r_tb = row / (p.tw * p.th * p.td);
+        const int x = xt * p.tw + r_tx, y = yt * p.th + r_ty, z = zt * p.td + r_tz;
+        const int b = bt * p.tb + r_tb;
+        const bool valid = (x < p.W) && (y < p.H) && (z < p.D) && (b < p.B);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MT + m) * N);
+#pragma unroll 1
+        for (int c0 = 0; c0 < N; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + (uint32_t)c0, r);
+          tmem_ld_wait();
+          float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          v[j] = leaky_relu(__uint_as_float(r[j]) + __ldg(p.bias + n0 + c0 + j));
-        }
-        if constexpr (EPI == EPI_STORE) {
-          if (valid) {
-            const size_t vox = (((size_t)b * p.D + z) * p.H + y) * p.W + x;
-            uint4* dst =
-                reinterpret_cast<uint4*>(p.out + vox * p.out_cstride + p.out_coff + n0 + c0);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint4 o;
-              o.x = pack_bf16x2(v[8 * g + 0], v[8 * g + 1]);
-              o.y = pack_bf16x2(v[8 * g + 2], v[8 * g + 3]);
-              o.z = pack_bf16x2(v[8 * g + 4], v[8 * g + 5]);
-              o.w = pack_bf16x2(v[8 * g + 6], v[8 * g + 7]);
-              dst[g] = o;
-            }
+          for (int j = 0; j < 32; ++j) {
+            v[j] = leaky_relu(__uint_as_float(r[j]) + __ldg(p.bias + n0 + c0 + j));
           }
-        } else {
-          const int t = p.trim;
-          const int Dz = p.D - 2 * t, Hy = p.H - 2 * t, Wx = p.W - 2 * t;
-          const bool keep = valid && x >= t && x < p.W - t && y >= t && y < p.H - t && z >= t &&
-                            z < p.D - t;
-          if (keep) {
-            for (int oc = 0; oc < p.head_c; ++oc) {
-              float s = __ldg(p.head_b + oc);
+          if constexpr (EPI == EPI_STORE) {
+            if (valid) {
+              const size_t vox = (((size_t)b * p.D + z) * p.H + y) * p.W + x;
+              uint4* dst =
+                  reinterpret_cast<uint4*>(p.out + vox * p.out_cstride + p.out_coff + n0 + c0);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) s = fmaf(__ldg(p.head_w + oc * 32 + j), v[j], s);
-              if (p.apply_sigmoid) s = 1.f / (1.f + expf(-s));
-              const size_t o =
-                  ((((size_t)b * p.head_c + oc) * Dz + (z - t)) * Hy + (y - t)) * Wx + (x - t);
-              p.head_out[o] = s;
+              for (int g = 0; g < 4; ++g) {
+                uint4 o;
+                o.x = pack_bf16x2(v[8 * g + 0], v[8 * g + 1]);
+                o.y = pack_bf16x2(v[8 * g + 2], v[8 * g + 3]);
+                o.z = pack_bf16x2(v[8 * g + 4], v[8 * g + 5]);
+                o.w = pack_bf16x2(v[8 * g + 6], v[8 * g + 7]);
+                dst[g] = o;
+              }
+            }
+          } else {
+            const int t = p.trim;
+            const int Dz = p.D - 2 * t, Hy = p.H - 2 * t, Wx = p.W - 2 * t;
+            const bool keep = valid && x >= t && x < p.W - t && y >= t && y < p.H - t && z >= t &&
+                              z < p.D - t;
+            if (keep) {
+              for (int oc = 0; oc < p.head_c; ++oc) {
+                float s = __ldg(p.head_b + oc);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) s = fmaf(__ldg(p.head_w + oc * 32 + j), v[j], s);
+                if (p.apply_sigmoid) s = 1.f / (1.f + expf(-s));
+                const size_t o =
+                    ((((size_t)b * p.head_c + oc) * Dz + (z - t)) * Hy + (y - t)) * Wx + (x - t);
+                p.head_out[o] = s;
+              }
             }
           }
         }
