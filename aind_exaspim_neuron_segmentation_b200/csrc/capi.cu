@@ -175,7 +175,14 @@ int exa_slab_partial(exa_engine* e, float* halo_dev, void* stream) {
 }
 
 int exa_slab_stitch(exa_engine* e, const float* seed_dev, float* out_dev, void* stream) {
-  return guarded(e, [&] { return e->impl.slab_stitch(seed_dev, out_dev, (cudaStream_t)stream); });
+  return guarded(e, [&] { return e->impl.slab_stitch(seed_dev, out_dev, 0, (cudaStream_t)stream); });
+}
+
+int exa_slab_stitch_strided(exa_engine* e, const float* seed_dev, float* out_dev,
+                            int64_t channel_stride, void* stream) {
+  return guarded(e, [&] {
+    return e->impl.slab_stitch(seed_dev, out_dev, channel_stride, (cudaStream_t)stream);
+  });
 }
 
 int exa_count_patches(int D, int H, int W, const int32_t patch[3], const int32_t overlap[3]) {

@@ -856,13 +856,16 @@ Status Engine::slab_partial(float* halo_dev, cudaStream_t s) {
   return launch_stitch(a, s);
 }
 
-Status Engine::slab_stitch(const float* seed_dev, float* out_dev, cudaStream_t s) {
+Status Engine::slab_stitch(const float* seed_dev, float* out_dev, int64_t channel_stride,
+                           cudaStream_t s) {
   EXA_CUDA(cudaSetDevice(device_));
   EXA_CHECK(job_ready_, "slab_stitch: no slab job (call exa_slab_run first)");
   const int nz = slab_.out_z1 - slab_.out_z0;
   if (nz <= 0) return Status::OK();
-  return stitch_planes(seed_dev, out_dev, (size_t)nz * plan_.H * plan_.W, slab_.out_z0,
-                       slab_.out_z1, s);
+  const size_t dense = (size_t)nz * plan_.H * plan_.W;
+  EXA_CHECK(channel_stride == 0 || (size_t)channel_stride >= dense, "slab_stitch: channel stride too small");
+  return stitch_planes(seed_dev, out_dev, channel_stride ? (size_t)channel_stride : dense,
+                       slab_.out_z0, slab_.out_z1, s);
 }
 
 // finished planes [z0, z1) of the current slab job -> out (plane z0 first), channel stride given

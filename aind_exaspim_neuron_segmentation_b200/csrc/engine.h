@@ -61,7 +61,8 @@ class Engine {
   Status slab_run(const uint16_t* slab_dev, int D, int H, int W, const exa_predict_params& p,
                   int row_begin, int row_end, cudaStream_t s);
   Status slab_partial(float* halo_dev, cudaStream_t s);
-  Status slab_stitch(const float* seed_dev, float* out_dev, cudaStream_t s);
+  // channel_stride = 0: dense (C, out planes, H, W); otherwise elements between channels of out_dev
+  Status slab_stitch(const float* seed_dev, float* out_dev, int64_t channel_stride, cudaStream_t s);
 
   // per-category kernel timing with CUDA events on the launching stream (bench / roofline)
   enum Category { CAT_HIST = 0, CAT_STEM, CAT_CONV, CAT_POOL, CAT_UPSAMPLE, CAT_HEAD, CAT_STITCH,

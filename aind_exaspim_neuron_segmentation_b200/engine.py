@@ -174,10 +174,12 @@ class Engine:
                                                  _stream_ptr(self.device)),
                       self._h, "exa_slab_partial")
 
-    def slab_stitch(self, seed_dev, out_dev):
-        _native.check(self._lib.exa_slab_stitch(self._h, _ptr(seed_dev), _ptr(out_dev),
-                                                _stream_ptr(self.device)),
-                      self._h, "exa_slab_stitch")
+    def slab_stitch(self, seed_dev, out_dev, channel_stride=0):
+        """out_dev: dense (C, own planes, H, W), or -- with channel_stride -- a view whose first
+        element is plane out_z0 of channel 0 of a larger channel-major array."""
+        _native.check(self._lib.exa_slab_stitch_strided(self._h, _ptr(seed_dev), _ptr(out_dev),
+                                                        int(channel_stride), _stream_ptr(self.device)),
+                      self._h, "exa_slab_stitch_strided")
 
 
 # -- host helpers that need no GPU --------------------------------------------------

@@ -200,6 +200,10 @@ class _EngineSlabBackend:
     def stitch(self, seed, out):
         self.engine.slab_stitch(seed, out)
 
+    def stitch_into(self, seed, full, z0):
+        """Stitch the owned planes straight into full[:, z0:...] of the (C, D, H, W) output."""
+        self.engine.slab_stitch(seed, full[:, z0:], channel_stride=full.stride(0))
+
     def to_device(self, host_u16):
         return torch.from_numpy(host_u16).to(self.device, non_blocking=True)
 
@@ -245,6 +249,7 @@ class SlabJob:
         self.hist_range = (nxt[order], nxt[order + 1]) if self.has_rows else (0, 0)
         self.own_planes = [max(p["out_z1"] - p["out_z0"], 0) if r[1] > r[0] else 0
                            for p, r in zip(self.all_plans, self.all_rows)]
+        self._full = None  # gathered output, allocated once and re-used by every run()
 
     def slab_bounds(self):
         """Input planes [z0, z1) this rank needs resident."""
@@ -294,25 +299,42 @@ class SlabJob:
                 for req in dist.batch_isend_irecv(ops):
                     req.wait()
         nz_own = self.own_planes[self.rank]
-        own = torch.zeros((c, nz_own, h, w), dtype=torch.float32, device=dev)
-        if self.has_rows and nz_own > 0:
-            be.stitch(seed, own)
         if not gather or self.world == 1:
+            own = torch.zeros((c, nz_own, h, w), dtype=torch.float32, device=dev)
+            if self.has_rows and nz_own > 0:
+                be.stitch(seed, own)
             return own
-        # C3: gather of the owned planes (channel-major output: concatenate along z)
+        # C3: every rank ends up with the full (C, D, H, W) array.  The owned planes are stitched
+        # straight into it and the other ranks' planes arrive in place: the output is channel-
+        # major, so a rank's planes are one contiguous chunk per channel -- C sends and C receives
+        # per peer in ONE grouped NCCL call, no staging copies, no concatenation.
+        if self._full is None or self._full.device != dev:
+            self._full = torch.empty((c, d, h, w), dtype=torch.float32, device=dev)
+        full = self._full
+        starts = np.concatenate([[0], np.cumsum(self.own_planes)]).astype(int)
+        z0 = int(starts[self.rank])
+        if self.has_rows and nz_own > 0:
+            if hasattr(be, "stitch_into"):
+                be.stitch_into(seed, full, z0)
+            else:
+                own = torch.zeros((c, nz_own, h, w), dtype=torch.float32, device=dev)
+                be.stitch(seed, own)
+                full[:, z0:z0 + nz_own].copy_(own)
         be.sync()
-        pieces = [torch.empty((c, n, h, w), dtype=torch.float32, device=dev)
-                  for n in self.own_planes]
-        if len(set(self.own_planes)) == 1:
-            dist.all_gather(pieces, own, group=self.group)
-        else:
-            for g in range(self.world):  # ragged slabs: one broadcast per rank
-                if self.own_planes[g] == 0:
-                    continue
-                if g == self.rank:
-                    pieces[g].copy_(own)
-                dist.broadcast(pieces[g], src=self._peer(g), group=self.group)
-        return torch.cat(pieces, dim=1)
+        ops = []
+        for g in range(self.world):
+            if g == self.rank:
+                continue
+            gz0, gn = int(starts[g]), self.own_planes[g]
+            for ch in range(c):
+                if gn > 0:
+                    ops.append(dist.P2POp(dist.irecv, full[ch, gz0:gz0 + gn], self._peer(g), self.group))
+                if nz_own > 0:
+                    ops.append(dist.P2POp(dist.isend, full[ch, z0:z0 + nz_own], self._peer(g), self.group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        return full
 
     def own_bounds(self):
         z0 = self.plan["out_z0"] if self.has_rows else 0

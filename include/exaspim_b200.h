@@ -120,6 +120,11 @@ int exa_slab_run(exa_engine* e, const uint16_t* slab_dev, int D, int H, int W,
 int exa_slab_partial(exa_engine* e, float* halo_dev, void* stream);
 /* finished planes [out_z0,out_z1) -> out_dev (C, out_z1-out_z0, H, W); seed_dev may be NULL */
 int exa_slab_stitch(exa_engine* e, const float* seed_dev, float* out_dev, void* stream);
+/* same, writing straight into a larger channel-major array: out_dev points at plane out_z0 of
+ * channel 0 and consecutive channels are channel_stride elements apart (e.g. D*H*W of the full
+ * (C, D, H, W) output, so that the gather of the other ranks' planes needs no re-packing) */
+int exa_slab_stitch_strided(exa_engine* e, const float* seed_dev, float* out_dev,
+                            int64_t channel_stride, void* stream);
 
 /* host helpers mirroring count_patches / generate_patch_starts (inference.py:340-397);
  * starts receives n_patches*3 int32 (z,y,x) in the reference's order */
