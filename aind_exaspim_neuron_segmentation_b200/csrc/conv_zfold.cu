@@ -136,8 +136,8 @@ Status launch_conv_zfold(const Act& in, const Act& out, const __nv_bfloat16* w_z
     if (grid > a.tiles_total * a.n_halves) grid = a.tiles_total * a.n_halves;
   }
   {
-    static const char* dbg_env = getenv("EXA_ZF_DBG");  // development-only timing experiments
-    a.dbg = dbg_env ? atoi(dbg_env) : 0;
+    static const char* dbg_env = getenv("EXA_ZF_DBG");  // 8: print issuer cycles/plane and SM clock
+    a.dbg = dbg_env ? (atoi(dbg_env) & 8) : 0;
   }
   static long long* dbg_dev = nullptr;
   if (a.dbg & 8) {

@@ -47,7 +47,7 @@ struct ZfArgs {
   float head_b[8];           // they are constant-bank operands of the FMAs (no loads)
   float* head_out;           // [B][head_c][D-2t][H-2t][W-2t]
   int head_c, trim, apply_sigmoid;
-  int dbg;                   // development only (EXA_ZF_DBG): timing experiments, wrong results
+  int dbg;                   // EXA_ZF_DBG=8: record issuer cycles / wall time per CTA (results unchanged)
   long long* dbg_out;        // dbg & 8: [gridDim.x][4] issuer {cycles, ns, planes, 0}
 };
 
@@ -237,7 +237,6 @@ conv3x3_zfold_kernel(const __grid_constant__ CUtensorMap tmap_x,
       const uint32_t tfull0 = bar0 + 2u * (uint32_t)STAGES * 8u;
       const uint32_t tempty0 = tfull0 + (uint32_t)ZF_GROUPS * 8u;
       const uint32_t tempty_end = tempty0 + (uint32_t)ZF_GROUPS * 8u;
-      const bool nowait = (p.dbg & 2) != 0;
       uint64_t a_desc = a_desc0;     // descriptor of the current A stage
       uint32_t ea = empty0;          // empty_bar of the current stage
       uint32_t d0 = tmem_base;       // first column of the current accumulator group
@@ -254,8 +253,8 @@ conv3x3_zfold_kernel(const __grid_constant__ CUtensorMap tmap_x,
       }
       const int total = my_tiles * nin;
       for (int it = 0; it < total; ++it) {
-        if (!ftok && !nowait) mbar_wait(fa, fph);
-        if (!ttok && !nowait) mbar_wait(ta, tph);
+        if (!ftok) mbar_wait(fa, fph);
+        if (!ttok) mbar_wait(ta, tph);
         // probe the next plane's barriers now, consume the answers one plane later
         fa += 8u;
         if (fa == empty0) {
@@ -310,7 +309,6 @@ conv3x3_zfold_kernel(const __grid_constant__ CUtensorMap tmap_x,
     const int rx = row & 7, ry = row >> 3;
     const uint32_t tfull0 = smem_u32(tfull_bar), tempty0 = smem_u32(tempty_bar);
     const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-    const bool skip = (p.dbg & 1) != 0;
     constexpr int NC = EPI == EPI_STORE ? 16 : 32;    // accumulator columns per thread
     const uint32_t col_off = EPI == EPI_STORE ? (uint32_t)(hs * 16) : 0u;
 
@@ -325,7 +323,7 @@ conv3x3_zfold_kernel(const __grid_constant__ CUtensorMap tmap_x,
       }
 #pragma unroll
       for (int j = 0; j < NC; ++j) v[j] = 0.f;
-      if (!skip) {
+      {
 #pragma unroll
         for (int dz = -1; dz <= 1; ++dz) {
           const int z = po + dz;
@@ -382,7 +380,7 @@ conv3x3_zfold_kernel(const __grid_constant__ CUtensorMap tmap_x,
           const float c = leaky_relu(v[2 * j + 1] + bias[2 * j + 1]);
           pk[j] = pack_bf16x2(a, c);
         }
-        if (in_xy && !skip) st_global_256(dst, pk);
+        if (in_xy) st_global_256(dst, pk);
       };
 
       for (int tile = cta_in_class; tile < p.tiles_total; tile += ctas_per_class) {
@@ -455,7 +453,7 @@ conv3x3_zfold_kernel(const __grid_constant__ CUtensorMap tmap_x,
           float v[32];
           gather_plane(gi0, po, v);
           release_plane(gi0, po);
-          if (!skip && keep_xy && po >= t && po < p.D - t) {
+          if (keep_xy && po >= t && po < p.D - t) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = leaky_relu(v[j] + bias[j]);
             float* o = p.head_out + (size_t)b * p.head_c * cstride +

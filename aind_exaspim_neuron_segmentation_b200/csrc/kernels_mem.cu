@@ -588,8 +588,8 @@ upsample2_bf16_kernel(const __nv_bfloat16* __restrict__ in, int in_cstride, int 
 struct PlaneXY {
   f32x2 v[2][2][4];  // [y out][x out][channel pair]
 };
-__device__ __forceinline__ void upsample_plane_xy(const __nv_bfloat16* __restrict__ base, size_t plane_vox,
-                                                  int Wi, int in_cstride, const AxisTaps& ty,
+__device__ __forceinline__ void upsample_plane_xy(const __nv_bfloat16* __restrict__ plane_base,
+                                                  const int (&off)[3][3], const AxisTaps& ty,
                                                   const AxisTaps& tx, PlaneXY& o) {
   const f32x2 zero = f2_pack(0.f, 0.f);
   const f32x2 xa0 = f2_pack(tx.a0, tx.a0), xa1 = f2_pack(tx.a1, tx.a1);
@@ -599,8 +599,7 @@ __device__ __forceinline__ void upsample_plane_xy(const __nv_bfloat16* __restric
   for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
     for (int dx = 0; dx < 3; ++dx)
-      q[dy][dx] = *reinterpret_cast<const uint4*>(
-          base + (plane_vox + (size_t)ty.w[dy] * Wi + tx.w[dx]) * in_cstride);
+      q[dy][dx] = *reinterpret_cast<const uint4*>(plane_base + off[dy][dx]);
   f32x2 pxa[3][4], pxb[3][4];  // x-interpolated rows: output 2xj / 2xj+1
 #pragma unroll
   for (int dy = 0; dy < 3; ++dy) {
@@ -641,33 +640,50 @@ upsample_march_bf16_kernel(const __nv_bfloat16* __restrict__ in, int in_cstride,
   const int zj_begin = jz0 + (int)blockIdx.y * njz, zj_end = min(zj_begin + njz, (rg.hi[0] + 1) / 2);
   if (zj_begin >= zj_end) return;
   const AxisTaps ty = axis_taps(yj, Hi), tx = axis_taps(xj, Wi);
-  const __nv_bfloat16* base = in + in_coff + 8 * c8;
-  const size_t plane = (size_t)Hi * Wi;
-  const size_t vol0 = (size_t)b * Di * plane;
+  // all in-plane offsets are fixed for the thread: element offsets of the 3x3 window in a plane
+  // and of the 2x2 output pixels (32-bit; a patch plane is far below 2^31 elements)
+  int off[3][3];
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) off[dy][dx] = (ty.w[dy] * Wi + tx.w[dx]) * in_cstride;
   const int Ho = 2 * Hi, Wo = 2 * Wi, Do = 2 * Di;
+  int ooff[2][2];
+  bool ok[2][2];
+#pragma unroll
+  for (int bb = 0; bb < 2; ++bb)
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int yo = 2 * yj + bb, xo = 2 * xj + c;
+      ooff[bb][c] = (yo * Wo + xo) * out_cstride;
+      ok[bb][c] = yo >= rg.lo[1] && yo < rg.hi[1] && xo >= rg.lo[2] && xo < rg.hi[2];
+    }
+  const size_t in_plane = (size_t)Hi * Wi * in_cstride;
+  const size_t out_plane = (size_t)Ho * Wo * out_cstride;
+  const __nv_bfloat16* ibase = in + in_coff + 8 * c8 + (size_t)b * Di * in_plane;
+  __nv_bfloat16* obase = out + out_coff + 8 * c8 + (size_t)b * Do * out_plane;
 
   // rolling window: planes (zj-1, zj, zj+1), clamped at the borders
   PlaneXY pm, pc, pn;
-  upsample_plane_xy(base, vol0 + (size_t)max(zj_begin - 1, 0) * plane, Wi, in_cstride, ty, tx, pm);
-  upsample_plane_xy(base, vol0 + (size_t)zj_begin * plane, Wi, in_cstride, ty, tx, pc);
-  const bool y_ok[2] = {2 * yj >= rg.lo[1] && 2 * yj < rg.hi[1], 2 * yj + 1 >= rg.lo[1] && 2 * yj + 1 < rg.hi[1]};
-  const bool x_ok[2] = {2 * xj >= rg.lo[2] && 2 * xj < rg.hi[2], 2 * xj + 1 >= rg.lo[2] && 2 * xj + 1 < rg.hi[2]};
+  upsample_plane_xy(ibase + (size_t)max(zj_begin - 1, 0) * in_plane, off, ty, tx, pm);
+  upsample_plane_xy(ibase + (size_t)zj_begin * in_plane, off, ty, tx, pc);
+  const f32x2 zero = f2_pack(0.f, 0.f);
   for (int zj = zj_begin; zj < zj_end; ++zj) {
-    if (zj + 1 <= Di - 1) upsample_plane_xy(base, vol0 + (size_t)(zj + 1) * plane, Wi, in_cstride, ty, tx, pn);
+    if (zj + 1 <= Di - 1) upsample_plane_xy(ibase + (size_t)(zj + 1) * in_plane, off, ty, tx, pn);
     else pn = pc;  // clamped: window element 2 = plane zj
     const AxisTaps tz = axis_taps(zj, Di);
     const f32x2 za0 = f2_pack(tz.a0, tz.a0), za1 = f2_pack(tz.a1, tz.a1);
     const f32x2 zb0 = f2_pack(tz.b0, tz.b0), zb1 = f2_pack(tz.b1, tz.b1);
-    const f32x2 zero = f2_pack(0.f, 0.f);
 #pragma unroll
     for (int a = 0; a < 2; ++a) {
       const int zo = 2 * zj + a;
       if (zo < rg.lo[0] || zo >= rg.hi[0]) continue;
+      __nv_bfloat16* oplane = obase + (size_t)zo * out_plane;
 #pragma unroll
       for (int bb = 0; bb < 2; ++bb)
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          if (!(y_ok[bb] && x_ok[c])) continue;
+          if (!ok[bb][c]) continue;
           uint32_t o[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -677,9 +693,7 @@ upsample_march_bf16_kernel(const __nv_bfloat16* __restrict__ in, int in_cstride,
             f2_unpack(r, lo, hi);
             o[j] = pack_bf16x2(lo, hi);
           }
-          const size_t ovox = (((size_t)b * Do + zo) * Ho + (2 * yj + bb)) * Wo + (2 * xj + c);
-          *reinterpret_cast<uint4*>(out + ovox * out_cstride + out_coff + 8 * c8) =
-              make_uint4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<uint4*>(oplane + ooff[bb][c]) = make_uint4(o[0], o[1], o[2], o[3]);
         }
     }
     pm = pc;
