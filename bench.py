@@ -179,6 +179,32 @@ def measured_peaks():
     return {"bf16_tflops": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+def hbm_kernels(prof, n_patches, voxels, steps, peak_gbs):
+    """Achieved GB/s of the memory-bound kernels from their ALGORITHMIC bytes
+    and their summed CUDA-event time, against the measured copy bandwidth."""
+    up_bytes = 0
+    for lvl_out, c in ((3, 256), (2, 128), (1, 64)):     # up1..up3: full output, input at half res
+        n = 96 >> lvl_out
+        up_bytes += n ** 3 * c * 2 + (n // 2) ** 3 * c * 2
+    up_bytes += 84 ** 3 * 32 * 2 + 42 ** 3 * 32 * 2       # up4: the 84^3 box the last convs need
+    algo = {
+        # gather: 2 B read + 2 x 2 B (hi, lo) written, re-read by the stem; stem output 64 B per voxel
+        "stem": n_patches * 96 ** 3 * (2 + 4 + 4 + 64),
+        "upsample": n_patches * up_bytes,
+        # stitch: every trimmed patch voxel read once (3 x 4 B), every output voxel written once
+        "stitch": n_patches * 3 * 80 ** 3 * 4 + voxels * 12,
+        "histogram": voxels * 2,
+    }
+    out = {}
+    for k, b in algo.items():
+        ms = prof[k][0] / steps
+        if ms > 0:
+            gbs = b / (ms * 1e-3) / 1e9
+            out[k] = {"algorithmic_bytes": b, "ms_per_step": ms, "achieved_gbs": gbs,
+                      "frac_of_measured_hbm": gbs / peak_gbs}
+    return out
+
+
 def ncu_traffic():
     """Per-launch DRAM bytes of the dominant conv kernel from the committed ncu capture."""
     path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
@@ -412,6 +438,7 @@ def run_b200(args):
                 "per_layer": per_layer,
             },
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
+            "hbm_kernels": hbm_kernels(prof, n_patches_rank, voxels / n, args.steps, peaks["hbm_gbs"]),
             "clocks": clocks,
             "checksum": checksum,
         }
