@@ -439,19 +439,29 @@ conv3x3_zfold2_kernel(const __grid_constant__ CUtensorMap tmap_x,
             continue;
           }
           wait_plane(gi0, po);
+          // the partials of planes po-1 and po are issued together (64 registers in flight), the
+          // third follows while they are being added
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = bias[j];
+          {
+            uint32_t a0[32], a1[32];
+            const bool has_prev = po - 1 >= zin0, has_next = po + 1 < zin1;
+            const uint32_t gi = gi0 + (uint32_t)(po - zin0);
+            if (has_prev) tmem_ld_32x32(tmem_lane + ((gi - 1u) % ZF_GROUPS) * 96u + 64u, a0);
+            tmem_ld_32x32(tmem_lane + (gi % ZF_GROUPS) * 96u + 32u, a1);
+            tmem_ld_wait();
+            if (has_prev) {
 #pragma unroll
-          for (int dz = -1; dz <= 1; ++dz) {  // one 32-column load at a time: 32 + 32 live registers
-            const int z = po + dz;
-            if (z >= zin0 && z < zin1) {
-              const uint32_t gi = gi0 + (uint32_t)(z - zin0);
-              uint32_t acc[32];
-              tmem_ld_32x32(tmem_lane + (gi % ZF_GROUPS) * 96u + (uint32_t)((1 - dz) * 32), acc);
+              for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(a0[j]);
+            }
+            if (has_next) tmem_ld_32x32(tmem_lane + ((gi + 1u) % ZF_GROUPS) * 96u, a0);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(a1[j]);
+            if (has_next) {
               tmem_ld_wait();
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(acc[j]);
+              for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(a0[j]);
             }
           }
           tc_fence_before();
@@ -464,9 +474,17 @@ conv3x3_zfold2_kernel(const __grid_constant__ CUtensorMap tmap_x,
 #pragma unroll
             for (int oc = 0; oc < 8; ++oc) {
               if (oc < p.head_c) {  // uniform; weights are immediate constant-bank operands
-                float r = p.head_b[oc];
+                // four independent partial sums: the epilogue is latency-bound (2-3 warps per
+                // scheduler), a 32-deep dependent FMA chain per channel would dominate it
+                float r0 = p.head_b[oc], r1 = 0.f, r2 = 0.f, r3 = 0.f;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) r = fmaf(p.head_w[oc][j], v[j], r);
+                for (int j = 0; j < 32; j += 4) {
+                  r0 = fmaf(p.head_w[oc][j], v[j], r0);
+                  r1 = fmaf(p.head_w[oc][j + 1], v[j + 1], r1);
+                  r2 = fmaf(p.head_w[oc][j + 2], v[j + 2], r2);
+                  r3 = fmaf(p.head_w[oc][j + 3], v[j + 3], r3);
+                }
+                float r = (r0 + r1) + (r2 + r3);
                 if (p.apply_sigmoid) r = __fdividef(1.f, 1.f + __expf(-r));
                 o[(size_t)oc * cstride] = r;
               }
