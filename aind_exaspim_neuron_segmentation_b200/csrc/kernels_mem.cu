@@ -588,24 +588,28 @@ upsample2_bf16_kernel(const __nv_bfloat16* __restrict__ in, int in_cstride, int 
 struct PlaneXY {
   f32x2 v[2][2][4];  // [y out][x out][channel pair]
 };
-__device__ __forceinline__ void upsample_plane_xy(const __nv_bfloat16* __restrict__ plane_base,
-                                                  const int (&off)[3][3], const AxisTaps& ty,
-                                                  const AxisTaps& tx, PlaneXY& o) {
-  const f32x2 zero = f2_pack(0.f, 0.f);
-  const f32x2 xa0 = f2_pack(tx.a0, tx.a0), xa1 = f2_pack(tx.a1, tx.a1);
-  const f32x2 xb0 = f2_pack(tx.b0, tx.b0), xb1 = f2_pack(tx.b1, tx.b1);
+struct PlaneLoads {
   uint4 q[3][3];
+};
+__device__ __forceinline__ void upsample_load(const __nv_bfloat16* __restrict__ plane_base,
+                                              const int (&off)[3][3], PlaneLoads& l) {
 #pragma unroll
   for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
     for (int dx = 0; dx < 3; ++dx)
-      q[dy][dx] = *reinterpret_cast<const uint4*>(plane_base + off[dy][dx]);
+      l.q[dy][dx] = *reinterpret_cast<const uint4*>(plane_base + off[dy][dx]);
+}
+__device__ __forceinline__ void upsample_plane_xy(const PlaneLoads& l, const AxisTaps& ty,
+                                                  const AxisTaps& tx, PlaneXY& o) {
+  const f32x2 zero = f2_pack(0.f, 0.f);
+  const f32x2 xa0 = f2_pack(tx.a0, tx.a0), xa1 = f2_pack(tx.a1, tx.a1);
+  const f32x2 xb0 = f2_pack(tx.b0, tx.b0), xb1 = f2_pack(tx.b1, tx.b1);
   f32x2 pxa[3][4], pxb[3][4];  // x-interpolated rows: output 2xj / 2xj+1
 #pragma unroll
   for (int dy = 0; dy < 3; ++dy) {
-    const uint32_t w0[4] = {q[dy][0].x, q[dy][0].y, q[dy][0].z, q[dy][0].w};
-    const uint32_t w1[4] = {q[dy][1].x, q[dy][1].y, q[dy][1].z, q[dy][1].w};
-    const uint32_t w2[4] = {q[dy][2].x, q[dy][2].y, q[dy][2].z, q[dy][2].w};
+    const uint32_t w0[4] = {l.q[dy][0].x, l.q[dy][0].y, l.q[dy][0].z, l.q[dy][0].w};
+    const uint32_t w1[4] = {l.q[dy][1].x, l.q[dy][1].y, l.q[dy][1].z, l.q[dy][1].w};
+    const uint32_t w2[4] = {l.q[dy][2].x, l.q[dy][2].y, l.q[dy][2].z, l.q[dy][2].w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const f32x2 f0 = bf16x2_to_f2(w0[j]), f1 = bf16x2_to_f2(w1[j]), f2 = bf16x2_to_f2(w2[j]);
@@ -624,6 +628,11 @@ __device__ __forceinline__ void upsample_plane_xy(const __nv_bfloat16* __restric
   }
 }
 
+// Along z every output plane blends two consecutive input planes: output 2j = a0(j)*p[j-1] +
+// a1(j)*p[j], output 2j+1 = b0(j)*p[j] + b1(j)*p[j+1] (indices clamped).  So only TWO
+// x/y-interpolated planes are live: when plane j+1 arrives, outputs 2j+1 and 2j+2 are emitted
+// from (p[j], p[j+1]).  The loads of plane j+2 are issued before that blend, so their latency
+// hides behind ~100 packed FMAs and eight stores.
 __global__ void __launch_bounds__(128)
 upsample_march_bf16_kernel(const __nv_bfloat16* __restrict__ in, int in_cstride, int in_coff,
                            __nv_bfloat16* __restrict__ out, int out_cstride, int out_coff, int Di,
@@ -640,8 +649,7 @@ upsample_march_bf16_kernel(const __nv_bfloat16* __restrict__ in, int in_cstride,
   const int zj_begin = jz0 + (int)blockIdx.y * njz, zj_end = min(zj_begin + njz, (rg.hi[0] + 1) / 2);
   if (zj_begin >= zj_end) return;
   const AxisTaps ty = axis_taps(yj, Hi), tx = axis_taps(xj, Wi);
-  // all in-plane offsets are fixed for the thread: element offsets of the 3x3 window in a plane
-  // and of the 2x2 output pixels (32-bit; a patch plane is far below 2^31 elements)
+  // all in-plane offsets are fixed for the thread (32-bit; a patch plane is far below 2^31 elements)
   int off[3][3];
 #pragma unroll
   for (int dy = 0; dy < 3; ++dy)
@@ -662,41 +670,52 @@ upsample_march_bf16_kernel(const __nv_bfloat16* __restrict__ in, int in_cstride,
   const size_t out_plane = (size_t)Ho * Wo * out_cstride;
   const __nv_bfloat16* ibase = in + in_coff + 8 * c8 + (size_t)b * Di * in_plane;
   __nv_bfloat16* obase = out + out_coff + 8 * c8 + (size_t)b * Do * out_plane;
-
-  // rolling window: planes (zj-1, zj, zj+1), clamped at the borders
-  PlaneXY pm, pc, pn;
-  upsample_plane_xy(ibase + (size_t)max(zj_begin - 1, 0) * in_plane, off, ty, tx, pm);
-  upsample_plane_xy(ibase + (size_t)zj_begin * in_plane, off, ty, tx, pc);
   const f32x2 zero = f2_pack(0.f, 0.f);
-  for (int zj = zj_begin; zj < zj_end; ++zj) {
-    if (zj + 1 <= Di - 1) upsample_plane_xy(ibase + (size_t)(zj + 1) * in_plane, off, ty, tx, pn);
-    else pn = pc;  // clamped: window element 2 = plane zj
-    const AxisTaps tz = axis_taps(zj, Di);
-    const f32x2 za0 = f2_pack(tz.a0, tz.a0), za1 = f2_pack(tz.a1, tz.a1);
-    const f32x2 zb0 = f2_pack(tz.b0, tz.b0), zb1 = f2_pack(tz.b1, tz.b1);
+
+  // one output plane zo = w_lo * lo + w_hi * hi, stored for the (up to) four pixels of the column
+  auto emit = [&](int zo, float w_lo, float w_hi, const PlaneXY& lo, const PlaneXY& hi) {
+    if (zo < rg.lo[0] || zo >= rg.hi[0]) return;
+    const f32x2 wl = f2_pack(w_lo, w_lo), wh = f2_pack(w_hi, w_hi);
+    __nv_bfloat16* oplane = obase + (size_t)zo * out_plane;
 #pragma unroll
-    for (int a = 0; a < 2; ++a) {
-      const int zo = 2 * zj + a;
-      if (zo < rg.lo[0] || zo >= rg.hi[0]) continue;
-      __nv_bfloat16* oplane = obase + (size_t)zo * out_plane;
+    for (int bb = 0; bb < 2; ++bb)
 #pragma unroll
-      for (int bb = 0; bb < 2; ++bb)
+      for (int c = 0; c < 2; ++c) {
+        if (!ok[bb][c]) continue;
+        uint32_t o[4];
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          if (!ok[bb][c]) continue;
-          uint32_t o[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const f32x2 r = a == 0 ? f2_fma(za1, pc.v[bb][c][j], f2_fma(za0, pm.v[bb][c][j], zero))
-                                   : f2_fma(zb1, pn.v[bb][c][j], f2_fma(zb0, pc.v[bb][c][j], zero));
-            float lo, hi;
-            f2_unpack(r, lo, hi);
-            o[j] = pack_bf16x2(lo, hi);
-          }
-          *reinterpret_cast<uint4*>(oplane + ooff[bb][c]) = make_uint4(o[0], o[1], o[2], o[3]);
+        for (int j = 0; j < 4; ++j) {
+          const f32x2 r = f2_fma(wh, hi.v[bb][c][j], f2_fma(wl, lo.v[bb][c][j], zero));
+          float a, d;
+          f2_unpack(r, a, d);
+          o[j] = pack_bf16x2(a, d);
         }
+        *reinterpret_cast<uint4*>(oplane + ooff[bb][c]) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+  };
+
+  PlaneLoads ld;
+  PlaneXY pc, pn;  // interpolated planes zj and zj+1
+  {
+    // prologue: output 2*zj_begin blends planes (zj_begin-1, zj_begin)
+    PlaneXY pm;
+    upsample_load(ibase + (size_t)max(zj_begin - 1, 0) * in_plane, off, ld);
+    upsample_plane_xy(ld, ty, tx, pm);
+    upsample_load(ibase + (size_t)zj_begin * in_plane, off, ld);
+    upsample_plane_xy(ld, ty, tx, pc);
+    const AxisTaps tz = axis_taps(zj_begin, Di);
+    emit(2 * zj_begin, tz.a0, tz.a1, pm, pc);
+  }
+  upsample_load(ibase + (size_t)min(zj_begin + 1, Di - 1) * in_plane, off, ld);
+  for (int zj = zj_begin; zj < zj_end; ++zj) {
+    upsample_plane_xy(ld, ty, tx, pn);  // plane min(zj+1, Di-1) (clamped: window element 2)
+    if (zj + 1 < zj_end) upsample_load(ibase + (size_t)min(zj + 2, Di - 1) * in_plane, off, ld);
+    const AxisTaps tz = axis_taps(zj, Di);
+    emit(2 * zj + 1, tz.b0, tz.b1, pc, pn);
+    if (zj + 1 < zj_end) {
+      const AxisTaps tn = axis_taps(zj + 1, Di);
+      emit(2 * zj + 2, tn.a0, tn.a1, pc, pn);
     }
-    pm = pc;
     pc = pn;
   }
 }
