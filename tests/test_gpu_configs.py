@@ -77,3 +77,25 @@ def test_config5_watershed_adapted_rand_agreement():
           "segments", int(seg_ref.max()))
     assert score >= 0.99, score
     assert frag_score >= 0.9, frag_score
+
+
+@pytest.mark.parametrize("patch,overlap,trim,shape", [
+    ((32, 48, 80), (8, 16, 16), 4, (70, 100, 150)),     # anisotropic: mixes K1z2 / K1 paths per level
+    ((64, 32, 112), (16, 8, 32), 8, (64, 60, 200)),     # levels with H % 16 != 0 and W % 8 != 0
+])
+def test_anisotropic_patch_shapes_match_oracle(patch, overlap, trim, shape):
+    """Every multiple-of-16 patch shape must work: layers that do not meet a fast kernel's shape
+    rules fall back to the generic tcgen05 kernel, never to wrong results."""
+    from aind_exaspim_neuron_segmentation_b200 import predict
+    from oracle.predict_ref import predict_ref
+    from oracle.unet_ref import make_forward_fn
+
+    sd = state_dict_for("rescaled", 51)
+    vol = lightsheet_volume(shape, 52)
+    kw = dict(patch_shape=patch, overlap=overlap, trim=trim)
+    ref = predict_ref(vol, make_forward_fn(sd), **kw)
+    out = predict(vol, _model(51, "bf16"), verbose=False, **kw)
+    err = float(np.abs(out - ref).max())
+    print(patch, "max abs err", err)
+    assert err <= BF16_TOL, err
+    assert np.array_equal(out == 0, ref == 0)
