@@ -6,34 +6,34 @@
 
 namespace exa {
 
-Status launch_stem_tc(const __nv_bfloat16* xhi, const __nv_bfloat16* xlo, const __nv_bfloat16* w_band,
-                      const float* bias, const Act& out, int num_sms, cudaStream_t s) {
+Status launch_stem_tc(const __nv_bfloat16* xs, const __nv_bfloat16* w_band, const float* bias,
+                      const Act& out, int num_sms, cudaStream_t s) {
   EXA_CHECK(!out.fp32 && out.C == 32 && out.cstride == 32 && out.coff == 0,
             "stem_tc: output must be dense bf16 C=32");
-  EXA_CHECK(out.D % 16 == 0 && out.H % 8 == 0 && out.W % 8 == 0, "stem_tc: patch dims");
+  EXA_CHECK(out.D % 16 == 0 && out.H % 8 == 0 && out.W % 4 == 0, "stem_tc: patch dims");
   StemTcArgs a{};
   a.B = out.B;
   a.P[0] = out.D; a.P[1] = out.H; a.P[2] = out.W;
-  a.ntz = out.D / 16; a.nty = out.H / 8; a.ntx = out.W / 8;
+  a.ntz = out.D / 16; a.nty = out.H / 8; a.ntx = ceil_div(out.W, 4 * STEM_SUBS);
   a.tiles_total = out.B * a.ntz * a.nty * a.ntx;
   a.bias = bias;
   a.out = (__nv_bfloat16*)out.ptr;
-  CUtensorMap thi, tlo, tw;
+  CUtensorMap tx, tw;
   {
-    // normalised input, x innermost, rows padded to W + 16 with voxel x at index x + 1
-    // (launch_stem_split): 4-D (Xp, Y, Z, B), box (16, 10, 18, 1)
-    const uint64_t wp = (uint64_t)out.W + 16;
-    uint64_t dims[4] = {wp, (uint64_t)out.H, (uint64_t)out.D, (uint64_t)out.B};
-    uint64_t strides[3] = {wp * 2, wp * out.H * 2, wp * out.H * out.D * 2};
-    uint32_t box[4] = {16, 10, 18, 1};
-    EXA_TRY(make_tmap_bf16(&thi, (void*)xhi, 4, dims, strides, box, 32));
-    EXA_TRY(make_tmap_bf16(&tlo, (void*)xlo, 4, dims, strides, box, 32));
+    // normalised input as interleaved (hi, lo) bf16 pairs, x innermost, rows padded to W + 8
+    // voxels with voxel x at index x + 1 (launch_stem_split): 4-D (2*Xp, Y, Z, B) in bf16
+    // elements, box (64 = 32 voxels, 10, 18, 1)
+    const uint64_t wp = (uint64_t)out.W + 8;
+    uint64_t dims[4] = {2 * wp, (uint64_t)out.H, (uint64_t)out.D, (uint64_t)out.B};
+    uint64_t strides[3] = {wp * 4, wp * out.H * 4, wp * out.H * out.D * 4};
+    uint32_t box[4] = {64, 10, 18, 1};  // 32 voxels per row: one box serves six x sub-tiles
+    EXA_TRY(make_tmap_bf16(&tx, (void*)xs, 4, dims, strides, box, 128));
   }
   {
-    // band matrices: 3-D (16 x', 256 (xo, c), 9 (kz, ky)), box (16, 256, 1)
-    uint64_t dims[3] = {16, 256, 9};
-    uint64_t strides[2] = {32, 32 * 256};
-    uint32_t box[3] = {16, 256, 1};
+    // band matrices: 3-D (16 = 8 x' x (hi, lo), 128 = (xo, c), 9 = (kz, ky)), box (16, 128, 1)
+    uint64_t dims[3] = {16, 128, 9};
+    uint64_t strides[2] = {32, 32 * 128};
+    uint32_t box[3] = {16, 128, 1};
     EXA_TRY(make_tmap_bf16(&tw, (void*)w_band, 3, dims, strides, box, 32));
   }
   static bool configured = false;
@@ -43,7 +43,7 @@ Status launch_stem_tc(const __nv_bfloat16* xhi, const __nv_bfloat16* xlo, const 
     configured = true;
   }
   const int grid = a.tiles_total < num_sms ? a.tiles_total : num_sms;
-  stem_tc_kernel<<<grid, ZF_THREADS, StemTcSmem::TOTAL, s>>>(thi, tlo, tw, a);
+  stem_tc_kernel<<<grid, ZF_THREADS, StemTcSmem::TOTAL, s>>>(tx, tw, a);
   EXA_CUDA(cudaGetLastError());
   return Status::OK();
 }

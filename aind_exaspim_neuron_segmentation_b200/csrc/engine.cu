@@ -423,15 +423,17 @@ Status Engine::finalize_weights() {
         for (int co = 0; co < 32; ++co) stem_.w[tap][co] = (float)wsrc(co, 0, tap);
       for (int co = 0; co < 32; ++co) stem_.b[co] = bias[co];
       if (precision_ == EXA_PRECISION_BF16) {
-        // Toeplitz (band) form for the tensor-core stem: B[kz,ky][n = xo*32 + c][k = x'] =
-        // w[c][kz][ky][kx = x' - xo], bf16-rounded once like every other layer's weights
-        std::vector<uint16_t> band((size_t)9 * 256 * 16, 0);
+        // Toeplitz (band) form for the tensor-core stem (conv_stem.cuh): B[kz,ky][n = xo*32 + c]
+        // [k = 2*x' + part] = w[c][kz][ky][kx = x' - xo] for both the hi and the lo part of the
+        // input, bf16-rounded once like every other layer's weights
+        std::vector<uint16_t> band((size_t)9 * 128 * 16, 0);
         for (int t9 = 0; t9 < 9; ++t9)
-          for (int xo = 0; xo < 8; ++xo)
+          for (int xo = 0; xo < 4; ++xo)
             for (int c = 0; c < 32; ++c)
               for (int kx = 0; kx < 3; ++kx)
-                band[((size_t)t9 * 256 + xo * 32 + c) * 16 + xo + kx] =
-                    f32_to_bf16_rn(stem_.w[t9 * 3 + kx][c]);
+                for (int part = 0; part < 2; ++part)
+                  band[((size_t)t9 * 128 + xo * 32 + c) * 16 + 2 * (xo + kx) + part] =
+                      f32_to_bf16_rn(stem_.w[t9 * 3 + kx][c]);
         free_dev(stem_band_);
         free_dev(stem_bias_);
         stem_band_ = nullptr;
@@ -500,9 +502,9 @@ WsLayout layout(int B, int pz, int py, int px) {
     off += (n + 127) / 128 * 128;  // 256-byte alignment for bf16, more for fp32
     return o;
   };
-  // normalised input, bf16 hi / lo parts, rows padded to px + 16 (tensor-core stem)
-  L.xhi = take((size_t)B * pz * py * (px + 16));
-  L.xlo = take((size_t)B * pz * py * (px + 16));
+  // normalised input as interleaved bf16 (hi, lo) pairs, rows padded to px + 8 voxels
+  L.xhi = take((size_t)B * pz * py * (px + 8) * 2);
+  L.xlo = 0;
   L.a0 = take(vox(0) * 32);    // inc.0 output; re-used for up4.0 output (A0 is dead by then)
   L.cat4 = take(vox(0) * 64);  // [x1 | up(u3)]
   L.p1 = take(vox(1) * 32);
@@ -646,17 +648,16 @@ Status Engine::run_network(const PatchSource& src, int batch, int pz, int py, in
     p_ups = &r_ups;
   }
 
-  if (!f32 && use_tc_stem_ && pz % 16 == 0 && py % 8 == 0 && px % 8 == 0) {
-    // inc.0 on the tensor cores: gather/normalise into bf16 hi+lo, then the Toeplitz-form conv
-    __nv_bfloat16* xhi = (__nv_bfloat16*)((char*)ws_ + L.xhi * esz);
-    __nv_bfloat16* xlo = (__nv_bfloat16*)((char*)ws_ + L.xlo * esz);
+  if (!f32 && use_tc_stem_ && pz % 16 == 0 && py % 8 == 0 && px % 4 == 0) {
+    // inc.0 on the tensor cores: gather/normalise into bf16 (hi, lo) pairs, then the Toeplitz-form conv
+    __nv_bfloat16* xs = (__nv_bfloat16*)((char*)ws_ + L.xhi * esz);
     {
       Scope sc(this, CAT_STEM, s);
-      EXA_TRY(launch_stem_split(src, batch, pz, py, px, xhi, xlo, s));
+      EXA_TRY(launch_stem_split(src, batch, pz, py, px, xs, s));
     }
     {
       Scope sc(this, CAT_STEM, s);
-      EXA_TRY(launch_stem_tc(xhi, xlo, stem_band_, stem_bias_, a0, num_sms_, s));
+      EXA_TRY(launch_stem_tc(xs, stem_band_, stem_bias_, a0, num_sms_, s));
     }
   } else {
     Scope sc(this, CAT_STEM, s);

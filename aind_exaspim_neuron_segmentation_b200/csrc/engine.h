@@ -115,7 +115,7 @@ class Engine {
   std::map<std::string, HostTensor> raw_;
   ConvLayer layers_[18];
   StemWeights stem_{};
-  __nv_bfloat16* stem_band_ = nullptr;  // [9 (kz,ky)][256 (xo,c)][16 x'] Toeplitz weights (conv_stem.cuh)
+  __nv_bfloat16* stem_band_ = nullptr;  // [9 (kz,ky)][128 (xo,c)][16 (x',hi|lo)] Toeplitz weights (conv_stem.cuh)
   float* stem_bias_ = nullptr;          // [32]
   bool use_tc_stem_ = true;             // EXA_NO_TC_STEM=1: SIMT fp32 stem also in bf16 mode
   float* head_w_ = nullptr;

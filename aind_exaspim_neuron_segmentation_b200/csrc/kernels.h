@@ -70,10 +70,11 @@ struct StitchArgs {
 
 Status launch_stem(const PatchSource& src, const StemWeights& w, const Act& out, cudaStream_t s);
 // tensor-core stem (bf16 mode): input split into bf16 hi/lo, then the Toeplitz-form conv
-Status launch_stem_split(const PatchSource& src, int B, int Pz, int Py, int Px, __nv_bfloat16* xhi,
-                         __nv_bfloat16* xlo, cudaStream_t s);
-Status launch_stem_tc(const __nv_bfloat16* xhi, const __nv_bfloat16* xlo, const __nv_bfloat16* w_band,
-                      const float* bias, const Act& out, int num_sms, cudaStream_t s);
+// xs: interleaved (hi, lo) bf16 pairs, [B][Pz][Py][Px + 8] voxels (2 bf16 each)
+Status launch_stem_split(const PatchSource& src, int B, int Pz, int Py, int Px, __nv_bfloat16* xs,
+                         cudaStream_t s);
+Status launch_stem_tc(const __nv_bfloat16* xs, const __nv_bfloat16* w_band, const float* bias,
+                      const Act& out, int num_sms, cudaStream_t s);
 Status launch_conv_umma(const Act& in, const Act& out, const __nv_bfloat16* w_packed,
                         const float* bias, const HeadParams* head, int num_sms, cudaStream_t s);
 // Output sub-box [lo, hi) (z, y, x) a conv has to produce; voxels outside are left untouched.

@@ -268,65 +268,69 @@ Status launch_stem(const PatchSource& src, const StemWeights& w, const Act& out,
 }
 
 // K0b for the tensor-core stem: gather + clip + normalise + far-end reflect padding
-// (inference.py:79-80,188-191; img_util.py:378-379,424-428,526-531), written as a bf16 hi/lo
-// pair per voxel (x = hi + lo to 2^-17 relative), x innermost: [B][Pz][Py][Px].
+// (inference.py:79-80,188-191; img_util.py:378-379,424-428,526-531), written as an interleaved
+// bf16 (hi, lo) pair per voxel (x = hi + lo to 2^-17 relative), x innermost: [B][Pz][Py][Px+8].
+// Voxel x is stored at index x + 1: element 0 and the tail are zeros (the conv's zero padding),
+// so that every 8-voxel window the tensor-core stem fetches starts at a multiple of 4 voxels
+// (TMA needs 16 B aligned innermost offsets).
 template <bool FROM_VOLUME>
 __global__ void __launch_bounds__(256)
-stem_split_kernel(const StemArgs a, __nv_bfloat16* __restrict__ xhi, __nv_bfloat16* __restrict__ xlo) {
-  // Rows are padded to Wp = Px + 16 with the voxel x stored at index x + 1: element 0 and the
-  // tail are zeros (the conv's zero padding), so that every 16-element window the tensor-core
-  // stem fetches starts at a multiple of 8 elements (TMA needs 16 B aligned innermost offsets).
-  // grid: x = (py, pair of row elements), y = pz, z = b
-  const int Wp = a.Px + 16;
-  const unsigned hw = (unsigned)Wp / 2;
+stem_split_kernel(const StemArgs a, __nv_bfloat162* __restrict__ xs) {
+  // grid: x = (py, group of 4 row elements), y = pz, z = b; one 16 B store per thread
+  const int Wp = a.Px + 8;
+  const unsigned gw = (unsigned)Wp / 4;
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (unsigned)a.Py * hw) return;
-  const int xp = 2 * (int)(i % hw), py = (int)(i / hw), pz = blockIdx.y, b = blockIdx.z;
-  float v[2] = {0.f, 0.f};
-  int sz = 0, sy = 0, sx = 0, Lx = 0;
+  if (i >= (unsigned)a.Py * gw) return;
+  const int xp = 4 * (int)(i % gw), py = (int)(i / gw), pz = blockIdx.y, b = blockIdx.z;
+  int sx = 0, Lx = 0;
   size_t rowi = 0;
   if (FROM_VOLUME) {
-    sz = a.src.starts[3 * b + 0]; sy = a.src.starts[3 * b + 1]; sx = a.src.starts[3 * b + 2];
+    const int sz = a.src.starts[3 * b + 0], sy = a.src.starts[3 * b + 1];
+    sx = a.src.starts[3 * b + 2];
     const int Lz = min(a.Pz, a.src.gD - sz), Ly = min(a.Py, a.src.gH - sy);
     Lx = min(a.Px, a.src.gW - sx);
     const int gz = sz + (pz < Lz ? pz : reflect_index(pz, Lz));
     const int gy = sy + (py < Ly ? py : reflect_index(py, Ly));
     rowi = ((size_t)(gz - a.src.vz0) * a.src.gH + gy) * a.src.gW;
+  } else {
+    rowi = (((size_t)b * a.Pz + pz) * a.Py + py) * a.Px;
   }
+  uint32_t w[4];
 #pragma unroll
-  for (int k = 0; k < 2; ++k) {
+  for (int k = 0; k < 4; ++k) {
     const int px = xp + k - 1;
-    if (px < 0 || px >= a.Px) continue;
-    if (FROM_VOLUME) {
-      const int gx = sx + (px < Lx ? px : reflect_index(px, Lx));
-      const int raw = min((int)__ldg(a.src.vol + rowi + gx), a.src.clip);
-      v[k] = __ldg(a.src.lut + raw);
-    } else {
-      v[k] = __ldg(a.src.x + (((size_t)b * a.Pz + pz) * a.Py + py) * a.Px + px);
+    float v = 0.f;
+    if (px >= 0 && px < a.Px) {
+      if (FROM_VOLUME) {
+        const int gx = sx + (px < Lx ? px : reflect_index(px, Lx));
+        v = __ldg(a.src.lut + min((int)__ldg(a.src.vol + rowi + gx), a.src.clip));
+      } else {
+        v = __ldg(a.src.x + rowi + px);
+      }
     }
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+    __nv_bfloat162 hl;
+    hl.x = h;
+    hl.y = l;
+    w[k] = *reinterpret_cast<uint32_t*>(&hl);
   }
-  const __nv_bfloat16 h0 = __float2bfloat16_rn(v[0]), h1 = __float2bfloat16_rn(v[1]);
-  const __nv_bfloat16 l0 = __float2bfloat16_rn(v[0] - __bfloat162float(h0));
-  const __nv_bfloat16 l1 = __float2bfloat16_rn(v[1] - __bfloat162float(h1));
   const size_t o = (((size_t)b * a.Pz + pz) * a.Py + py) * Wp + xp;
-  __nv_bfloat162 hh, ll;
-  hh.x = h0; hh.y = h1; ll.x = l0; ll.y = l1;
-  *reinterpret_cast<__nv_bfloat162*>(xhi + o) = hh;
-  *reinterpret_cast<__nv_bfloat162*>(xlo + o) = ll;
+  *reinterpret_cast<uint4*>(xs + o) = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-Status launch_stem_split(const PatchSource& src, int B, int Pz, int Py, int Px, __nv_bfloat16* xhi,
-                         __nv_bfloat16* xlo, cudaStream_t s) {
-  EXA_CHECK(Px % 8 == 0 && Pz <= 65535 && B <= 65535, "stem_split: patch dims");
+Status launch_stem_split(const PatchSource& src, int B, int Pz, int Py, int Px, __nv_bfloat16* xs,
+                         cudaStream_t s) {
+  EXA_CHECK(Px % 4 == 0 && Pz <= 65535 && B <= 65535, "stem_split: patch dims");
   StemArgs a;
   a.src = src;
   a.B = B; a.Pz = Pz; a.Py = Py; a.Px = Px;
   a.out = nullptr;
-  const dim3 grid((unsigned)ceil_div(Py * ((Px + 16) / 2), 256), (unsigned)Pz, (unsigned)B);
+  const dim3 grid((unsigned)ceil_div(Py * ((Px + 8) / 4), 256), (unsigned)Pz, (unsigned)B);
   const bool from_vol = src.vol != nullptr;
   EXA_CHECK(from_vol || src.x != nullptr, "stem_split: no input source");
-  if (from_vol) stem_split_kernel<true><<<grid, 256, 0, s>>>(a, xhi, xlo);
-  else stem_split_kernel<false><<<grid, 256, 0, s>>>(a, xhi, xlo);
+  if (from_vol) stem_split_kernel<true><<<grid, 256, 0, s>>>(a, (__nv_bfloat162*)xs);
+  else stem_split_kernel<false><<<grid, 256, 0, s>>>(a, (__nv_bfloat162*)xs);
   EXA_CUDA(cudaGetLastError());
   return Status::OK();
 }
