@@ -129,6 +129,14 @@ _SIGNATURES = {
                                        ctypes.c_void_p]),
     "exa_slab_stitch_strided": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                                ctypes.c_int64, ctypes.c_void_p]),
+    "exa_slab_predict": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_int, ctypes.POINTER(PredictParams), ctypes.c_int,
+                                        ctypes.c_int, ctypes.c_void_p, ctypes.c_int64,
+                                        ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+                                        ctypes.c_void_p]),
+    "exa_slab_finish": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
+                                       ctypes.c_void_p]),
     "exa_count_patches": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                          ctypes.POINTER(ctypes.c_int32),
                                          ctypes.POINTER(ctypes.c_int32)]),

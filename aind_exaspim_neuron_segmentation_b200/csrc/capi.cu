@@ -185,6 +185,25 @@ int exa_slab_stitch_strided(exa_engine* e, const float* seed_dev, float* out_dev
   });
 }
 
+int exa_slab_predict(exa_engine* e, const uint16_t* slab_dev, int D, int H, int W,
+                     const exa_predict_params* p, int row_begin, int row_end, float* out_dev,
+                     int64_t channel_stride, float* out_host, int64_t host_channel_stride,
+                     float* halo_dev, void* stream) {
+  return guarded(e, [&] {
+    EXA_CHECK(p != nullptr, "slab_predict: null params");
+    return e->impl.slab_predict(slab_dev, D, H, W, *p, row_begin, row_end, out_dev, channel_stride,
+                                out_host, host_channel_stride, halo_dev, (cudaStream_t)stream);
+  });
+}
+
+int exa_slab_finish(exa_engine* e, const float* seed_dev, float* out_dev, int64_t channel_stride,
+                    float* out_host, int64_t host_channel_stride, void* stream) {
+  return guarded(e, [&] {
+    return e->impl.slab_finish(seed_dev, out_dev, channel_stride, out_host, host_channel_stride,
+                               (cudaStream_t)stream);
+  });
+}
+
 int exa_count_patches(int D, int H, int W, const int32_t patch[3], const int32_t overlap[3]) {
   if (!patch || !overlap) return EXA_ERR_INVALID;
   const int dims[3] = {D, H, W};

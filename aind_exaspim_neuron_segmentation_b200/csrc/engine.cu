@@ -163,6 +163,8 @@ Engine::~Engine() {
   free_dev(starts_dev_);
   free_dev(hist_dev_);
   free_dev(seed_);
+  free_dev(probs_hold_);
+  if (copy_event_) cudaEventDestroy(copy_event_);
   free_dev(vol_stage_);
   free_dev(out_stage_);
   if (copy_stream_) cudaStreamDestroy(copy_stream_);
@@ -890,10 +892,130 @@ Status Engine::stitch_planes(const float* seed_dev, float* out_dev, size_t out_c
   return launch_stitch(a, s);
 }
 
-// Whole volume in groups of z patch-rows.  Each group is a slab job: run its patches, stitch the
-// planes it owns (seeded with the previous group's partial sums for the shared planes, so the
-// fp32 summation order is the reference's), hand partial sums to the next group.  Finished
-// planes are copied to the host on a second stream while the next group computes.
+// Rows [R0, R1) of the volume in groups of z patch-rows.  Each group is a slab job: run its
+// patches, stitch the planes it owns (seeded with the previous group's partial sums for the shared
+// planes, so the fp32 summation order is the reference's), hand partial sums to the next group.
+// Finished planes are copied to the host on a second stream while the next group computes.
+// vol_dev points at plane vol_z0; out_dev / out_host at plane out_zbase (channel strides in
+// elements).  The last group's partial sums for the next rank go to halo_out.  With defer_seed the
+// planes of the first group that need the previous rank's partial sums are left out (their
+// patches stay in a held buffer) until pipeline_finish() gets that seed.
+Status Engine::pipeline_rows(const uint16_t* vol_dev, int vol_z0, int D, int H, int W,
+                             const exa_predict_params& p, int R0, int R1, float* out_dev,
+                             size_t out_cstride, float* out_host, size_t host_cstride,
+                             int out_zbase, float* halo_out, bool defer_seed, cudaStream_t s) {
+  Plan plan;
+  EXA_TRY(make_plan(D, H, W, p, &plan));
+  EXA_CHECK(R0 >= 0 && R0 <= R1 && R1 <= plan.az.n, "row range out of bounds");
+  const size_t plane = (size_t)H * W;
+  held_valid_ = false;
+  // group size: at least one wave of patches per group; a single group when planes can be
+  // covered by more than two rows (no pairwise hand-over possible)
+  const int per_row = plan.ay.n * plan.ax.n;
+  const int batch = p.batch > 0 ? p.batch : 32;
+  int rows_per_group = std::max(1, ceil_div(batch, per_row));
+  const int keep = plan.az.patch - 2 * plan.az.trim;
+  if (keep > 2 * plan.az.stride) rows_per_group = plan.az.n;
+  if (out_host && !copy_stream_) {
+    EXA_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+  }
+  const size_t seed_elems = (size_t)out_channels_ * keep * plane;  // upper bound on shared planes
+  if (rows_per_group < R1 - R0 && seed_elems * sizeof(float) > seed_bytes_) {
+    free_dev(seed_);
+    seed_ = nullptr;
+    seed_bytes_ = 0;
+    EXA_CUDA(cudaMalloc(&seed_, seed_elems * sizeof(float)));
+    seed_bytes_ = seed_elems * sizeof(float);
+  }
+  Status st = Status::OK();
+  bool have_seed = false;
+  for (int r0 = R0; r0 < R1 && st.ok; r0 += rows_per_group) {
+    const int r1 = std::min(r0 + rows_per_group, R1);
+    st = slab_run(vol_dev + (size_t)(r0 * plan.az.stride - vol_z0) * plane, D, H, W, p, r0, r1, s);
+    if (!st.ok) break;
+    const bool first = r0 == R0, last = r1 == R1;
+    const bool hold = first && defer_seed && slab_.seed_z1 > slab_.seed_z0;
+    const int z0 = hold ? slab_.seed_z1 : slab_.out_z0, z1 = slab_.out_z1;
+    if (z1 > z0) {
+      st = stitch_planes(have_seed ? seed_ : nullptr, out_dev + (size_t)(z0 - out_zbase) * plane,
+                         out_cstride, z0, z1, s);
+      if (!st.ok) break;
+    }
+    have_seed = slab_.halo_z1 > slab_.halo_z0;
+    if (have_seed) {  // after the stitch above has consumed the previous seed
+      if (last && halo_out == nullptr) {
+        st = Status::Err("slab_predict: rows end before the volume does but no halo buffer given");
+        break;
+      }
+      st = slab_partial(last ? halo_out : seed_, s);
+      if (!st.ok) break;
+      if (last) have_seed = false;
+    }
+    if (hold) {  // later groups write their patches to the other buffer
+      held_slab_ = slab_;
+      held_plan_ = plan_;
+      held_rows_[0] = r0;
+      held_rows_[1] = r1;
+      std::swap(probs_, probs_hold_);
+      std::swap(probs_bytes_, probs_hold_bytes_);
+      held_valid_ = true;
+      job_ready_ = false;
+    }
+    if (out_host && z1 > z0) st = copy_planes_to_host(out_dev, out_cstride, out_host, host_cstride,
+                                                     out_zbase, z0, z1, plane, s);
+  }
+  return st;
+}
+
+// D2H of finished planes [z0, z1) on the copy stream, ordered after the work queued on s so far
+Status Engine::copy_planes_to_host(const float* out_dev, size_t out_cstride, float* out_host,
+                                   size_t host_cstride, int out_zbase, int z0, int z1, size_t plane,
+                                   cudaStream_t s) {
+  if (!copy_event_) EXA_CUDA(cudaEventCreateWithFlags(&copy_event_, cudaEventDisableTiming));
+  EXA_CUDA(cudaEventRecord(copy_event_, s));
+  EXA_CUDA(cudaStreamWaitEvent(copy_stream_, copy_event_, 0));
+  for (int c = 0; c < out_channels_; ++c) {
+    const size_t zoff = (size_t)(z0 - out_zbase) * plane;
+    EXA_CUDA(cudaMemcpyAsync(out_host + c * host_cstride + zoff, out_dev + c * out_cstride + zoff,
+                             (size_t)(z1 - z0) * plane * 4, cudaMemcpyDeviceToHost, copy_stream_));
+  }
+  return Status::OK();
+}
+
+// Second half of a deferred pipeline: stitch the held planes with the previous rank's partial
+// sums, copy them out and wait for every copy of the job.
+Status Engine::pipeline_finish(const float* seed_in, float* out_dev, size_t out_cstride,
+                               float* out_host, size_t host_cstride, int out_zbase,
+                               cudaStream_t s) {
+  Status st = Status::OK();
+  if (held_valid_) {
+    std::swap(probs_, probs_hold_);
+    std::swap(probs_bytes_, probs_hold_bytes_);
+    slab_ = held_slab_;
+    plan_ = held_plan_;
+    row_begin_ = held_rows_[0];
+    row_end_ = held_rows_[1];
+    job_ready_ = true;
+    held_valid_ = false;
+    const int z0 = slab_.seed_z0, z1 = slab_.seed_z1;
+    const size_t plane = (size_t)plan_.H * plan_.W;
+    if (seed_in == nullptr) {
+      st = Status::Err("slab_finish: the first rows share planes with the previous rank: seed needed");
+    } else {
+      st = stitch_planes(seed_in, out_dev + (size_t)(z0 - out_zbase) * plane, out_cstride, z0, z1, s);
+    }
+    if (st.ok && out_host)
+      st = copy_planes_to_host(out_dev, out_cstride, out_host, host_cstride, out_zbase, z0, z1,
+                               plane, s);
+  }
+  if (out_host && copy_stream_) {
+    cudaError_t e = cudaStreamSynchronize(copy_stream_);
+    if (e != cudaSuccess && st.ok)
+      st = Status::Err(std::string("predict: D2H failed: ") + cudaGetErrorString(e));
+  }
+  return st;
+}
+
 Status Engine::predict_pipeline(const uint16_t* vol_dev, int D, int H, int W,
                                 const exa_predict_params& p, float* out_dev, float* out_host,
                                 cudaStream_t s) {
@@ -918,58 +1040,41 @@ Status Engine::predict_pipeline(const uint16_t* vol_dev, int D, int H, int W,
     }
     return Status::OK();
   }
-  // group size: at least one wave of patches per group; a single group when planes can be
-  // covered by more than two rows (no pairwise hand-over possible)
-  const int per_row = plan.ay.n * plan.ax.n;
-  const int batch = p.batch > 0 ? p.batch : 32;
-  int rows_per_group = std::max(1, ceil_div(batch, per_row));
-  const int keep = plan.az.patch - 2 * plan.az.trim;
-  if (keep > 2 * plan.az.stride) rows_per_group = plan.az.n;
-  if (out_host && !copy_stream_) {
-    EXA_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
-  }
-  const size_t seed_elems = (size_t)out_channels_ * keep * plane;  // upper bound on shared planes
-  if (rows_per_group < plan.az.n && seed_elems * sizeof(float) > seed_bytes_) {
-    free_dev(seed_);
-    seed_ = nullptr;
-    seed_bytes_ = 0;
-    EXA_CUDA(cudaMalloc(&seed_, seed_elems * sizeof(float)));
-    seed_bytes_ = seed_elems * sizeof(float);
-  }
-  std::vector<cudaEvent_t> events;
-  Status st = Status::OK();
-  bool have_seed = false;
-  for (int r0 = 0; r0 < plan.az.n && st.ok; r0 += rows_per_group) {
-    const int r1 = std::min(r0 + rows_per_group, plan.az.n);
-    st = slab_run(vol_dev + (size_t)(r0 * plan.az.stride) * plane, D, H, W, p, r0, r1, s);
-    if (!st.ok) break;
-    const int z0 = slab_.out_z0, z1 = slab_.out_z1;
-    st = stitch_planes(have_seed ? seed_ : nullptr, out_dev + (size_t)z0 * plane, nvox, z0, z1, s);
-    if (!st.ok) break;
-    have_seed = slab_.halo_z1 > slab_.halo_z0;
-    if (have_seed) {
-      st = slab_partial(seed_, s);  // after the stitch above has consumed the previous seed
-      if (!st.ok) break;
-    }
-    if (out_host && z1 > z0) {
-      cudaEvent_t ev;
-      EXA_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-      events.push_back(ev);
-      EXA_CUDA(cudaEventRecord(ev, s));
-      EXA_CUDA(cudaStreamWaitEvent(copy_stream_, ev, 0));
-      for (int c = 0; c < out_channels_; ++c) {
-        const size_t off = (size_t)c * nvox + (size_t)z0 * plane;
-        EXA_CUDA(cudaMemcpyAsync(out_host + off, out_dev + off, (size_t)(z1 - z0) * plane * 4,
-                                 cudaMemcpyDeviceToHost, copy_stream_));
-      }
-    }
-  }
-  if (out_host) {
-    cudaError_t e = cudaStreamSynchronize(copy_stream_);
-    if (e != cudaSuccess && st.ok)
-      st = Status::Err(std::string("predict: D2H failed: ") + cudaGetErrorString(e));
-  }
-  for (cudaEvent_t ev : events) cudaEventDestroy(ev);
+  Status st = pipeline_rows(vol_dev, 0, D, H, W, p, 0, plan.az.n, out_dev, nvox, out_host, nvox, 0,
+                            nullptr, false, s);
+  Status fin = pipeline_finish(nullptr, out_dev, nvox, out_host, nvox, 0, s);
+  return st.ok ? fin : st;
+}
+
+// One rank's rows of a sharded volume (normalisation already set): everything but the planes
+// shared with the previous rank is finished and on its way to the host when this returns.
+Status Engine::slab_predict(const uint16_t* slab_dev, int D, int H, int W,
+                            const exa_predict_params& p, int row_begin, int row_end, float* out_dev,
+                            int64_t channel_stride, float* out_host, int64_t host_channel_stride,
+                            float* halo_dev, cudaStream_t s) {
+  EXA_CUDA(cudaSetDevice(device_));
+  Plan plan;
+  EXA_TRY(make_plan(D, H, W, p, &plan));
+  exa_slab_plan whole;
+  EXA_TRY(plan_slab(plan, row_begin, row_end, &whole));
+  pipe_zbase_ = whole.out_z0;
+  if (row_begin == row_end) return Status::OK();
+  const size_t dense = (size_t)std::max(whole.out_z1 - whole.out_z0, 0) * H * W;
+  EXA_CHECK(slab_dev && (out_dev || dense == 0), "slab_predict: null buffer");
+  EXA_CHECK((size_t)channel_stride >= dense && (!out_host || (size_t)host_channel_stride >= dense),
+            "slab_predict: channel stride too small");
+  return pipeline_rows(slab_dev, whole.in_z0, D, H, W, p, row_begin, row_end, out_dev,
+                       (size_t)channel_stride, out_host, (size_t)host_channel_stride, whole.out_z0,
+                       halo_dev, true, s);
+}
+
+Status Engine::slab_finish(const float* seed_dev, float* out_dev, int64_t channel_stride,
+                           float* out_host, int64_t host_channel_stride, cudaStream_t s) {
+  EXA_CUDA(cudaSetDevice(device_));
+  Status st = pipeline_finish(seed_dev, out_dev, (size_t)channel_stride, out_host,
+                              (size_t)host_channel_stride, pipe_zbase_, s);
+  cudaError_t e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess && st.ok) st = Status::Err(std::string("slab_finish: ") + cudaGetErrorString(e));
   return st;
 }
 

@@ -63,6 +63,13 @@ class Engine {
   Status slab_partial(float* halo_dev, cudaStream_t s);
   // channel_stride = 0: dense (C, out planes, H, W); otherwise elements between channels of out_dev
   Status slab_stitch(const float* seed_dev, float* out_dev, int64_t channel_stride, cudaStream_t s);
+  // rows [row_begin,row_end) as a row-group pipeline with overlapped D2H (out_host may be null);
+  // slab_finish() completes the planes that need the previous rank's partial sums
+  Status slab_predict(const uint16_t* slab_dev, int D, int H, int W, const exa_predict_params& p,
+                      int row_begin, int row_end, float* out_dev, int64_t channel_stride,
+                      float* out_host, int64_t host_channel_stride, float* halo_dev, cudaStream_t s);
+  Status slab_finish(const float* seed_dev, float* out_dev, int64_t channel_stride, float* out_host,
+                     int64_t host_channel_stride, cudaStream_t s);
 
   // per-category kernel timing with CUDA events on the launching stream (bench / roofline)
   enum Category { CAT_HIST = 0, CAT_STEM, CAT_CONV, CAT_POOL, CAT_UPSAMPLE, CAT_HEAD, CAT_STITCH,
@@ -80,6 +87,15 @@ class Engine {
   Status ensure_workspace(int batch, int pz, int py, int px);
   Status predict_pipeline(const uint16_t* vol_dev, int D, int H, int W, const exa_predict_params& p,
                           float* out_dev, float* out_host, cudaStream_t s);
+  Status pipeline_rows(const uint16_t* vol_dev, int vol_z0, int D, int H, int W,
+                       const exa_predict_params& p, int R0, int R1, float* out_dev,
+                       size_t out_cstride, float* out_host, size_t host_cstride, int out_zbase,
+                       float* halo_out, bool defer_seed, cudaStream_t s);
+  Status pipeline_finish(const float* seed_in, float* out_dev, size_t out_cstride, float* out_host,
+                         size_t host_cstride, int out_zbase, cudaStream_t s);
+  Status copy_planes_to_host(const float* out_dev, size_t out_cstride, float* out_host,
+                             size_t host_cstride, int out_zbase, int z0, int z1, size_t plane,
+                             cudaStream_t s);
   Status stitch_planes(const float* seed_dev, float* out_dev, size_t out_cstride, int z0, int z1,
                        cudaStream_t s);
   Status run_network(const PatchSource& src, int batch, int pz, int py, int px,
@@ -149,6 +165,15 @@ class Engine {
   void* out_stage_ = nullptr;
   size_t out_stage_bytes_ = 0;
   cudaStream_t copy_stream_ = nullptr;
+  cudaEvent_t copy_event_ = nullptr;
+  // first row group of a deferred pipeline: its patches wait here for the previous rank's seed
+  float* probs_hold_ = nullptr;
+  size_t probs_hold_bytes_ = 0;
+  bool held_valid_ = false;
+  exa_slab_plan held_slab_{};
+  Plan held_plan_;
+  int held_rows_[2] = {0, 0};
+  int pipe_zbase_ = 0;
 };
 
 }  // namespace exa

@@ -181,6 +181,26 @@ class Engine:
                                                         int(channel_stride), _stream_ptr(self.device)),
                       self._h, "exa_slab_stitch_strided")
 
+    def slab_predict(self, slab_dev, shape, params, row_begin, row_end, out_dev, out_host, halo_dev):
+        """Rows [row_begin,row_end) as a row-group pipeline; out_dev / out_host: dense
+        (C, own planes, H, W) float32 (out_host a host tensor, ideally pinned, or None).  Finish
+        with :meth:`slab_finish` after the halo/seed exchange."""
+        d, h, w = shape
+        cs = out_dev.stride(0) if out_dev.dim() == 4 and out_dev.shape[0] > 1 else out_dev[0].numel()
+        hs = 0 if out_host is None else (out_host.stride(0) if out_host.shape[0] > 1 else out_host[0].numel())
+        code = self._lib.exa_slab_predict(self._h, _ptr(slab_dev), d, h, w, ctypes.byref(params),
+                                          row_begin, row_end, _ptr(out_dev), int(cs),
+                                          _ptr(out_host), int(hs), _ptr(halo_dev),
+                                          _stream_ptr(self.device))
+        _native.check(code, self._h, "exa_slab_predict")
+
+    def slab_finish(self, seed_dev, out_dev, out_host):
+        cs = out_dev.stride(0) if out_dev.shape[0] > 1 else out_dev[0].numel()
+        hs = 0 if out_host is None else (out_host.stride(0) if out_host.shape[0] > 1 else out_host[0].numel())
+        code = self._lib.exa_slab_finish(self._h, _ptr(seed_dev), _ptr(out_dev), int(cs),
+                                         _ptr(out_host), int(hs), _stream_ptr(self.device))
+        _native.check(code, self._h, "exa_slab_finish")
+
 
 # -- host helpers that need no GPU --------------------------------------------------
 def plan_slab(shape, params, row_begin, row_end):

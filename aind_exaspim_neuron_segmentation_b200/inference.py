@@ -204,6 +204,13 @@ class _EngineSlabBackend:
         """Stitch the owned planes straight into full[:, z0:...] of the (C, D, H, W) output."""
         self.engine.slab_stitch(seed, full[:, z0:], channel_stride=full.stride(0))
 
+    def predict_rows(self, slab_u16, shape, params, rows, mn, mx, own, out_host, halo):
+        self.engine.set_normalization(mn, mx, params.brightness_clip)
+        self.engine.slab_predict(slab_u16, shape, params, rows[0], rows[1], own, out_host, halo)
+
+    def finish_rows(self, seed, own, out_host):
+        self.engine.slab_finish(seed, own, out_host)
+
     def to_device(self, host_u16):
         return torch.from_numpy(host_u16).to(self.device, non_blocking=True)
 
@@ -250,6 +257,7 @@ class SlabJob:
         self.own_planes = [max(p["out_z1"] - p["out_z0"], 0) if r[1] > r[0] else 0
                            for p, r in zip(self.all_plans, self.all_rows)]
         self._full = None  # gathered output, allocated once and re-used by every run()
+        self._own = None   # owned planes of run_pipelined(), likewise
 
     def slab_bounds(self):
         """Input planes [z0, z1) this rank needs resident."""
@@ -264,40 +272,79 @@ class SlabJob:
             return group_rank
         return self.dist.get_global_rank(self.group, group_rank)
 
+    def _normalization(self, slab):
+        """C1: global histogram -> exact percentiles (mn, mx)."""
+        be, clip = self.backend, self.params.brightness_clip
+        if self.has_rows and self.hist_range[1] > self.hist_range[0]:
+            z0 = self.plan["in_z0"]
+            hist = be.histogram(slab[self.hist_range[0] - z0:self.hist_range[1] - z0], clip)
+        else:
+            hist = torch.zeros(clip + 1, dtype=torch.int64, device=be.device)
+        if self.world > 1:
+            self.dist.all_reduce(hist, op=self.dist.ReduceOp.SUM, group=self.group)
+        return percentiles_from_hist(hist.cpu().numpy().astype(np.uint64), self.params.pct_lo,
+                                     self.params.pct_hi)
+
+    def _halo_buffer(self):
+        n_halo = self.plan["halo_z1"] - self.plan["halo_z0"] if self.has_rows else 0
+        if self.world == 1 or n_halo <= 0:
+            return None
+        return torch.empty((self.n_channels, n_halo) + self.shape[1:], dtype=torch.float32,
+                           device=self.backend.device)
+
+    def _exchange_halo(self, halo):
+        """C2: partial sums of the shared planes go to their owner (the next rank).  -> seed"""
+        dist = self.dist
+        if self.world == 1 or not self.has_rows:
+            return None
+        ops, seed = [], None
+        n_seed = self.plan["seed_z1"] - self.plan["seed_z0"]
+        if n_seed > 0:
+            seed = torch.empty((self.n_channels, n_seed) + self.shape[1:], dtype=torch.float32,
+                               device=self.backend.device)
+            ops.append(dist.P2POp(dist.irecv, seed, self._peer(self.rank - 1), self.group))
+        if halo is not None:
+            ops.append(dist.P2POp(dist.isend, halo, self._peer(self.rank + 1), self.group))
+        if ops:
+            self.backend.sync()  # partial sums are produced on the engine's stream
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        return seed
+
+    def run_pipelined(self, slab, out_host=None):
+        """``run(slab, gather=False)`` as a row-group pipeline: finished planes are stitched and
+        copied to ``out_host`` (float32 host tensor ``(C, own planes, H, W)``, ideally pinned)
+        while later rows still compute; only the planes shared with the previous rank wait for
+        the C2 exchange.  -> device float32 (C, own, H, W); ``out_host`` is complete on return."""
+        be = self.backend
+        c, (d, h, w) = self.n_channels, self.shape
+        nz_own = self.own_planes[self.rank]
+        if out_host is not None and tuple(out_host.shape) != (c, nz_own, h, w):
+            raise ValueError(f"out_host must have shape {(c, nz_own, h, w)}")
+        mn, mx = self._normalization(slab)
+        own = self._own
+        if own is None or tuple(own.shape) != (c, nz_own, h, w) or own.device != be.device:
+            own = self._own = torch.empty((c, nz_own, h, w), dtype=torch.float32, device=be.device)
+        halo = self._halo_buffer()
+        if self.has_rows:
+            be.predict_rows(slab, self.shape, self.params, self.rows, mn, mx, own, out_host, halo)
+        seed = self._exchange_halo(halo)
+        if self.has_rows:
+            be.finish_rows(seed, own, out_host)
+        return own
+
     def run(self, slab, gather=True):
         """slab: device uint16 planes [in_z0, in_z1).  -> device float32 (C, D|own, H, W)."""
         dist, be, p = self.dist, self.backend, self.params
         dev = be.device
         c, (d, h, w) = self.n_channels, self.shape
-        clip = p.brightness_clip
-        # C1: global histogram -> exact percentiles
-        if self.has_rows and self.hist_range[1] > self.hist_range[0]:
-            z0 = self.plan["in_z0"]
-            hist = be.histogram(slab[self.hist_range[0] - z0:self.hist_range[1] - z0], clip)
-        else:
-            hist = torch.zeros(clip + 1, dtype=torch.int64, device=dev)
-        if self.world > 1:
-            dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=self.group)
-        mn, mx = percentiles_from_hist(hist.cpu().numpy().astype(np.uint64), p.pct_lo, p.pct_hi)
+        mn, mx = self._normalization(slab)
         if self.has_rows:
             be.run(slab, self.shape, p, self.rows, mn, mx)
-        # C2: partial sums of the shared planes go to their owner (the next rank)
-        seed = None
-        if self.world > 1 and self.has_rows:
-            n_halo = self.plan["halo_z1"] - self.plan["halo_z0"]
-            n_seed = self.plan["seed_z1"] - self.plan["seed_z0"]
-            ops, halo = [], None
-            if n_seed > 0:
-                seed = torch.empty((c, n_seed, h, w), dtype=torch.float32, device=dev)
-                ops.append(dist.P2POp(dist.irecv, seed, self._peer(self.rank - 1), self.group))
-            if n_halo > 0:
-                halo = torch.empty((c, n_halo, h, w), dtype=torch.float32, device=dev)
-                be.partial(halo)
-                ops.append(dist.P2POp(dist.isend, halo, self._peer(self.rank + 1), self.group))
-            if ops:
-                be.sync()  # partial sums are produced on the engine's stream
-                for req in dist.batch_isend_irecv(ops):
-                    req.wait()
+        halo = self._halo_buffer()
+        if halo is not None:
+            be.partial(halo)
+        seed = self._exchange_halo(halo)
         nz_own = self.own_planes[self.rank]
         if not gather or self.world == 1:
             own = torch.zeros((c, nz_own, h, w), dtype=torch.float32, device=dev)
@@ -355,13 +402,17 @@ def predict_sharded(
     group=None,
     gather=True,
     backend=None,
+    out=None,
 ):
     """``predict`` sharded by z patch-rows over the ranks of a ``torch.distributed`` group.
 
     One process per GPU; every rank passes the same ``img`` (only its slab, including the
     input halo it shares with the next rank, is uploaded).  With ``gather`` every rank
     returns the full ``(C, D, H, W)`` array; otherwise ``(z0, z1, planes)`` with the planes
-    it owns.  With a world size of 1 this is the same computation as ``predict``.
+    it owns -- those are produced by the row-group pipeline (``SlabJob.run_pipelined``), their
+    device->host copies overlapped with the remaining rows, into ``out`` when given (C-contiguous
+    float32 ``(C, z1 - z0, H, W)``, e.g. pinned memory; ``SlabJob.own_bounds`` gives the range).
+    With a world size of 1 this is the same computation as ``predict``.
     """
     vol = _as_volume_u16(img, brightness_clip)
     if backend is None:
@@ -369,9 +420,14 @@ def predict_sharded(
     params = _native.make_params(patch_shape, overlap, trim, brightness_clip,
                                  normalization_percentiles, batch=max(int(batch_size), 32))
     job = SlabJob(vol.shape, params, 3 if affinity_mode else 1, backend, group)
-    result = job.run(job.upload(vol), gather=gather)
-    out = result.cpu().numpy()
     if gather:
-        return out if affinity_mode else out[0]
+        full = job.run(job.upload(vol), gather=True).cpu().numpy()
+        return full if affinity_mode else full[0]
     z0, z1 = job.own_bounds()
+    shape = (job.n_channels, z1 - z0) + vol.shape[1:]
+    if out is None:
+        out = np.empty(shape, dtype=np.float32)
+    if out.shape != shape or out.dtype != np.float32 or not out.flags.c_contiguous:
+        raise ValueError(f"out must be a C-contiguous float32 array of shape {shape}")
+    job.run_pipelined(job.upload(vol), torch.from_numpy(out))
     return z0, z1, (out if affinity_mode else out[0])

@@ -330,11 +330,9 @@ def run_b200(args):
             # (pinned buffers; H2D, all kernels and the row-pipelined D2H inside the call)
             return predict(host.numpy(), model, verbose=False, patch_shape=PATCH, overlap=OVERLAP,
                            trim=TRIM, batch_size=args.batch, out=host_out.numpy())
-        s = host.to(dev, non_blocking=True)
-        own = job.run(s, gather=False)
-        host_out.copy_(own, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return own
+        # sharded form of the same call (predict_sharded(gather=False, out=...)): every rank
+        # uploads its slab and gets its owned planes in pinned host memory, D2H row-pipelined
+        return job.run_pipelined(host.to(dev, non_blocking=True), host_out)
 
     for _ in range(max(args.warmup, 3)):
         out = step_device()

@@ -125,6 +125,21 @@ int exa_slab_stitch(exa_engine* e, const float* seed_dev, float* out_dev, void* 
  * (C, D, H, W) output, so that the gather of the other ranks' planes needs no re-packing) */
 int exa_slab_stitch_strided(exa_engine* e, const float* seed_dev, float* out_dev,
                             int64_t channel_stride, void* stream);
+/* Rows [row_begin,row_end) as one pipelined job (the sharded form of exa_predict's inner loop,
+ * inference.py:93-125): the rows run in groups, every finished plane is stitched into out_dev
+ * (plane out_z0 first, channels channel_stride elements apart) and, when out_host is not NULL,
+ * copied to out_host (pinned memory recommended; same layout with host_channel_stride) on a second
+ * stream while the next group computes.  Needs exa_set_normalization first.  The partial sums for
+ * the next rank go to halo_dev (as exa_slab_partial; NULL only for the last rows).  The planes
+ * shared with the previous rank [seed_z0,seed_z1) are NOT produced here: exchange halo/seed
+ * between the ranks, then call exa_slab_finish with the received seed (NULL for the first rows),
+ * which stitches and copies those planes and returns once out_host is complete. */
+int exa_slab_predict(exa_engine* e, const uint16_t* slab_dev, int D, int H, int W,
+                     const exa_predict_params* p, int row_begin, int row_end, float* out_dev,
+                     int64_t channel_stride, float* out_host, int64_t host_channel_stride,
+                     float* halo_dev, void* stream);
+int exa_slab_finish(exa_engine* e, const float* seed_dev, float* out_dev, int64_t channel_stride,
+                    float* out_host, int64_t host_channel_stride, void* stream);
 
 /* host helpers mirroring count_patches / generate_patch_starts (inference.py:340-397);
  * starts receives n_patches*3 int32 (z,y,x) in the reference's order */

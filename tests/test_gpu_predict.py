@@ -133,6 +133,27 @@ def test_device_path_equals_host_path_and_slabs_equal_single():
                 seed = None
         assert np.array_equal(out, host), cuts   # bit-identical: same summation order
 
+    # the pipelined form (exa_slab_predict + exa_slab_finish): row groups inside each rank's rows,
+    # D2H overlapped, the planes shared with the previous rank finished last
+    for cuts in ([0, 2, nz], [0, 1, 3, nz], [0, nz], [0, 3, 4, nz]):
+        out = np.zeros_like(host)
+        pending = None   # (halo of the previous "rank")
+        for r0, r1 in zip(cuts, cuts[1:]):
+            pl = plan_slab(shape, params, r0, r1)
+            slab = vdev[pl["in_z0"]:pl["in_z1"]].contiguous()
+            n_own = pl["out_z1"] - pl["out_z0"]
+            own = torch.full((3, n_own, shape[1], shape[2]), -1.0, device="cuda")
+            own_host = torch.full((3, n_own, shape[1], shape[2]), -2.0).pin_memory()
+            nh = pl["halo_z1"] - pl["halo_z0"]
+            halo = torch.empty((3, nh, shape[1], shape[2]), device="cuda") if nh > 0 else None
+            eng.set_normalization(mn, mx, 1000)
+            eng.slab_predict(slab, shape, params, r0, r1, own, own_host, halo)
+            eng.slab_finish(pending, own, own_host)
+            assert np.array_equal(own_host.numpy(), own.cpu().numpy())
+            out[:, pl["out_z0"]:pl["out_z1"]] = own_host.numpy()
+            pending = halo
+        assert np.array_equal(out, host), cuts
+
 
 def test_full_size_properties_512():
     """BASELINE config 2 size: properties that do not need the (17-minute) CPU oracle."""

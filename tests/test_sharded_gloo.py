@@ -93,6 +93,18 @@ class OracleSlabBackend:
         out.copy_(torch.from_numpy(acc))
 
 
+    # pipelined form (exa_slab_predict / exa_slab_finish): same pieces, the seed planes last
+    def predict_rows(self, slab, shape, params, rows, mn, mx, own, out_host, halo):
+        self.run(slab, shape, params, rows, mn, mx)
+        if halo is not None:
+            self.partial(halo)
+
+    def finish_rows(self, seed, own, out_host):
+        self.stitch(seed, own)
+        if out_host is not None:
+            out_host.copy_(own)
+
+
 def _worker(rank, world, port, shape, kw, result_path):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -111,6 +123,9 @@ def _worker(rank, world, port, shape, kw, result_path):
         own = job.run(job.upload(vol), gather=False).numpy()
         z0, z1 = job.own_bounds()
         assert np.array_equal(full[:, z0:z1], own)
+        host = torch.empty(own.shape, dtype=torch.float32)
+        piped = job.run_pipelined(job.upload(vol), host).numpy()
+        assert np.array_equal(piped, own) and np.array_equal(host.numpy(), own)
         if rank == 0:
             np.save(result_path, full)
     finally:
