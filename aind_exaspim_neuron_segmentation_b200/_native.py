@@ -137,6 +137,8 @@ _SIGNATURES = {
     "exa_slab_finish": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                        ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
                                        ctypes.c_void_p]),
+    "exa_set_peer_outputs": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                            ctypes.POINTER(ctypes.c_void_p), ctypes.c_int]),
     "exa_count_patches": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                          ctypes.POINTER(ctypes.c_int32),
                                          ctypes.POINTER(ctypes.c_int32)]),

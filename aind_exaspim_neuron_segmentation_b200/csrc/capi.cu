@@ -204,6 +204,11 @@ int exa_slab_finish(exa_engine* e, const float* seed_dev, float* out_dev, int64_
   });
 }
 
+int exa_set_peer_outputs(exa_engine* e, float* local_base, int64_t elems, float* const* peer_bases,
+                         int n_peers) {
+  return guarded(e, [&] { return e->impl.set_peer_outputs(local_base, elems, peer_bases, n_peers); });
+}
+
 int exa_count_patches(int D, int H, int W, const int32_t patch[3], const int32_t overlap[3]) {
   if (!patch || !overlap) return EXA_ERR_INVALID;
   const int dims[3] = {D, H, W};

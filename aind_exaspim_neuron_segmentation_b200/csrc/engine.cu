@@ -888,8 +888,27 @@ Status Engine::stitch_planes(const float* seed_dev, float* out_dev, size_t out_c
     a.seed_z0 = slab_.seed_z0;
     a.seed_z1 = slab_.seed_z1;
   }
+  if (peer_local_ && out_dev >= peer_local_ && out_dev < peer_local_ + peer_elems_) {
+    const ptrdiff_t off = out_dev - peer_local_;
+    a.n_peers = (int)peer_bases_.size();
+    for (int i = 0; i < a.n_peers; ++i) a.peer_out[i] = peer_bases_[i] + off;
+  }
   Scope sc(this, CAT_STITCH, s);
   return launch_stitch(a, s);
+}
+
+Status Engine::set_peer_outputs(float* local_base, int64_t elems, float* const* peer_bases,
+                                int n_peers) {
+  EXA_CHECK(n_peers >= 0 && n_peers <= EXA_MAX_PEERS, "set_peer_outputs: too many peers");
+  EXA_CHECK(n_peers == 0 || (local_base && peer_bases && elems > 0), "set_peer_outputs: null argument");
+  peer_bases_.clear();
+  peer_local_ = n_peers > 0 ? local_base : nullptr;
+  peer_elems_ = n_peers > 0 ? elems : 0;
+  for (int i = 0; i < n_peers; ++i) {
+    EXA_CHECK(peer_bases[i] != nullptr, "set_peer_outputs: null peer pointer");
+    peer_bases_.push_back(peer_bases[i]);
+  }
+  return Status::OK();
 }
 
 // Rows [R0, R1) of the volume in groups of z patch-rows.  Each group is a slab job: run its

@@ -71,6 +71,10 @@ class Engine {
   Status slab_finish(const float* seed_dev, float* out_dev, int64_t channel_stride, float* out_host,
                      int64_t host_channel_stride, cudaStream_t s);
 
+  // fused gather: while set, every stitch whose destination lies inside [local_base, +elems)
+  // also stores to the same offset of each peer base (peer-mapped copies of the same array)
+  Status set_peer_outputs(float* local_base, int64_t elems, float* const* peer_bases, int n_peers);
+
   // per-category kernel timing with CUDA events on the launching stream (bench / roofline)
   enum Category { CAT_HIST = 0, CAT_STEM, CAT_CONV, CAT_POOL, CAT_UPSAMPLE, CAT_HEAD, CAT_STITCH,
                   CAT_COUNT };
@@ -174,6 +178,9 @@ class Engine {
   Plan held_plan_;
   int held_rows_[2] = {0, 0};
   int pipe_zbase_ = 0;
+  float* peer_local_ = nullptr;
+  int64_t peer_elems_ = 0;
+  std::vector<float*> peer_bases_;
 };
 
 }  // namespace exa

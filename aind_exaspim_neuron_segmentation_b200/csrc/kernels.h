@@ -55,6 +55,7 @@ struct AxisGeom {
   int dim = 0, patch = 0, stride = 0, trim = 0, n = 0;
 };
 
+#define EXA_MAX_PEERS 15
 struct StitchArgs {
   const float* probs = nullptr;  // [n_slots][C][Pt][Pt][Pt]
   int C = 0;
@@ -66,6 +67,10 @@ struct StitchArgs {
   int finalize = 1;                // 1: divide by coverage count; 0: raw partial sums
   const float* seed = nullptr;     // optional partial sums [C][seed_z1-seed_z0][H][W] added FIRST
   int seed_z0 = 0, seed_z1 = 0;
+  // fused all-gather (multi-GPU): every finished element is also stored, at the
+  // same offset, into the peers' copies of the output array over NVLink (peer-mapped pointers)
+  int n_peers = 0;
+  float* peer_out[EXA_MAX_PEERS] = {};
 };
 
 Status launch_stem(const PatchSource& src, const StemWeights& w, const Act& out, cudaStream_t s);

@@ -872,7 +872,9 @@ stitch_kernel(const StitchArgs a) {
       }
     }
     if (a.finalize && cnt > 0) acc = acc / (float)cnt;
-    a.out[(size_t)c * a.out_cstride + ((size_t)zl * H + y) * W + x] = acc;
+    const size_t o = (size_t)c * a.out_cstride + ((size_t)zl * H + y) * W + x;
+    a.out[o] = acc;
+    for (int p = 0; p < a.n_peers; ++p) a.peer_out[p][o] = acc;
   }
 }
 
@@ -922,7 +924,10 @@ stitch_kernel_x4(const StitchArgs a) {
       if ((cnt & (cnt - 1)) == 0) { acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv; }
       else { acc.x /= (float)cnt; acc.y /= (float)cnt; acc.z /= (float)cnt; acc.w /= (float)cnt; }
     }
-    *reinterpret_cast<float4*>(a.out + (size_t)c * a.out_cstride + ((size_t)zl * H + y) * W + x) = acc;
+    const size_t o = (size_t)c * a.out_cstride + ((size_t)zl * H + y) * W + x;
+    *reinterpret_cast<float4*>(a.out + o) = acc;
+    // the gather, fused: one 16 B store per peer (a warp writes 512 contiguous bytes per peer)
+    for (int p = 0; p < a.n_peers; ++p) *reinterpret_cast<float4*>(a.peer_out[p] + o) = acc;
   }
 }
 
@@ -935,6 +940,9 @@ Status launch_stitch(const StitchArgs& a, cudaStream_t s) {
   const bool x4 = a.ax.dim % 4 == 0 && a.ax.trim % 4 == 0 && a.ax.stride % 4 == 0 && keep_x % 4 == 0 &&
                   chan % 4 == 0 && a.out_cstride % 4 == 0 && ((uintptr_t)a.out & 15) == 0 &&
                   ((uintptr_t)a.probs & 15) == 0 && ((uintptr_t)a.seed & 15) == 0;
+  for (int p = 0; p < a.n_peers; ++p)
+    EXA_CHECK(a.peer_out[p] != nullptr && ((uintptr_t)a.peer_out[p] & 15) == ((uintptr_t)a.out & 15),
+              "stitch: peer output misaligned");
   if (x4) {
     const dim3 blocks4((unsigned)ceil_div64((int64_t)a.ay.dim * (a.ax.dim / 4), 256), (unsigned)nz);
     stitch_kernel_x4<<<blocks4, 256, 0, s>>>(a);

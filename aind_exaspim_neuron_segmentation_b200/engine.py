@@ -201,6 +201,14 @@ class Engine:
                                          _ptr(out_host), int(hs), _stream_ptr(self.device))
         _native.check(code, self._h, "exa_slab_finish")
 
+    def set_peer_outputs(self, full, peer_ptrs):
+        """Fused gather: stitches into ``full`` (this rank's (C, D, H, W) array) also store to the
+        peer-mapped copies at ``peer_ptrs`` (ints).  An empty list switches it off."""
+        arr = (ctypes.c_void_p * max(len(peer_ptrs), 1))(*[int(p) for p in peer_ptrs])
+        code = self._lib.exa_set_peer_outputs(self._h, _ptr(full) if peer_ptrs else ctypes.c_void_p(0),
+                                              full.numel() if peer_ptrs else 0, arr, len(peer_ptrs))
+        _native.check(code, self._h, "exa_set_peer_outputs")
+
 
 # -- host helpers that need no GPU --------------------------------------------------
 def plan_slab(shape, params, row_begin, row_end):

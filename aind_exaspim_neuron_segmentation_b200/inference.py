@@ -18,6 +18,8 @@ SURVEY.md 8e); with a world size of 1 it is the same computation as ``predict``.
 """
 
 import itertools
+import os
+import warnings
 
 import numpy as np
 import torch
@@ -211,6 +213,20 @@ class _EngineSlabBackend:
     def finish_rows(self, seed, own, out_host):
         self.engine.slab_finish(seed, own, out_host)
 
+    def symmetric_full(self, shape, group):
+        """The gathered (C, D, H, W) output in torch symmetric memory: every rank's copy is mapped
+        into every other rank's address space over NVLink.  -> (full, handle, peer pointers)."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+
+        full = symm.empty(*shape, dtype=torch.float32, device=self.device)
+        hdl = symm.rendezvous(full, group if group is not None else dist.group.WORLD)
+        ptrs = [int(p) for r, p in enumerate(hdl.buffer_ptrs) if r != hdl.rank]
+        return full, hdl, ptrs
+
+    def set_peers(self, full, ptrs):
+        self.engine.set_peer_outputs(full, ptrs)
+
     def to_device(self, host_u16):
         return torch.from_numpy(host_u16).to(self.device, non_blocking=True)
 
@@ -258,6 +274,9 @@ class SlabJob:
                            for p, r in zip(self.all_plans, self.all_rows)]
         self._full = None  # gathered output, allocated once and re-used by every run()
         self._own = None   # owned planes of run_pipelined(), likewise
+        self._fused = None  # tri-state: not tried / fused peer-store gather / NCCL gather
+        self._hdl = None
+        self._peer_ptrs = []
 
     def slab_bounds(self):
         """Input planes [z0, z1) this rank needs resident."""
@@ -333,11 +352,48 @@ class SlabJob:
             be.finish_rows(seed, own, out_host)
         return own
 
+    def _fused_gather_ready(self):
+        """C3 without a gather pass: the output lives in symmetric memory and the stitch kernel
+        stores every finished element to all ranks' copies (exa_set_peer_outputs).  Falls back to
+        the grouped NCCL send/recv gather when the backend has no peer mapping (CPU test backend),
+        ``EXA_GATHER=nccl`` is set, or the symmetric-memory rendezvous is not possible here."""
+        if self._fused is None:
+            self._fused = False
+            if hasattr(self.backend, "symmetric_full") and os.environ.get("EXA_GATHER", "") != "nccl":
+                try:
+                    self._full, self._hdl, self._peer_ptrs = self.backend.symmetric_full(
+                        (self.n_channels,) + self.shape, self.group)
+                    self._fused = True
+                except Exception as exc:  # noqa: BLE001 -- e.g. no P2P between the GPUs of this box
+                    warnings.warn(f"symmetric-memory gather unavailable ({exc}); using NCCL send/recv")
+        return self._fused
+
+    def _run_fused_gather(self, slab):
+        be, full = self.backend, self._full
+        mn, mx = self._normalization(slab)   # the all-reduce also orders this step's peer stores
+        z0 = int(sum(self.own_planes[:self.rank]))  # after every rank's reads of the last result
+        own = full[:, z0:z0 + self.own_planes[self.rank]]
+        halo = self._halo_buffer()
+        be.set_peers(full, self._peer_ptrs)
+        try:
+            if self.has_rows:
+                be.predict_rows(slab, self.shape, self.params, self.rows, mn, mx, own, None, halo)
+            seed = self._exchange_halo(halo)
+            if self.has_rows:
+                be.finish_rows(seed, own, None)
+        finally:
+            be.set_peers(full, [])
+        self._hdl.barrier()   # every rank's stores have landed before anyone reads `full`
+        return full
+
     def run(self, slab, gather=True):
         """slab: device uint16 planes [in_z0, in_z1).  -> device float32 (C, D|own, H, W)."""
         dist, be, p = self.dist, self.backend, self.params
         dev = be.device
         c, (d, h, w) = self.n_channels, self.shape
+        nz_own = self.own_planes[self.rank]
+        if gather and self.world > 1 and self._fused_gather_ready():
+            return self._run_fused_gather(slab)
         mn, mx = self._normalization(slab)
         if self.has_rows:
             be.run(slab, self.shape, p, self.rows, mn, mx)
@@ -345,7 +401,6 @@ class SlabJob:
         if halo is not None:
             be.partial(halo)
         seed = self._exchange_halo(halo)
-        nz_own = self.own_planes[self.rank]
         if not gather or self.world == 1:
             own = torch.zeros((c, nz_own, h, w), dtype=torch.float32, device=dev)
             if self.has_rows and nz_own > 0:

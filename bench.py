@@ -470,12 +470,64 @@ def emit(line):
         os.write(_JSON_FD, data)
 
 
+# --- "library on the same box" bar -----------------------------------------
+def run_library_bar(args):
+    """The reference's own GPU path is PyTorch/cuDNN: time the oracle's torch restatement of the
+    network (forward + sigmoid, B=16 patches of 96^3 as inference.py:33) on cuda:0 in the three
+    settings BASELINE.md names.  Not part of the bench contract: prints one JSON line with
+    "impl": "library" for DESIGN.md; the product never takes this path."""
+    import contextlib
+
+    import torch
+
+    from oracle.unet_ref import rescaled_state_dict, unet_forward
+
+    dev = torch.device("cuda", 0)
+    sd = {k: v.to(dev) for k, v in rescaled_state_dict(0).items()}
+    torch.backends.cudnn.benchmark = True
+    x = torch.rand(16, 1, 96, 96, 96, device=dev)
+    out = {}
+    for name in ("fp32_ieee", "tf32", "bf16_autocast", "bf16_autocast_channels_last"):
+        tf32 = name != "fp32_ieee"
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        ctx = torch.autocast("cuda", dtype=torch.bfloat16) if name.startswith("bf16") \
+            else contextlib.nullcontext()
+        xin, w = x, sd
+        if name.endswith("channels_last"):
+            xin = x.contiguous(memory_format=torch.channels_last_3d)
+            w = {k: (v.contiguous(memory_format=torch.channels_last_3d) if v.dim() == 5 else v)
+                 for k, v in sd.items()}
+        try:
+            with ctx:
+                for _ in range(2):
+                    torch.sigmoid(unet_forward(xin, w))
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(args.steps):
+                    torch.sigmoid(unet_forward(xin, w))
+                e1.record()
+                torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / args.steps
+            # one patch adds 64^3 stitched voxels at stride 64 (SURVEY 8d)
+            out[name] = {"ms_per_batch16": ms, "patches_per_s": 16e3 / ms,
+                         "voxels_per_s": 16e3 / ms * 64 ** 3,
+                         "conv_tflops": 16 * F_PATCH_96 / (ms * 1e-3) / 1e12}
+        except Exception as exc:  # noqa: BLE001 -- a setting cuDNN cannot run is reported, not fatal
+            out[name] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
+        torch.cuda.empty_cache()
+    emit({"impl": "library", "what": "PyTorch/cuDNN forward+sigmoid of the same UNet3D, B=16 x 96^3, "
+          "forward only (no normalisation, patch extraction, D2H or stitching)",
+          "torch": torch.__version__, "cudnn": torch.backends.cudnn.version(), "settings": out})
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "library"])
     ap.add_argument("--batch", type=int, default=32, help="patches per wave")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
@@ -488,6 +540,8 @@ def main():
     capture_stdout()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "library":
+        run_library_bar(args)
     else:
         run_b200(args)
 

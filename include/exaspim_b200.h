@@ -140,6 +140,13 @@ int exa_slab_predict(exa_engine* e, const uint16_t* slab_dev, int D, int H, int 
                      float* halo_dev, void* stream);
 int exa_slab_finish(exa_engine* e, const float* seed_dev, float* out_dev, int64_t channel_stride,
                     float* out_host, int64_t host_channel_stride, void* stream);
+/* Fused all-gather: local_base is this GPU's copy of the full (C, D, H, W)
+ * output (elems floats) and peer_bases[i] the peer-mapped addresses of the other ranks' copies
+ * (CUDA IPC / symmetric memory; at most 15).  While set, the stitch kernel stores every finished
+ * element of a destination inside local_base's range to all copies, so no separate gather pass
+ * runs; the caller orders a cross-rank barrier after the last stitch.  n_peers = 0 clears it. */
+int exa_set_peer_outputs(exa_engine* e, float* local_base, int64_t elems, float* const* peer_bases,
+                         int n_peers);
 
 /* host helpers mirroring count_patches / generate_patch_starts (inference.py:340-397);
  * starts receives n_patches*3 int32 (z,y,x) in the reference's order */
