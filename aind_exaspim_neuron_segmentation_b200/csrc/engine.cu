@@ -164,6 +164,13 @@ Engine::~Engine() {
   free_dev(hist_dev_);
   free_dev(seed_);
   free_dev(probs_hold_);
+  free_dev(probs_alt_);
+  if (stitch_stream_) {
+    cudaStreamDestroy(stitch_stream_);
+    cudaEventDestroy(conv_done_);
+    cudaEventDestroy(probs_free_);
+    cudaEventDestroy(alt_free_);
+  }
   if (copy_event_) cudaEventDestroy(copy_event_);
   free_dev(vol_stage_);
   free_dev(out_stage_);
@@ -190,6 +197,8 @@ Status Engine::init() {
   use_zfold_ = !(nz && nz[0] == '1');
   const char* ns = getenv("EXA_NO_TC_STEM");
   use_tc_stem_ = !(ns && ns[0] == '1');
+  const char* no = getenv("EXA_NO_STITCH_OVERLAP");
+  overlap_stitch_ = !(no && no[0] == '1');
   const char* np = getenv("EXA_NO_PAIR");
   use_pair_ = !(np && np[0] == '1');
   return Status::OK();
@@ -946,18 +955,38 @@ Status Engine::pipeline_rows(const uint16_t* vol_dev, int vol_z0, int D, int H, 
     EXA_CUDA(cudaMalloc(&seed_, seed_elems * sizeof(float)));
     seed_bytes_ = seed_elems * sizeof(float);
   }
+  // The stitch of a group (and its peer stores, when the gather is fused into it) runs on a
+  // second stream while the next group's convolutions run on s: two patch buffers alternate,
+  // a buffer is rewritten only after the stitch that read it.
+  if (!stitch_stream_) {
+    int lo = 0, hi = 0;
+    EXA_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    EXA_CUDA(cudaStreamCreateWithPriority(&stitch_stream_, cudaStreamNonBlocking, hi));
+    EXA_CUDA(cudaEventCreateWithFlags(&conv_done_, cudaEventDisableTiming));
+    EXA_CUDA(cudaEventCreateWithFlags(&probs_free_, cudaEventDisableTiming));
+    EXA_CUDA(cudaEventCreateWithFlags(&alt_free_, cudaEventDisableTiming));
+  }
+  cudaStream_t ss = overlap_stitch_ ? stitch_stream_ : s;
   Status st = Status::OK();
   bool have_seed = false;
+  bool probs_busy = false, alt_busy = false;  // a stitch on ss still reads that buffer
+  cudaEvent_t last_rec = nullptr;             // last event recorded on ss
   for (int r0 = R0; r0 < R1 && st.ok; r0 += rows_per_group) {
     const int r1 = std::min(r0 + rows_per_group, R1);
+    if (probs_busy) EXA_CUDA(cudaStreamWaitEvent(s, probs_free_, 0));
+    probs_busy = false;
     st = slab_run(vol_dev + (size_t)(r0 * plan.az.stride - vol_z0) * plane, D, H, W, p, r0, r1, s);
     if (!st.ok) break;
+    if (ss != s) {
+      EXA_CUDA(cudaEventRecord(conv_done_, s));
+      EXA_CUDA(cudaStreamWaitEvent(ss, conv_done_, 0));
+    }
     const bool first = r0 == R0, last = r1 == R1;
     const bool hold = first && defer_seed && slab_.seed_z1 > slab_.seed_z0;
     const int z0 = hold ? slab_.seed_z1 : slab_.out_z0, z1 = slab_.out_z1;
     if (z1 > z0) {
       st = stitch_planes(have_seed ? seed_ : nullptr, out_dev + (size_t)(z0 - out_zbase) * plane,
-                         out_cstride, z0, z1, s);
+                         out_cstride, z0, z1, ss);
       if (!st.ok) break;
     }
     have_seed = slab_.halo_z1 > slab_.halo_z0;
@@ -966,11 +995,21 @@ Status Engine::pipeline_rows(const uint16_t* vol_dev, int vol_z0, int D, int H, 
         st = Status::Err("slab_predict: rows end before the volume does but no halo buffer given");
         break;
       }
-      st = slab_partial(last ? halo_out : seed_, s);
+      st = slab_partial(last ? halo_out : seed_, ss);
       if (!st.ok) break;
       if (last) have_seed = false;
     }
-    if (hold) {  // later groups write their patches to the other buffer
+    if (out_host && z1 > z0) {
+      st = copy_planes_to_host(out_dev, out_cstride, out_host, host_cstride, out_zbase, z0, z1,
+                               plane, ss);
+      if (!st.ok) break;
+    }
+    if (ss != s) {
+      EXA_CUDA(cudaEventRecord(probs_free_, ss));
+      probs_busy = true;
+      last_rec = probs_free_;
+    }
+    if (hold) {  // these patches wait for the previous rank's seed; they leave the rotation
       held_slab_ = slab_;
       held_plan_ = plan_;
       held_rows_[0] = r0;
@@ -979,10 +1018,17 @@ Status Engine::pipeline_rows(const uint16_t* vol_dev, int vol_z0, int D, int H, 
       std::swap(probs_bytes_, probs_hold_bytes_);
       held_valid_ = true;
       job_ready_ = false;
+      probs_busy = false;  // the buffer now in probs_ has no reader (pipeline_finish orders s after ss)
+    } else if (ss != s) {
+      std::swap(probs_, probs_alt_);
+      std::swap(probs_bytes_, probs_alt_bytes_);
+      std::swap(probs_free_, alt_free_);
+      std::swap(probs_busy, alt_busy);
+      job_ready_ = false;  // slab_ no longer describes probs_
     }
-    if (out_host && z1 > z0) st = copy_planes_to_host(out_dev, out_cstride, out_host, host_cstride,
-                                                     out_zbase, z0, z1, plane, s);
   }
+  // everything queued on the stitch stream is ordered before later work on s
+  if (last_rec) EXA_CUDA(cudaStreamWaitEvent(s, last_rec, 0));
   return st;
 }
 
