@@ -197,8 +197,8 @@ Status Engine::init() {
   use_zfold_ = !(nz && nz[0] == '1');
   const char* ns = getenv("EXA_NO_TC_STEM");
   use_tc_stem_ = !(ns && ns[0] == '1');
-  const char* no = getenv("EXA_NO_STITCH_OVERLAP");
-  overlap_stitch_ = !(no && no[0] == '1');
+  const char* so = getenv("EXA_STITCH_OVERLAP");
+  overlap_stitch_ = so && so[0] == '1';
   const char* np = getenv("EXA_NO_PAIR");
   use_pair_ = !(np && np[0] == '1');
   return Status::OK();
@@ -955,9 +955,11 @@ Status Engine::pipeline_rows(const uint16_t* vol_dev, int vol_z0, int D, int H, 
     EXA_CUDA(cudaMalloc(&seed_, seed_elems * sizeof(float)));
     seed_bytes_ = seed_elems * sizeof(float);
   }
-  // The stitch of a group (and its peer stores, when the gather is fused into it) runs on a
-  // second stream while the next group's convolutions run on s: two patch buffers alternate,
-  // a buffer is rewritten only after the stitch that read it.
+  // EXA_STITCH_OVERLAP=1: the stitch of a group (and its peer stores, when the gather is fused
+  // into it) runs on a second stream while the next group's convolutions run on s; two patch
+  // buffers alternate, a buffer is rewritten only after the stitch that read it.  Off by
+  // default: measured on the same boxes it is neutral at 1 GPU and slower at 2 and 8 GPUs
+  // (the stores compete with the HBM-bound stem of the next group).
   if (!stitch_stream_) {
     int lo = 0, hi = 0;
     EXA_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));

@@ -178,8 +178,8 @@ class Engine {
   Plan held_plan_;
   int held_rows_[2] = {0, 0};
   int pipe_zbase_ = 0;
-  // stitch stream: group k's stitch overlaps group k+1's convolutions (EXA_NO_STITCH_OVERLAP=1: off)
-  bool overlap_stitch_ = true;
+  // stitch stream: group k's stitch overlaps group k+1's convolutions (EXA_STITCH_OVERLAP=1: on)
+  bool overlap_stitch_ = false;
   cudaStream_t stitch_stream_ = nullptr;
   cudaEvent_t conv_done_ = nullptr, probs_free_ = nullptr, alt_free_ = nullptr;
   float* probs_alt_ = nullptr;
