@@ -834,8 +834,31 @@ Status Engine::slab_run(const uint16_t* slab_dev, int D, int H, int W, const exa
     head.trim = t;
     head.apply_sigmoid = 1;  // inference.py:158
     EXA_TRY(run_network(src, nb, p.patch[0], p.patch[1], p.patch[2], head, s));
+    if (band_.on) {
+      job_ready_ = true;  // the stitch below only reads patches that are complete
+      EXA_TRY(stream_band(i0 + nb, n_slab, s));
+      job_ready_ = false;
+    }
   }
   job_ready_ = true;
+  return Status::OK();
+}
+
+// Patches [0, patches_done) of the current one-row slab job are finished: every output row
+// y < ky_done*stride + trim is covered only by finished patches (the next window row starts
+// there), so those rows of the group's planes are final -- stitch them and start their D2H.
+Status Engine::stream_band(int patches_done, int n_slab, cudaStream_t s) {
+  const AxisGeom& ay = plan_.ay;
+  const int ky_done = patches_done / plan_.ax.n;
+  const int y_done = patches_done >= n_slab ? ay.dim : std::min(ky_done * ay.stride + ay.trim, ay.dim);
+  if (y_done <= band_.y_done || band_.z1 <= band_.z0) return Status::OK();
+  const size_t plane = (size_t)plan_.H * plan_.W;
+  EXA_TRY(stitch_planes(band_.seed, band_.out_dev + (size_t)(band_.z0 - band_.out_zbase) * plane,
+                        band_.out_cstride, band_.z0, band_.z1, s, band_.y_done, y_done));
+  if (band_.out_host)
+    EXA_TRY(copy_planes_to_host(band_.out_dev, band_.out_cstride, band_.out_host, band_.host_cstride,
+                                band_.out_zbase, band_.z0, band_.z1, plane, s, band_.y_done, y_done));
+  band_.y_done = y_done;
   return Status::OK();
 }
 
@@ -882,13 +905,15 @@ Status Engine::slab_stitch(const float* seed_dev, float* out_dev, int64_t channe
 
 // finished planes [z0, z1) of the current slab job -> out (plane z0 first), channel stride given
 Status Engine::stitch_planes(const float* seed_dev, float* out_dev, size_t out_cstride, int z0,
-                             int z1, cudaStream_t s) {
+                             int z1, cudaStream_t s, int y0, int y1) {
   EXA_CHECK(job_ready_, "stitch: no slab job");
   if (z1 <= z0) return Status::OK();
   EXA_CHECK(out_dev != nullptr, "slab_stitch: null buffer");
   StitchArgs a = stitch_base(plan_, probs_, out_channels_, row_begin_, row_end_);
   a.z_begin = z0;
   a.z_end = z1;
+  a.y_begin = y0;
+  a.y_end = y1;
   a.out = out_dev;
   a.out_cstride = out_cstride;
   a.finalize = 1;
@@ -977,7 +1002,25 @@ Status Engine::pipeline_rows(const uint16_t* vol_dev, int vol_z0, int D, int H, 
     const int r1 = std::min(r0 + rows_per_group, R1);
     if (probs_busy) EXA_CUDA(cudaStreamWaitEvent(s, probs_free_, 0));
     probs_busy = false;
+    // one-row groups with a host destination stream finished y-bands while the row still runs
+    band_ = BandSink();
+    if (out_host && r1 - r0 == 1 && ss == s) {
+      exa_slab_plan g;
+      st = plan_slab(plan, r0, r1, &g);
+      if (!st.ok) break;
+      band_.on = true;
+      band_.seed = have_seed ? seed_ : nullptr;
+      band_.out_dev = out_dev;
+      band_.out_cstride = out_cstride;
+      band_.out_host = out_host;
+      band_.host_cstride = host_cstride;
+      band_.out_zbase = out_zbase;
+      band_.z0 = (r0 == R0 && defer_seed && g.seed_z1 > g.seed_z0) ? g.seed_z1 : g.out_z0;
+      band_.z1 = g.out_z1;
+    }
     st = slab_run(vol_dev + (size_t)(r0 * plan.az.stride - vol_z0) * plane, D, H, W, p, r0, r1, s);
+    const bool banded = band_.on;
+    band_.on = false;
     if (!st.ok) break;
     if (ss != s) {
       EXA_CUDA(cudaEventRecord(conv_done_, s));
@@ -986,7 +1029,7 @@ Status Engine::pipeline_rows(const uint16_t* vol_dev, int vol_z0, int D, int H, 
     const bool first = r0 == R0, last = r1 == R1;
     const bool hold = first && defer_seed && slab_.seed_z1 > slab_.seed_z0;
     const int z0 = hold ? slab_.seed_z1 : slab_.out_z0, z1 = slab_.out_z1;
-    if (z1 > z0) {
+    if (z1 > z0 && !banded) {
       st = stitch_planes(have_seed ? seed_ : nullptr, out_dev + (size_t)(z0 - out_zbase) * plane,
                          out_cstride, z0, z1, ss);
       if (!st.ok) break;
@@ -1001,7 +1044,7 @@ Status Engine::pipeline_rows(const uint16_t* vol_dev, int vol_z0, int D, int H, 
       if (!st.ok) break;
       if (last) have_seed = false;
     }
-    if (out_host && z1 > z0) {
+    if (out_host && z1 > z0 && !banded) {
       st = copy_planes_to_host(out_dev, out_cstride, out_host, host_cstride, out_zbase, z0, z1,
                                plane, ss);
       if (!st.ok) break;
@@ -1037,14 +1080,23 @@ Status Engine::pipeline_rows(const uint16_t* vol_dev, int vol_z0, int D, int H, 
 // D2H of finished planes [z0, z1) on the copy stream, ordered after the work queued on s so far
 Status Engine::copy_planes_to_host(const float* out_dev, size_t out_cstride, float* out_host,
                                    size_t host_cstride, int out_zbase, int z0, int z1, size_t plane,
-                                   cudaStream_t s) {
+                                   cudaStream_t s, int y0, int y1) {
   if (!copy_event_) EXA_CUDA(cudaEventCreateWithFlags(&copy_event_, cudaEventDisableTiming));
   EXA_CUDA(cudaEventRecord(copy_event_, s));
   EXA_CUDA(cudaStreamWaitEvent(copy_stream_, copy_event_, 0));
+  const bool band = y1 > y0 && !(y0 == 0 && (size_t)y1 * plan_.W == plane);
   for (int c = 0; c < out_channels_; ++c) {
     const size_t zoff = (size_t)(z0 - out_zbase) * plane;
-    EXA_CUDA(cudaMemcpyAsync(out_host + c * host_cstride + zoff, out_dev + c * out_cstride + zoff,
-                             (size_t)(z1 - z0) * plane * 4, cudaMemcpyDeviceToHost, copy_stream_));
+    if (!band) {
+      EXA_CUDA(cudaMemcpyAsync(out_host + c * host_cstride + zoff, out_dev + c * out_cstride + zoff,
+                               (size_t)(z1 - z0) * plane * 4, cudaMemcpyDeviceToHost, copy_stream_));
+    } else {  // rows [y0, y1) of every plane: one contiguous run per plane, plane pitch apart
+      const size_t yoff = (size_t)y0 * plan_.W;
+      EXA_CUDA(cudaMemcpy2DAsync(out_host + c * host_cstride + zoff + yoff, plane * 4,
+                                 out_dev + c * out_cstride + zoff + yoff, plane * 4,
+                                 (size_t)(y1 - y0) * plan_.W * 4, (size_t)(z1 - z0),
+                                 cudaMemcpyDeviceToHost, copy_stream_));
+    }
   }
   return Status::OK();
 }

@@ -99,9 +99,10 @@ class Engine {
                          size_t host_cstride, int out_zbase, cudaStream_t s);
   Status copy_planes_to_host(const float* out_dev, size_t out_cstride, float* out_host,
                              size_t host_cstride, int out_zbase, int z0, int z1, size_t plane,
-                             cudaStream_t s);
+                             cudaStream_t s, int y0 = 0, int y1 = 0);
   Status stitch_planes(const float* seed_dev, float* out_dev, size_t out_cstride, int z0, int z1,
-                       cudaStream_t s);
+                       cudaStream_t s, int y0 = 0, int y1 = 0);
+  Status stream_band(int patches_done, int n_slab, cudaStream_t s);
   Status run_network(const PatchSource& src, int batch, int pz, int py, int px,
                      const HeadParams& head, cudaStream_t s);
   Status conv(const ConvLayer& L, const Act& in, const Act& out, const HeadParams* head,
@@ -178,6 +179,17 @@ class Engine {
   Plan held_plan_;
   int held_rows_[2] = {0, 0};
   int pipe_zbase_ = 0;
+  // y-band streaming inside a one-row group: rows of the group's planes are stitched and copied
+  // to the host as soon as the patches covering them are done (set by pipeline_rows)
+  struct BandSink {
+    bool on = false;
+    const float* seed = nullptr;
+    float* out_dev = nullptr;
+    size_t out_cstride = 0;
+    float* out_host = nullptr;
+    size_t host_cstride = 0;
+    int out_zbase = 0, z0 = 0, z1 = 0, y_done = 0;
+  } band_;
   // stitch stream: group k's stitch overlaps group k+1's convolutions (EXA_STITCH_OVERLAP=1: on)
   bool overlap_stitch_ = false;
   cudaStream_t stitch_stream_ = nullptr;

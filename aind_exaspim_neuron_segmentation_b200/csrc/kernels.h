@@ -62,6 +62,7 @@ struct StitchArgs {
   AxisGeom az, ay, ax;
   int row_begin = 0, row_end = 0;  // z rows whose patches are resident in `probs`
   int z_begin = 0, z_end = 0;      // output planes to produce
+  int y_begin = 0, y_end = 0;      // rows of those planes to produce (0, 0 = all)
   float* out = nullptr;            // [C][z_end-z_begin][H][W] (plane z_begin first), stride below
   size_t out_cstride = 0;          // elements between channels of `out`
   int finalize = 1;                // 1: divide by coverage count; 0: raw partial sums

@@ -836,9 +836,9 @@ stitch_kernel(const StitchArgs a) {
   const int H = a.ay.dim, W = a.ax.dim;
   // grid: x covers one (y, x) plane, y = plane index -> 32-bit index math only
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (unsigned)H * W) return;
+  if (i >= (unsigned)(a.y_end - a.y_begin) * W) return;
   const int x = (int)(i % (unsigned)W);
-  const int y = (int)(i / (unsigned)W);
+  const int y = a.y_begin + (int)(i / (unsigned)W);
   const int zl = blockIdx.y;
   const int z = a.z_begin + zl;
 
@@ -885,9 +885,9 @@ __global__ void __launch_bounds__(256)
 stitch_kernel_x4(const StitchArgs a) {
   const int H = a.ay.dim, W = a.ax.dim, W4 = W >> 2;
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (unsigned)H * W4) return;
+  if (i >= (unsigned)(a.y_end - a.y_begin) * W4) return;
   const int x = 4 * (int)(i % (unsigned)W4);
-  const int y = (int)(i / (unsigned)W4);
+  const int y = a.y_begin + (int)(i / (unsigned)W4);
   const int zl = blockIdx.y;
   const int z = a.z_begin + zl;
   int kz0, kz1, ky0, ky1, kx0, kx1;
@@ -931,9 +931,12 @@ stitch_kernel_x4(const StitchArgs a) {
   }
 }
 
-Status launch_stitch(const StitchArgs& a, cudaStream_t s) {
-  const int nz = a.z_end - a.z_begin;
-  if (nz <= 0 || a.ay.dim <= 0 || a.ax.dim <= 0) return Status::OK();
+Status launch_stitch(const StitchArgs& a_in, cudaStream_t s) {
+  StitchArgs a = a_in;
+  if (a.y_begin == 0 && a.y_end == 0) a.y_end = a.ay.dim;
+  const int nz = a.z_end - a.z_begin, ny = a.y_end - a.y_begin;
+  EXA_CHECK(a.y_begin >= 0 && a.y_end <= a.ay.dim, "stitch: row range out of bounds");
+  if (nz <= 0 || ny <= 0 || a.ax.dim <= 0) return Status::OK();
   EXA_CHECK(nz <= 65535, "stitch: too many planes for one launch");
   const int keep_x = a.ax.patch - 2 * a.ax.trim;
   const size_t chan = (size_t)(a.az.patch - 2 * a.az.trim) * (a.ay.patch - 2 * a.ay.trim) * keep_x;
@@ -944,12 +947,12 @@ Status launch_stitch(const StitchArgs& a, cudaStream_t s) {
     EXA_CHECK(a.peer_out[p] != nullptr && ((uintptr_t)a.peer_out[p] & 15) == ((uintptr_t)a.out & 15),
               "stitch: peer output misaligned");
   if (x4) {
-    const dim3 blocks4((unsigned)ceil_div64((int64_t)a.ay.dim * (a.ax.dim / 4), 256), (unsigned)nz);
+    const dim3 blocks4((unsigned)ceil_div64((int64_t)ny * (a.ax.dim / 4), 256), (unsigned)nz);
     stitch_kernel_x4<<<blocks4, 256, 0, s>>>(a);
     EXA_CUDA(cudaGetLastError());
     return Status::OK();
   }
-  const dim3 blocks((unsigned)ceil_div64((int64_t)a.ay.dim * a.ax.dim, 256), (unsigned)nz);
+  const dim3 blocks((unsigned)ceil_div64((int64_t)ny * a.ax.dim, 256), (unsigned)nz);
   stitch_kernel<<<blocks, 256, 0, s>>>(a);
   EXA_CUDA(cudaGetLastError());
   return Status::OK();

@@ -135,7 +135,12 @@ def test_device_path_equals_host_path_and_slabs_equal_single():
 
     # the pipelined form (exa_slab_predict + exa_slab_finish): row groups inside each rank's rows,
     # D2H overlapped, the planes shared with the previous rank finished last
-    for cuts in ([0, 2, nz], [0, 1, 3, nz], [0, nz], [0, 3, 4, nz]):
+    # batch=2 with 4 patches per row: one-row groups whose finished y-bands are stitched and copied
+    # while the row still runs
+    params_band = _native.make_params((32, 32, 32), (8, 8, 8), 4, 1000, (1, 99.9), batch=2)
+    assert np.array_equal(eng.predict_host(vol, params_band), host)
+    for cuts, prm in [(c, q) for q in (params, params_band)
+                      for c in ([0, 2, nz], [0, 1, 3, nz], [0, nz], [0, 3, 4, nz])]:
         out = np.zeros_like(host)
         pending = None   # (halo of the previous "rank")
         for r0, r1 in zip(cuts, cuts[1:]):
@@ -147,7 +152,7 @@ def test_device_path_equals_host_path_and_slabs_equal_single():
             nh = pl["halo_z1"] - pl["halo_z0"]
             halo = torch.empty((3, nh, shape[1], shape[2]), device="cuda") if nh > 0 else None
             eng.set_normalization(mn, mx, 1000)
-            eng.slab_predict(slab, shape, params, r0, r1, own, own_host, halo)
+            eng.slab_predict(slab, shape, prm, r0, r1, own, own_host, halo)
             eng.slab_finish(pending, own, own_host)
             assert np.array_equal(own_host.numpy(), own.cpu().numpy())
             out[:, pl["out_z0"]:pl["out_z1"]] = own_host.numpy()
