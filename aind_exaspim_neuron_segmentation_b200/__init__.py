@@ -7,6 +7,7 @@ __version__ = "0.1.0"
 
 from . import inference  # noqa: F401
 from .inference import (  # noqa: F401
+    affinities_to_segmentation,
     count_patches,
     generate_patch_starts,
     load_model,

@@ -15,9 +15,10 @@ import subprocess
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_PKG_DIR, "csrc")
 LIB_PATH = os.path.join(_PKG_DIR, "libexaspim_b200.so")
-SOURCES = ["capi.cu", "engine.cu", "kernels_mem.cu", "conv_umma.cu", "conv_zfold.cu", "conv_stem.cu"]
+SOURCES = ["capi.cu", "engine.cu", "kernels_mem.cu", "conv_umma.cu", "conv_zfold.cu", "conv_stem.cu",
+           "watershed.cu"]
 HEADERS = ["common.cuh", "conv_umma.cuh", "conv_zfold.cuh", "conv_zfold2.cuh", "conv_stem.cuh", "engine.h",
-           "kernels.h", "tmap.h"]
+           "kernels.h", "tmap.h", "watershed.h"]
 
 PRECISION_BF16 = 0
 PRECISION_FP32 = 1
@@ -139,6 +140,16 @@ _SIGNATURES = {
                                        ctypes.c_void_p]),
     "exa_set_peer_outputs": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
                                             ctypes.POINTER(ctypes.c_void_p), ctypes.c_int]),
+    "exa_affinities_to_segmentation": (ctypes.c_int, [
+        ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+        ctypes.POINTER(ctypes.c_double), ctypes.c_int, ctypes.c_double, ctypes.c_double,
+        ctypes.c_int64, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64),
+        ctypes.POINTER(ctypes.c_int64)]),
+    "exa_affinities_to_segmentation_device": (ctypes.c_int, [
+        ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+        ctypes.POINTER(ctypes.c_double), ctypes.c_int, ctypes.c_double, ctypes.c_double,
+        ctypes.c_int64, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64),
+        ctypes.POINTER(ctypes.c_int64), ctypes.c_void_p]),
     "exa_count_patches": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                          ctypes.POINTER(ctypes.c_int32),
                                          ctypes.POINTER(ctypes.c_int32)]),

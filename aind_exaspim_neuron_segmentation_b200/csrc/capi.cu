@@ -6,6 +6,7 @@
 
 #include "../../include/exaspim_b200.h"
 #include "engine.h"
+#include "watershed.h"
 
 struct exa_engine {
   exa::Engine impl;
@@ -207,6 +208,29 @@ int exa_slab_finish(exa_engine* e, const float* seed_dev, float* out_dev, int64_
 int exa_set_peer_outputs(exa_engine* e, float* local_base, int64_t elems, float* const* peer_bases,
                          int n_peers) {
   return guarded(e, [&] { return e->impl.set_peer_outputs(local_base, elems, peer_bases, n_peers); });
+}
+
+int exa_affinities_to_segmentation(int device, const float* aff_host, int D, int H, int W,
+                                   const double* thresholds, int n_thresholds, double aff_low,
+                                   double aff_high, int64_t min_segment_size, uint64_t* seg_host,
+                                   int64_t* n_fragments, int64_t* n_segments) {
+  return guarded_static([&] {
+    return exa::affinities_to_segmentation_host(device, aff_host, D, H, W, thresholds, n_thresholds,
+                                                aff_low, aff_high, min_segment_size, seg_host,
+                                                n_fragments, n_segments);
+  });
+}
+
+int exa_affinities_to_segmentation_device(const float* aff_dev, int D, int H, int W,
+                                          const double* thresholds, int n_thresholds,
+                                          double aff_low, double aff_high,
+                                          int64_t min_segment_size, uint64_t* seg_dev,
+                                          int64_t* n_fragments, int64_t* n_segments, void* stream) {
+  return guarded_static([&] {
+    return exa::affinities_to_segmentation_device(aff_dev, D, H, W, thresholds, n_thresholds,
+                                                  aff_low, aff_high, min_segment_size, seg_dev,
+                                                  n_fragments, n_segments, (cudaStream_t)stream);
+  });
 }
 
 int exa_count_patches(int D, int H, int W, const int32_t patch[3], const int32_t overlap[3]) {

@@ -28,7 +28,8 @@ from . import _native
 from .engine import Engine, percentiles_from_hist, plan_slab
 from .machine_learning.unet3d import UNet3D
 
-__all__ = ["predict", "predict_sharded", "load_model", "count_patches", "generate_patch_starts"]
+__all__ = ["predict", "predict_sharded", "load_model", "count_patches", "generate_patch_starts",
+           "affinities_to_segmentation"]
 
 
 # --- tiling helpers (host integer logic) --------------------------------------------
@@ -167,6 +168,52 @@ def predict(
         pbar.update(n_patches)
         pbar.close()
     return out if affinity_mode else out[0]
+
+
+# --- downstream of the hot path: affinities -> segmentation ---------------------------------
+def affinities_to_segmentation(affinities, agglomeration_thresholds=[0.6, 0.8, 0.9],  # noqa: B006
+                               min_segment_size=100):
+    """Affinity maps ``(3, D, H, W)`` -> segmentation; reference inference.py:196-237.
+
+    Same signature and defaults (``waterz.agglomerate`` with ``aff_threshold_low=0.1``,
+    ``aff_threshold_high=0.9999``, the segmentation of the LAST threshold, then
+    ``remove_small_segments``).  Watershed fragments, the region graph and the relabelling run on
+    the GPU (``csrc/watershed.cu``); the merge queue over the region graph runs on the host.
+    numpy in -> new ``uint64 (D, H, W)`` array out, as waterz returns; a CUDA tensor in -> an
+    ``int64`` CUDA tensor out (no host round trip, e.g. straight from ``predict_sharded``).
+    """
+    import ctypes
+
+    thr = [float(t) for t in agglomeration_thresholds]
+    if not thr:
+        raise ValueError("agglomeration_thresholds must not be empty")
+    thr_c = (ctypes.c_double * len(thr))(*thr)
+    n_frag, n_seg = ctypes.c_int64(0), ctypes.c_int64(0)
+    lib = _native.lib()
+    if isinstance(affinities, torch.Tensor) and affinities.is_cuda:
+        aff = affinities.to(torch.float32).contiguous()
+        if aff.dim() != 4 or aff.shape[0] != 3:
+            raise ValueError("affinities must have shape (3, D, H, W)")
+        d, h, w = (int(v) for v in aff.shape[1:])
+        seg = torch.empty((d, h, w), dtype=torch.int64, device=aff.device)
+        with torch.cuda.device(aff.device):
+            code = lib.exa_affinities_to_segmentation_device(
+                ctypes.c_void_p(aff.data_ptr()), d, h, w, thr_c, len(thr), 0.1, 0.9999,
+                int(min_segment_size), ctypes.c_void_p(seg.data_ptr()), ctypes.byref(n_frag),
+                ctypes.byref(n_seg), ctypes.c_void_p(torch.cuda.current_stream(aff.device).cuda_stream))
+        _native.check(code, None, "exa_affinities_to_segmentation_device")
+        return seg
+    aff = np.ascontiguousarray(np.asarray(affinities).astype(np.float32, copy=False))
+    if aff.ndim != 4 or aff.shape[0] != 3:
+        raise ValueError("affinities must have shape (3, D, H, W)")
+    d, h, w = aff.shape[1:]
+    seg = np.empty((d, h, w), dtype=np.uint64)
+    code = lib.exa_affinities_to_segmentation(
+        torch.cuda.current_device(), aff.ctypes.data_as(ctypes.c_void_p), d, h, w, thr_c, len(thr),
+        0.1, 0.9999, int(min_segment_size), seg.ctypes.data_as(ctypes.c_void_p),
+        ctypes.byref(n_frag), ctypes.byref(n_seg))
+    _native.check(code, None, "exa_affinities_to_segmentation")
+    return seg
 
 
 # --- multi-GPU: z-row slabs ---------------------------------------------------------------

@@ -57,15 +57,34 @@ LAYER_SHAPES = {1: (0, 32, 32), 2: (1, 32, 64), 3: (1, 64, 64), 4: (2, 64, 128),
                 14: (1, 128, 64), 15: (1, 64, 32), 16: (0, 64, 32), 17: (0, 32, 32)}
 
 
-def layer_flops_96(i):
-    """Executed FLOPs (2*MACs) of conv layer i per 96^3 patch; the last two layers only compute the
-    kept box (80^3) and that box grown by one voxel (82^3)."""
+def layer_flops(i, p=96):
+    """Executed FLOPs (2*MACs) of conv layer i per p^3 patch; the last two layers only compute the
+    kept box ((p-16)^3) and that box grown by one voxel."""
     lvl, cin, cout = LAYER_SHAPES[i]
-    side = {16: 82, 17: 80}.get(i, 96 >> lvl)
+    side = {16: p - 2 * TRIM + 2, 17: p - 2 * TRIM}.get(i, p >> lvl)
     return 2 * side ** 3 * cout * 27 * cin
 
 
-assert sum(layer_flops_96(i) for i in LAYER_SHAPES) == F_CONV_96
+def conv_flops_executed(p=96):
+    return sum(layer_flops(i, p) for i in LAYER_SHAPES)
+
+
+def patch_flops_algorithmic(p=96):
+    """2*MACs of all 19 convs on the full p^3 patch (370 145 230 848 at 96,
+    877 381 287 936 at 128)."""
+    full = sum(2 * (p >> lvl) ** 3 * cout * 27 * cin for lvl, cin, cout in LAYER_SHAPES.values())
+    return full + 2 * p ** 3 * 32 * 27 + 2 * p ** 3 * 3 * 32
+
+
+assert conv_flops_executed(96) == F_CONV_96 and patch_flops_algorithmic(96) == F_PATCH_96
+assert patch_flops_algorithmic(128) == 877_381_287_936
+
+
+def n_patches_of(shape):
+    n = 1
+    for d, pp, ov in zip(shape, PATCH, OVERLAP):
+        n *= len(range(0, d - pp + (pp - ov), pp - ov))
+    return n
 
 
 def volume_shape(n_gpus):
@@ -272,7 +291,7 @@ def run_reference(args):
 def workload_config(n):
     shape = volume_shape(n)
     return {"workload": f"predict() on a synthetic {shape[0]}x{shape[1]}x{shape[2]} uint16 volume, "
-                        f"patch 96^3 overlap 32 trim 8 ({(shape[0] // 64) * (shape[1] // 64) * (shape[2] // 64)} "
+                        f"patch {PATCH[0]}^3 overlap 32 trim 8 ({n_patches_of(shape)} "
                         "patches), random-init UNet3D, affinity_mode=True",
             "volume": list(shape), "patch_shape": list(PATCH), "overlap": list(OVERLAP), "trim": TRIM,
             "sharding": f"z patch-rows over {n} GPU(s)" if n > 1 else "single GPU",
@@ -388,9 +407,9 @@ def run_b200(args):
 
     if rank == 0:
         peaks = measured_peaks()
-        n_patches_rank = (job.rows[1] - job.rows[0]) * (shape[1] // 64) * (shape[2] // 64)
+        n_patches_rank = (job.rows[1] - job.rows[0]) * n_patches_of((PATCH[0],) + tuple(shape[1:]))
         conv_ms, conv_launches = prof["conv"]
-        conv_flops = n_patches_rank * F_CONV_96 * args.steps
+        conv_flops = n_patches_rank * conv_flops_executed(PATCH[0]) * args.steps
         achieved_all = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
         # the dominant kernel: the z-folded CTA-pair conv (conv_zfold2.cuh)
         per_layer, dom_ms, dom_flops, dom_launches = {}, 0.0, 0.0, 0
@@ -398,7 +417,7 @@ def run_b200(args):
         for i, (lms, ln, lname) in enumerate(layers):
             if i == 0 or ln == 0:
                 continue
-            fl = n_patches_rank * layer_flops_96(i) * args.steps
+            fl = n_patches_rank * layer_flops(i, PATCH[0]) * args.steps
             per_layer[str(i)] = {"kernel": lname, "cin": LAYER_SHAPES[i][1], "cout": LAYER_SHAPES[i][2],
                                  "ms_per_launch": lms / ln, "tflops": fl / (lms * 1e-3) / 1e12}
             if lname == dom_name:
@@ -431,8 +450,8 @@ def run_b200(args):
                 "share_of_step": dom_ms / (ms_step * args.steps),
                 "all_conv_kernels": {"achieved": achieved_all, "frac": achieved_all / peaks["bf16_tflops"],
                                      "launches": conv_launches, "share_of_step": conv_ms / (ms_step * args.steps),
-                                     "flops_per_patch": F_CONV_96,
-                                     "flops_per_patch_untrimmed": F_PATCH_96},
+                                     "flops_per_patch": conv_flops_executed(PATCH[0]),
+                                     "flops_per_patch_untrimmed": patch_flops_algorithmic(PATCH[0])},
                 "per_layer": per_layer,
             },
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
@@ -530,6 +549,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference", "library"])
     ap.add_argument("--batch", type=int, default=32, help="patches per wave")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--patch", type=int, default=96, choices=[96, 128],
+                    help="patch edge: 96 = the headline workload; 128 = BASELINE config 4 (not a bench line)")
     args = ap.parse_args()
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
         # convenience: launched without torchrun -> start one process per GPU ourselves
@@ -537,6 +558,8 @@ def main():
                f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1", "--master-port",
                "29531", os.path.abspath(__file__)] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
+    global PATCH
+    PATCH = (args.patch,) * 3
     capture_stdout()
     if args.impl == "reference":
         run_reference(args)

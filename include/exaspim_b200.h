@@ -148,6 +148,25 @@ int exa_slab_finish(exa_engine* e, const float* seed_dev, float* out_dev, int64_
 int exa_set_peer_outputs(exa_engine* e, float* local_base, int64_t elems, float* const* peer_bases,
                          int n_peers);
 
+/* ---- downstream of the path: affinities -> segmentation ---------------
+ * Replaces affinities_to_segmentation (inference.py:196-237): waterz.agglomerate(affinities,
+ * thresholds, aff_threshold_low, aff_threshold_high) -- watershed fragments, region graph,
+ * hierarchical merging by 1 - mean affinity up to the last threshold -- followed by
+ * remove_small_segments (img_util.py:536-559: segments with more than min_segment_size voxels
+ * are kept and renumbered from 1 in order of first appearance).  aff: float32 (3, D, H, W),
+ * aff[c][z,y,x] = edge to the next voxel along axis c; seg: uint64 (D, H, W).  Voxel-sized steps
+ * run on the GPU, the merge queue on the host.  n_fragments / n_segments may be NULL. */
+int exa_affinities_to_segmentation(int device, const float* aff_host, int D, int H, int W,
+                                   const double* thresholds, int n_thresholds, double aff_low,
+                                   double aff_high, int64_t min_segment_size, uint64_t* seg_host,
+                                   int64_t* n_fragments, int64_t* n_segments);
+/* same on device buffers of the current device (e.g. the output of exa_predict_device) */
+int exa_affinities_to_segmentation_device(const float* aff_dev, int D, int H, int W,
+                                          const double* thresholds, int n_thresholds,
+                                          double aff_low, double aff_high,
+                                          int64_t min_segment_size, uint64_t* seg_dev,
+                                          int64_t* n_fragments, int64_t* n_segments, void* stream);
+
 /* host helpers mirroring count_patches / generate_patch_starts (inference.py:340-397);
  * starts receives n_patches*3 int32 (z,y,x) in the reference's order */
 int exa_count_patches(int D, int H, int W, const int32_t patch[3], const int32_t overlap[3]);
