@@ -147,20 +147,23 @@ ws_union_kernel(const float* __restrict__ aff, const float* __restrict__ best, V
 // K7c: root of every voxel; flag = 1 for the root voxel of every fragment
 __global__ void __launch_bounds__(256)
 ws_flatten_kernel(size_t n, uint32_t* parent, const uint8_t* __restrict__ linked,
-                  uint32_t* __restrict__ flag) {
+                  uint32_t* __restrict__ root, uint32_t* __restrict__ flag) {
   const size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= n) return;
+  // the root goes to its own array: parent[] is still being rewritten by the path halving of
+  // other threads (always to an ancestor, but not necessarily to the root)
   const uint32_t r = uf_find(parent, (uint32_t)v);
-  parent[v] = r;  // roots keep pointing at themselves, so concurrent finds stay correct
+  root[v] = r;
   flag[v] = (linked[v] && r == (uint32_t)v) ? 1u : 0u;
 }
 
+// root index -> fragment id, in place
 __global__ void __launch_bounds__(256)
-ws_assign_kernel(size_t n, const uint32_t* __restrict__ parent, const uint8_t* __restrict__ linked,
-                 const uint32_t* __restrict__ rank, uint32_t* __restrict__ frag) {
+ws_assign_kernel(size_t n, const uint8_t* __restrict__ linked, const uint32_t* __restrict__ rank,
+                 uint32_t* __restrict__ frag) {
   const size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= n) return;
-  frag[v] = linked[v] ? rank[parent[v]] + 1u : 0u;
+  frag[v] = linked[v] ? rank[frag[v]] + 1u : 0u;
 }
 
 // K7d: faces between different (non-background) fragments
@@ -335,7 +338,7 @@ Status affinities_to_segmentation_device(const float* aff, int D, int H, int W,
   ws_union_kernel<<<blocks, 256, 0, s>>>(aff, best.as<float>(), g, low, high, parent.as<uint32_t>(),
                                           linked.as<uint8_t>());
   ws_flatten_kernel<<<blocks, 256, 0, s>>>(g.n, parent.as<uint32_t>(), linked.as<uint8_t>(),
-                                            flag.as<uint32_t>());
+                                            frag.as<uint32_t>(), flag.as<uint32_t>());
   EXA_CUDA(cudaGetLastError());
   uint32_t* rank = best.as<uint32_t>();  // `best` is dead from here on
   size_t tmp_bytes = 0;
@@ -345,8 +348,7 @@ Status affinities_to_segmentation_device(const float* aff, int D, int H, int W,
   uint32_t last_rank = 0, last_flag = 0;
   EXA_CUDA(cudaMemcpyAsync(&last_rank, rank + (g.n - 1), 4, cudaMemcpyDeviceToHost, s));
   EXA_CUDA(cudaMemcpyAsync(&last_flag, flag.as<uint32_t>() + (g.n - 1), 4, cudaMemcpyDeviceToHost, s));
-  ws_assign_kernel<<<blocks, 256, 0, s>>>(g.n, parent.as<uint32_t>(), linked.as<uint8_t>(), rank,
-                                           frag.as<uint32_t>());
+  ws_assign_kernel<<<blocks, 256, 0, s>>>(g.n, linked.as<uint8_t>(), rank, frag.as<uint32_t>());
   EXA_CUDA(cudaGetLastError());
   EXA_CUDA(cudaStreamSynchronize(s));
   const uint32_t n_frag = last_rank + last_flag;
