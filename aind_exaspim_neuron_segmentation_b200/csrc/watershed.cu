@@ -24,9 +24,11 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <queue>
 #include <tuple>
-#include <unordered_map>
 #include <vector>
 
 #include "common.cuh"
@@ -253,48 +255,147 @@ struct Stat {
 };
 using Entry = std::tuple<double, uint32_t, uint32_t, long long>;
 
+// neighbour table of one region: open addressing on fragment ids (>= 1), linear probing
+class NbrMap {
+ public:
+  uint32_t size() const { return live_; }
+  void reserve(uint32_t n) {
+    uint32_t cap = 4;
+    while ((uint64_t)cap * 3 < (uint64_t)(n + 1) * 4) cap <<= 1;
+    if (cap > key_.size()) rehash(cap);
+  }
+  Stat* find(uint32_t k) {
+    if (key_.empty()) return nullptr;
+    const uint32_t mask = (uint32_t)key_.size() - 1;
+    for (uint32_t i = hash(k) & mask;; i = (i + 1) & mask) {
+      if (key_[i] == k) return &val_[i];
+      if (key_[i] == kEmpty) return nullptr;
+    }
+  }
+  void put(uint32_t k, const Stat& v) {
+    if (Stat* p = find(k)) {
+      *p = v;
+      return;
+    }
+    if (((uint64_t)used_ + 1) * 4 > (uint64_t)key_.size() * 3) {
+      uint32_t cap = 4;
+      while ((uint64_t)cap * 3 < ((uint64_t)live_ + 2) * 4 * 2) cap <<= 1;  // room to double
+      rehash(cap);
+    }
+    const uint32_t mask = (uint32_t)key_.size() - 1;
+    for (uint32_t i = hash(k) & mask;; i = (i + 1) & mask) {
+      if (key_[i] == kEmpty || key_[i] == kTomb) {
+        if (key_[i] == kEmpty) ++used_;
+        key_[i] = k;
+        val_[i] = v;
+        ++live_;
+        return;
+      }
+    }
+  }
+  void erase(uint32_t k) {
+    if (key_.empty()) return;
+    const uint32_t mask = (uint32_t)key_.size() - 1;
+    for (uint32_t i = hash(k) & mask;; i = (i + 1) & mask) {
+      if (key_[i] == k) {
+        key_[i] = kTomb;
+        --live_;
+        return;
+      }
+      if (key_[i] == kEmpty) return;
+    }
+  }
+  template <typename F>
+  void for_each(F&& f) const {
+    for (size_t i = 0; i < key_.size(); ++i)
+      if (key_[i] != kEmpty && key_[i] != kTomb) f(key_[i], val_[i]);
+  }
+  void clear() {
+    std::vector<uint32_t>().swap(key_);
+    std::vector<Stat>().swap(val_);
+    live_ = used_ = 0;
+  }
+
+ private:
+  static constexpr uint32_t kEmpty = 0, kTomb = 0xffffffffu;
+  static uint32_t hash(uint32_t k) { return k * 2654435761u; }
+  void rehash(uint32_t cap) {
+    std::vector<uint32_t> ok(cap, kEmpty);
+    std::vector<Stat> ov(cap);
+    ok.swap(key_);
+    ov.swap(val_);
+    live_ = used_ = 0;
+    const uint32_t mask = cap - 1;
+    for (size_t j = 0; j < ok.size(); ++j) {
+      if (ok[j] == kEmpty || ok[j] == kTomb) continue;
+      uint32_t i = hash(ok[j]) & mask;
+      while (key_[i] != kEmpty) i = (i + 1) & mask;
+      key_[i] = ok[j];
+      val_[i] = ov[j];
+      ++live_;
+      ++used_;
+    }
+  }
+  std::vector<uint32_t> key_;
+  std::vector<Stat> val_;
+  uint32_t live_ = 0, used_ = 0;
+};
+
 std::vector<uint32_t> agglomerate(uint32_t n_frag, const std::vector<unsigned long long>& keys,
                                   const std::vector<double>& sums, const std::vector<int>& counts,
                                   double threshold) {
   std::vector<uint32_t> parent(n_frag + 1);
   for (uint32_t i = 0; i <= n_frag; ++i) parent[i] = i;
-  std::vector<std::unordered_map<uint32_t, Stat>> nbr(n_frag + 1);
-  std::priority_queue<Entry, std::vector<Entry>, std::greater<Entry>> heap;
+  std::vector<NbrMap> nbr(n_frag + 1);
+  {
+    std::vector<uint32_t> deg(n_frag + 1, 0);
+    for (unsigned long long k : keys) {
+      ++deg[(uint32_t)(k >> 32)];
+      ++deg[(uint32_t)(k & 0xffffffffu)];
+    }
+    for (uint32_t i = 1; i <= n_frag; ++i)
+      if (deg[i]) nbr[i].reserve(deg[i]);
+  }
+  std::vector<Entry> init;
+  init.reserve(keys.size());
   for (size_t i = 0; i < keys.size(); ++i) {
     const uint32_t a = (uint32_t)(keys[i] >> 32), b = (uint32_t)(keys[i] & 0xffffffffu);
     const Stat st{sums[i], (long long)counts[i]};
-    nbr[a][b] = st;
-    nbr[b][a] = st;
-    heap.emplace(1.0 - st.s / (double)st.c, a, b, st.c);
+    nbr[a].put(b, st);
+    nbr[b].put(a, st);
+    init.emplace_back(1.0 - st.s / (double)st.c, a, b, st.c);
   }
+  std::priority_queue<Entry, std::vector<Entry>, std::greater<Entry>> heap(std::greater<Entry>(),
+                                                                            std::move(init));
+  std::vector<std::pair<uint32_t, Stat>> moved;
   while (!heap.empty()) {
     const Entry e = heap.top();
     heap.pop();
     if (std::get<0>(e) >= threshold) break;
     uint32_t a = std::get<1>(e), b = std::get<2>(e);
     if (parent[a] != a || parent[b] != b) continue;
-    const auto it = nbr[a].find(b);
-    if (it == nbr[a].end() || it->second.c != std::get<3>(e)) continue;
+    const Stat* cur_ab = nbr[a].find(b);
+    if (cur_ab == nullptr || cur_ab->c != std::get<3>(e)) continue;
     if (nbr[a].size() < nbr[b].size()) std::swap(a, b);  // the node with fewer neighbours goes away
     parent[b] = a;
     nbr[a].erase(b);
-    for (const auto& kv : nbr[b]) {
+    moved.clear();
+    nbr[b].for_each([&](uint32_t nb, const Stat& st) {
+      if (nb != a) moved.emplace_back(nb, st);
+    });
+    nbr[b].clear();
+    for (const auto& kv : moved) {
       const uint32_t nb = kv.first;
-      if (nb == a) continue;
       nbr[nb].erase(b);
-      Stat cur;
-      const auto f = nbr[a].find(nb);
-      if (f != nbr[a].end()) {
-        cur.s = f->second.s + kv.second.s;
-        cur.c = f->second.c + kv.second.c;
-      } else {
-        cur = kv.second;
+      Stat cur = kv.second;
+      if (const Stat* f = nbr[a].find(nb)) {
+        cur.s = f->s + kv.second.s;
+        cur.c = f->c + kv.second.c;
       }
-      nbr[a][nb] = cur;
-      nbr[nb][a] = cur;
+      nbr[a].put(nb, cur);
+      nbr[nb].put(a, cur);
       heap.emplace(1.0 - cur.s / (double)cur.c, std::min(a, nb), std::max(a, nb), cur.c);
     }
-    nbr[b].clear();
   }
   std::vector<uint32_t> root(n_frag + 1);
   for (uint32_t i = 0; i <= n_frag; ++i) {
@@ -324,6 +425,17 @@ Status affinities_to_segmentation_device(const float* aff, int D, int H, int W,
   const double threshold = *std::max_element(thresholds, thresholds + n_thresholds);
   const float low = (float)aff_low, high = (float)aff_high;
   const unsigned blocks = grid_for(g.n);
+  // EXA_WS_PROF=1: wall time of the phases on stderr (every phase ends with a stream sync)
+  const char* prof_env = getenv("EXA_WS_PROF");
+  const bool prof = prof_env && prof_env[0] == '1';
+  auto t_last = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!prof) return;
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[exa watershed] %-28s %9.3f ms\n", what,
+            std::chrono::duration<double, std::milli>(now - t_last).count());
+    t_last = now;
+  };
 
   DevBuf best, parent, linked, flag, frag, tmp;
   EXA_TRY(best.alloc(g.n * 4));
@@ -353,6 +465,7 @@ Status affinities_to_segmentation_device(const float* aff, int D, int H, int W,
   EXA_CUDA(cudaStreamSynchronize(s));
   const uint32_t n_frag = last_rank + last_flag;
   if (n_fragments) *n_fragments = n_frag;
+  lap("fragments (GPU)");
 
   // ---- region graph ----
   uint32_t* cnt = flag.as<uint32_t>();  // root flags are dead
@@ -426,8 +539,11 @@ Status affinities_to_segmentation_device(const float* aff, int D, int H, int W,
     EXA_CUDA(cudaStreamSynchronize(s));
   }
 
+  lap("region graph (GPU)");
   // ---- agglomeration (host) ----
   const std::vector<uint32_t> root = agglomerate(n_frag, h_keys, h_sums, h_counts, threshold);
+  if (prof) fprintf(stderr, "[exa watershed] %u fragments, %zu region edges\n", n_frag, h_keys.size());
+  lap("merge queue (host)");
 
   // ---- small segments out, ids in order of first appearance (img_util.py:536-559) ----
   DevBuf sizes;
@@ -461,6 +577,7 @@ Status affinities_to_segmentation_device(const float* aff, int D, int H, int W,
   ws_relabel_kernel<<<blocks, 256, 0, s>>>(g.n, frag.as<uint32_t>(), lut_dev, seg);
   EXA_CUDA(cudaGetLastError());
   EXA_CUDA(cudaStreamSynchronize(s));  // lut (host vector) and the device buffers go out of scope
+  lap("sizes + relabel (GPU)");
   return Status::OK();
 }
 
