@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_PKG_DIR, "libexaspim_b200.so")
 SOURCES = ["capi.cu", "engine.cu", "kernels_mem.cu", "conv_umma.cu", "conv_zfold.cu", "conv_stem.cu",
            "watershed.cu"]
 HEADERS = ["common.cuh", "conv_umma.cuh", "conv_zfold.cuh", "conv_zfold2.cuh", "conv_stem.cuh", "engine.h",
-           "kernels.h", "tmap.h", "watershed.h"]
+           "kernels.h", "tmap.h", "watershed.h", "ws_agglomerate.h"]
 
 PRECISION_BF16 = 0
 PRECISION_FP32 = 1
@@ -145,6 +145,9 @@ _SIGNATURES = {
         ctypes.POINTER(ctypes.c_double), ctypes.c_int, ctypes.c_double, ctypes.c_double,
         ctypes.c_int64, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64),
         ctypes.POINTER(ctypes.c_int64)]),
+    "exa_region_agglomerate": (ctypes.c_int, [ctypes.c_uint32, ctypes.c_int64, ctypes.c_void_p,
+                                              ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double,
+                                              ctypes.c_void_p]),
     "exa_affinities_to_segmentation_device": (ctypes.c_int, [
         ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
         ctypes.POINTER(ctypes.c_double), ctypes.c_int, ctypes.c_double, ctypes.c_double,

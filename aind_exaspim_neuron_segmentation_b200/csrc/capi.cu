@@ -221,6 +221,14 @@ int exa_affinities_to_segmentation(int device, const float* aff_host, int D, int
   });
 }
 
+int exa_region_agglomerate(uint32_t n_fragments, int64_t n_edges, const uint64_t* pair_keys,
+                           const double* sums, const int32_t* counts, double threshold,
+                           uint32_t* root_out) {
+  return guarded_static([&] {
+    return exa::region_agglomerate(n_fragments, n_edges, pair_keys, sums, counts, threshold, root_out);
+  });
+}
+
 int exa_affinities_to_segmentation_device(const float* aff_dev, int D, int H, int W,
                                           const double* thresholds, int n_thresholds,
                                           double aff_low, double aff_high,

@@ -27,12 +27,11 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
-#include <queue>
-#include <tuple>
 #include <vector>
 
 #include "common.cuh"
 #include "watershed.h"
+#include "ws_agglomerate.h"
 
 namespace exa {
 
@@ -245,167 +244,6 @@ struct ToF64 {
   __host__ __device__ double operator()(float w) const { return (double)w; }
 };
 
-// Hierarchical agglomeration with OneMinus<MeanAffinity> scoring (waterz): merge the pair with the
-// smallest score while it is below the threshold; statistics of parallel edges add up.  Entries of
-// the heap are (score, a, b, count) compared lexicographically; an entry is stale when one of its
-// ends was merged away or the edge's count changed since it was pushed.
-struct Stat {
-  double s;
-  long long c;
-};
-using Entry = std::tuple<double, uint32_t, uint32_t, long long>;
-
-// neighbour table of one region: open addressing on fragment ids (>= 1), linear probing
-class NbrMap {
- public:
-  uint32_t size() const { return live_; }
-  void reserve(uint32_t n) {
-    uint32_t cap = 4;
-    while ((uint64_t)cap * 3 < (uint64_t)(n + 1) * 4) cap <<= 1;
-    if (cap > key_.size()) rehash(cap);
-  }
-  Stat* find(uint32_t k) {
-    if (key_.empty()) return nullptr;
-    const uint32_t mask = (uint32_t)key_.size() - 1;
-    for (uint32_t i = hash(k) & mask;; i = (i + 1) & mask) {
-      if (key_[i] == k) return &val_[i];
-      if (key_[i] == kEmpty) return nullptr;
-    }
-  }
-  void put(uint32_t k, const Stat& v) {
-    if (Stat* p = find(k)) {
-      *p = v;
-      return;
-    }
-    if (((uint64_t)used_ + 1) * 4 > (uint64_t)key_.size() * 3) {
-      uint32_t cap = 4;
-      while ((uint64_t)cap * 3 < ((uint64_t)live_ + 2) * 4 * 2) cap <<= 1;  // room to double
-      rehash(cap);
-    }
-    const uint32_t mask = (uint32_t)key_.size() - 1;
-    for (uint32_t i = hash(k) & mask;; i = (i + 1) & mask) {
-      if (key_[i] == kEmpty || key_[i] == kTomb) {
-        if (key_[i] == kEmpty) ++used_;
-        key_[i] = k;
-        val_[i] = v;
-        ++live_;
-        return;
-      }
-    }
-  }
-  void erase(uint32_t k) {
-    if (key_.empty()) return;
-    const uint32_t mask = (uint32_t)key_.size() - 1;
-    for (uint32_t i = hash(k) & mask;; i = (i + 1) & mask) {
-      if (key_[i] == k) {
-        key_[i] = kTomb;
-        --live_;
-        return;
-      }
-      if (key_[i] == kEmpty) return;
-    }
-  }
-  template <typename F>
-  void for_each(F&& f) const {
-    for (size_t i = 0; i < key_.size(); ++i)
-      if (key_[i] != kEmpty && key_[i] != kTomb) f(key_[i], val_[i]);
-  }
-  void clear() {
-    std::vector<uint32_t>().swap(key_);
-    std::vector<Stat>().swap(val_);
-    live_ = used_ = 0;
-  }
-
- private:
-  static constexpr uint32_t kEmpty = 0, kTomb = 0xffffffffu;
-  static uint32_t hash(uint32_t k) { return k * 2654435761u; }
-  void rehash(uint32_t cap) {
-    std::vector<uint32_t> ok(cap, kEmpty);
-    std::vector<Stat> ov(cap);
-    ok.swap(key_);
-    ov.swap(val_);
-    live_ = used_ = 0;
-    const uint32_t mask = cap - 1;
-    for (size_t j = 0; j < ok.size(); ++j) {
-      if (ok[j] == kEmpty || ok[j] == kTomb) continue;
-      uint32_t i = hash(ok[j]) & mask;
-      while (key_[i] != kEmpty) i = (i + 1) & mask;
-      key_[i] = ok[j];
-      val_[i] = ov[j];
-      ++live_;
-      ++used_;
-    }
-  }
-  std::vector<uint32_t> key_;
-  std::vector<Stat> val_;
-  uint32_t live_ = 0, used_ = 0;
-};
-
-std::vector<uint32_t> agglomerate(uint32_t n_frag, const std::vector<unsigned long long>& keys,
-                                  const std::vector<double>& sums, const std::vector<int>& counts,
-                                  double threshold) {
-  std::vector<uint32_t> parent(n_frag + 1);
-  for (uint32_t i = 0; i <= n_frag; ++i) parent[i] = i;
-  std::vector<NbrMap> nbr(n_frag + 1);
-  {
-    std::vector<uint32_t> deg(n_frag + 1, 0);
-    for (unsigned long long k : keys) {
-      ++deg[(uint32_t)(k >> 32)];
-      ++deg[(uint32_t)(k & 0xffffffffu)];
-    }
-    for (uint32_t i = 1; i <= n_frag; ++i)
-      if (deg[i]) nbr[i].reserve(deg[i]);
-  }
-  std::vector<Entry> init;
-  init.reserve(keys.size());
-  for (size_t i = 0; i < keys.size(); ++i) {
-    const uint32_t a = (uint32_t)(keys[i] >> 32), b = (uint32_t)(keys[i] & 0xffffffffu);
-    const Stat st{sums[i], (long long)counts[i]};
-    nbr[a].put(b, st);
-    nbr[b].put(a, st);
-    init.emplace_back(1.0 - st.s / (double)st.c, a, b, st.c);
-  }
-  std::priority_queue<Entry, std::vector<Entry>, std::greater<Entry>> heap(std::greater<Entry>(),
-                                                                            std::move(init));
-  std::vector<std::pair<uint32_t, Stat>> moved;
-  while (!heap.empty()) {
-    const Entry e = heap.top();
-    heap.pop();
-    if (std::get<0>(e) >= threshold) break;
-    uint32_t a = std::get<1>(e), b = std::get<2>(e);
-    if (parent[a] != a || parent[b] != b) continue;
-    const Stat* cur_ab = nbr[a].find(b);
-    if (cur_ab == nullptr || cur_ab->c != std::get<3>(e)) continue;
-    if (nbr[a].size() < nbr[b].size()) std::swap(a, b);  // the node with fewer neighbours goes away
-    parent[b] = a;
-    nbr[a].erase(b);
-    moved.clear();
-    nbr[b].for_each([&](uint32_t nb, const Stat& st) {
-      if (nb != a) moved.emplace_back(nb, st);
-    });
-    nbr[b].clear();
-    for (const auto& kv : moved) {
-      const uint32_t nb = kv.first;
-      nbr[nb].erase(b);
-      Stat cur = kv.second;
-      if (const Stat* f = nbr[a].find(nb)) {
-        cur.s = f->s + kv.second.s;
-        cur.c = f->c + kv.second.c;
-      }
-      nbr[a].put(nb, cur);
-      nbr[nb].put(a, cur);
-      heap.emplace(1.0 - cur.s / (double)cur.c, std::min(a, nb), std::max(a, nb), cur.c);
-    }
-  }
-  std::vector<uint32_t> root(n_frag + 1);
-  for (uint32_t i = 0; i <= n_frag; ++i) {
-    uint32_t x = i;
-    while (parent[x] != x) x = parent[x];
-    root[i] = x;
-  }
-  return root;
-}
-
 inline unsigned grid_for(size_t n) { return (unsigned)((n + 255) / 256); }
 
 }  // namespace
@@ -541,7 +379,7 @@ Status affinities_to_segmentation_device(const float* aff, int D, int H, int W,
 
   lap("region graph (GPU)");
   // ---- agglomeration (host) ----
-  const std::vector<uint32_t> root = agglomerate(n_frag, h_keys, h_sums, h_counts, threshold);
+  const std::vector<uint32_t> root = ws::agglomerate(n_frag, h_keys, h_sums, h_counts, threshold);
   if (prof) fprintf(stderr, "[exa watershed] %u fragments, %zu region edges\n", n_frag, h_keys.size());
   lap("merge queue (host)");
 
@@ -578,6 +416,23 @@ Status affinities_to_segmentation_device(const float* aff, int D, int H, int W,
   EXA_CUDA(cudaGetLastError());
   EXA_CUDA(cudaStreamSynchronize(s));  // lut (host vector) and the device buffers go out of scope
   lap("sizes + relabel (GPU)");
+  return Status::OK();
+}
+
+Status region_agglomerate(uint32_t n_fragments, int64_t n_edges, const uint64_t* pair_keys,
+                          const double* sums, const int32_t* counts, double threshold,
+                          uint32_t* root_out) {
+  EXA_CHECK(n_edges >= 0 && root_out && (n_edges == 0 || (pair_keys && sums && counts)),
+            "region_agglomerate: null argument");
+  std::vector<unsigned long long> k(pair_keys, pair_keys + n_edges);
+  std::vector<double> s(sums, sums + n_edges);
+  std::vector<int> c(counts, counts + n_edges);
+  for (int64_t i = 0; i < n_edges; ++i) {
+    const uint64_t a = k[i] >> 32, b = k[i] & 0xffffffffu;
+    EXA_CHECK(a >= 1 && a < b && b <= n_fragments && c[i] > 0, "region_agglomerate: bad edge");
+  }
+  const std::vector<uint32_t> root = ws::agglomerate(n_fragments, k, s, c, threshold);
+  std::copy(root.begin(), root.end(), root_out);
   return Status::OK();
 }
 

@@ -20,4 +20,10 @@ Status affinities_to_segmentation_host(int device, const float* aff, int D, int 
                                        double aff_high, int64_t min_segment_size, uint64_t* seg,
                                        int64_t* n_fragments, int64_t* n_segments);
 
+// the host merge queue alone (no GPU): edges (a << 32 | b, a < b) with summed affinity and face
+// count -> root fragment of every fragment 0..n_fragments (root_out has n_fragments + 1 entries)
+Status region_agglomerate(uint32_t n_fragments, int64_t n_edges, const uint64_t* pair_keys,
+                          const double* sums, const int32_t* counts, double threshold,
+                          uint32_t* root_out);
+
 }  // namespace exa

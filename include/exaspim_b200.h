@@ -167,6 +167,14 @@ int exa_affinities_to_segmentation_device(const float* aff_dev, int D, int H, in
                                           int64_t min_segment_size, uint64_t* seg_dev,
                                           int64_t* n_fragments, int64_t* n_segments, void* stream);
 
+/* the merge queue of the function above on its own (host, no GPU needed): region graph edges
+ * pair_keys[i] = a << 32 | b with 1 <= a < b <= n_fragments, sums[i] = summed affinity and
+ * counts[i] = number of faces between a and b; root_out[0..n_fragments] receives the surviving
+ * fragment every fragment was merged into while the smallest 1 - sum/count was < threshold */
+int exa_region_agglomerate(uint32_t n_fragments, int64_t n_edges, const uint64_t* pair_keys,
+                           const double* sums, const int32_t* counts, double threshold,
+                           uint32_t* root_out);
+
 /* host helpers mirroring count_patches / generate_patch_starts (inference.py:340-397);
  * starts receives n_patches*3 int32 (z,y,x) in the reference's order */
 int exa_count_patches(int D, int H, int W, const int32_t patch[3], const int32_t overlap[3]);
