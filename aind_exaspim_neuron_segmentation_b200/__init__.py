@@ -13,5 +13,6 @@ from .inference import (  # noqa: F401
     load_model,
     predict,
     predict_sharded,
+    predict_streamed,
 )
 from .machine_learning.unet3d import UNet3D  # noqa: F401

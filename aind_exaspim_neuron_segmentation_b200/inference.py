@@ -28,8 +28,8 @@ from . import _native
 from .engine import Engine, percentiles_from_hist, plan_slab
 from .machine_learning.unet3d import UNet3D
 
-__all__ = ["predict", "predict_sharded", "load_model", "count_patches", "generate_patch_starts",
-           "affinities_to_segmentation"]
+__all__ = ["predict", "predict_sharded", "predict_streamed", "load_model", "count_patches",
+           "generate_patch_starts", "affinities_to_segmentation"]
 
 
 # --- tiling helpers (host integer logic) --------------------------------------------
@@ -168,6 +168,101 @@ def predict(
         pbar.update(n_patches)
         pbar.close()
     return out if affinity_mode else out[0]
+
+
+# --- volumes larger than memory: chunks of z patch-rows, one after the other ------------------
+def predict_streamed(
+    img,
+    model,
+    out,
+    affinity_mode=True,
+    batch_size=16,
+    brightness_clip=1000,
+    normalization_percentiles=(1, 99.9),
+    patch_shape=(96, 96, 96),
+    overlap=(32, 32, 32),
+    trim=8,
+    rows_per_chunk=4,
+    precision=None,
+):
+    """``predict`` for volumes that fit neither in host nor in device memory.
+
+    ``img`` is anything with a ``(D, H, W)`` ``.shape`` that returns planes for ``img[z0:z1]``
+    (``np.memmap``, a zarr / N5 / HDF5 array, ...); ``out`` anything that accepts
+    ``out[:, z0:z1] = planes`` (``out[z0:z1]`` when ``affinity_mode=False``).  The reference holds
+    the whole volume plus 16 B/voxel of accumulators in RAM (inference.py:80,91-92); here only
+    ``rows_per_chunk`` z patch-rows are resident at a time.  Two passes over the input: the global
+    percentiles need every voxel (exact 1001-bin histogram, accumulated per chunk), then the
+    chunks run one after the other exactly like the ranks of ``predict_sharded`` -- each hands the
+    partial sums of the planes it shares with the next one forward -- so the result is bit-identical
+    to ``predict``.  Returns ``out``.
+    """
+    _check_clip(img, brightness_clip)
+    shape = tuple(int(v) for v in img.shape)
+    if len(shape) != 3:
+        raise ValueError("predict_streamed expects a (D, H, W) array-like")
+    engine = _engine_for(model, precision)
+    c = 3 if affinity_mode else 1
+    if engine.out_channels != c:
+        raise ValueError(f"model has {engine.out_channels} output channels but affinity_mode={affinity_mode} "
+                         f"needs {c}")
+    params = _native.make_params(patch_shape, overlap, trim, brightness_clip,
+                                 normalization_percentiles, batch=max(int(batch_size), 32))
+    clip = params.brightness_clip
+    dev = engine.device
+    d, h, w = shape
+    nz = plan_slab(shape, params, 0, 0)["nz"]
+    rows_per_chunk = max(1, int(rows_per_chunk))
+    if patch_shape[0] - 2 * trim > 2 * (patch_shape[0] - overlap[0]):
+        rows_per_chunk = nz   # planes covered by three rows cannot be handed over pairwise
+    stride_z = patch_shape[0] - overlap[0]
+
+    def planes(z0, z1):
+        arr = np.asarray(_as_volume_u16(img[z0:z1], clip))
+        if not arr.flags.writeable:   # e.g. a read-only memory map
+            arr = arr.copy()
+        return torch.from_numpy(arr).to(dev)
+
+    def store(z0, z1, host):
+        if affinity_mode:
+            out[:, z0:z1] = host
+        else:
+            out[z0:z1] = host[0]
+
+    # pass 1: exact global percentiles from per-chunk histograms
+    hist = torch.zeros(clip + 1, dtype=torch.int64, device=dev)
+    step = max(rows_per_chunk * stride_z, 1)
+    for z0 in range(0, d, step):
+        hist += engine.histogram(planes(z0, min(z0 + step, d)), clip)
+    mn, mx = percentiles_from_hist(hist.cpu().numpy().astype(np.uint64), params.pct_lo, params.pct_hi)
+    if nz == 0 or count_patches((1, 1) + shape, patch_shape, overlap) == 0:
+        zero = np.zeros((c, min(step, d), h, w), dtype=np.float32)
+        for z0 in range(0, d, step):
+            store(z0, min(z0 + step, d), zero[:, :min(z0 + step, d) - z0])
+        return out
+    # pass 2: row chunks; the halo of one chunk seeds the next
+    engine.set_normalization(mn, mx, clip)
+    plans = [plan_slab(shape, params, r0, min(r0 + rows_per_chunk, nz))
+             for r0 in range(0, nz, rows_per_chunk)]
+    max_own = max(p["out_z1"] - p["out_z0"] for p in plans)
+    own_dev = torch.empty((c, max_own, h, w), dtype=torch.float32, device=dev)
+    own_host = torch.empty((c, max_own, h, w), dtype=torch.float32).pin_memory()
+    seed = None
+    for i, pl in enumerate(plans):
+        r0 = i * rows_per_chunk
+        r1 = min(r0 + rows_per_chunk, nz)
+        n_own = pl["out_z1"] - pl["out_z0"]
+        n_halo = pl["halo_z1"] - pl["halo_z0"]
+        halo = torch.empty((c, n_halo, h, w), dtype=torch.float32, device=dev) if n_halo > 0 else None
+        slab = planes(pl["in_z0"], pl["in_z1"])
+        # dense (C, n_own, H, W) views of the re-used buffers
+        od = own_dev.view(-1)[:c * n_own * h * w].view(c, n_own, h, w)
+        oh = own_host.view(-1)[:c * n_own * h * w].view(c, n_own, h, w)
+        engine.slab_predict(slab, shape, params, r0, r1, od, oh, halo)
+        engine.slab_finish(seed, od, oh)
+        store(pl["out_z0"], pl["out_z1"], oh.numpy())
+        seed = halo
+    return out
 
 
 # --- downstream of the hot path: affinities -> segmentation ---------------------------------

@@ -160,6 +160,32 @@ def test_device_path_equals_host_path_and_slabs_equal_single():
         assert np.array_equal(out, host), cuts
 
 
+def test_predict_streamed_equals_predict(tmp_path):
+    """Out-of-core form: memory-mapped input and output, a few z patch-rows resident at a time,
+    bit-identical to predict() (same summation order through the halo hand-over)."""
+    from aind_exaspim_neuron_segmentation_b200 import predict, predict_streamed
+
+    model = _model("rescaled", 23)
+    shape = (150, 40, 56)
+    vol = lightsheet_volume(shape, 24)
+    kw = dict(patch_shape=(32, 32, 32), overlap=(8, 8, 8), trim=4)
+    ref = predict(vol, model, verbose=False, **kw)
+    src = np.memmap(tmp_path / "vol.u16", dtype=np.uint16, mode="w+", shape=shape)
+    src[:] = vol
+    for rows in (1, 2, 100):
+        dst = np.memmap(tmp_path / f"aff{rows}.f32", dtype=np.float32, mode="w+", shape=(3,) + shape)
+        dst[:] = -1
+        assert predict_streamed(src, model, dst, rows_per_chunk=rows, **kw) is dst
+        assert np.array_equal(np.asarray(dst), ref), rows
+    # foreground mode writes (D, H, W); a volume below one patch stride gives zeros like predict()
+    fg = _model("rescaled", 13, "bf16", 1)
+    out1 = np.full(shape, -1, np.float32)
+    predict_streamed(src, fg, out1, affinity_mode=False, rows_per_chunk=2, **kw)
+    assert np.array_equal(out1, predict(vol, fg, affinity_mode=False, verbose=False, **kw))
+    with pytest.raises(ValueError):
+        predict_streamed(vol[None], model, np.empty((3,) + shape, np.float32), **kw)
+
+
 def test_full_size_properties_512():
     """BASELINE config 2 size: properties that do not need the (17-minute) CPU oracle."""
     from aind_exaspim_neuron_segmentation_b200 import predict
