@@ -323,6 +323,9 @@ def split_rows(n_rows, world_size):
     return out
 
 
+_SYMMETRIC_OUTPUTS = {}
+
+
 class _EngineSlabBackend:
     """Slab compute on the native engine (device tensors)."""
 
@@ -361,10 +364,17 @@ class _EngineSlabBackend:
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm
 
-        full = symm.empty(*shape, dtype=torch.float32, device=self.device)
-        hdl = symm.rendezvous(full, group if group is not None else dist.group.WORLD)
-        ptrs = [int(p) for r, p in enumerate(hdl.buffer_ptrs) if r != hdl.rank]
-        return full, hdl, ptrs
+        # one buffer per (shape, device, group), kept for the life of the process: symmetric
+        # allocations are expensive to set up and every job of that shape can share it -- the
+        # gathered array a job returns is valid until the next gather of the same shape
+        pg = group if group is not None else dist.group.WORLD
+        key = (tuple(shape), str(self.device), pg.group_name)
+        if key not in _SYMMETRIC_OUTPUTS:
+            full = symm.empty(*shape, dtype=torch.float32, device=self.device)
+            hdl = symm.rendezvous(full, pg)
+            ptrs = [int(p) for r, p in enumerate(hdl.buffer_ptrs) if r != hdl.rank]
+            _SYMMETRIC_OUTPUTS[key] = (full, hdl, ptrs)
+        return _SYMMETRIC_OUTPUTS[key]
 
     def set_peers(self, full, ptrs):
         self.engine.set_peer_outputs(full, ptrs)
