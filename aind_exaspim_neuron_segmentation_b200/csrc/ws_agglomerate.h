@@ -123,10 +123,21 @@ class BucketQueue {
     bin_.resize(nb);
     scale_ = threshold > 0 ? (double)nb / threshold : 0.0;
   }
+  // the initial edges at once: bins sized exactly, then heapified (no per-entry reallocation)
+  void bulk_load(const std::vector<Entry>& all) {
+    std::vector<uint32_t> n(bin_.size(), 0);
+    for (const Entry& e : all)
+      if (std::get<0>(e) < thr_) ++n[bin_of(std::get<0>(e))];
+    for (size_t i = 0; i < bin_.size(); ++i) bin_[i].reserve(n[i] + n[i] / 2);
+    for (const Entry& e : all)
+      if (std::get<0>(e) < thr_) bin_[bin_of(std::get<0>(e))].push_back(e);
+    for (std::vector<Entry>& h : bin_) std::make_heap(h.begin(), h.end(), std::greater<Entry>());
+    cur_ = 0;
+  }
   void push(const Entry& e) {
     const double sc = std::get<0>(e);
     if (!(sc < thr_)) return;
-    size_t i = sc <= 0 ? 0 : std::min((size_t)(sc * scale_), bin_.size() - 1);
+    const size_t i = bin_of(sc);
     if (i < cur_) cur_ = i;  // rounding put a merged score one ulp under the minimum
     bin_[i].push_back(e);
     std::push_heap(bin_[i].begin(), bin_[i].end(), std::greater<Entry>());
@@ -142,6 +153,9 @@ class BucketQueue {
   }
 
  private:
+  size_t bin_of(double sc) const {
+    return sc <= 0 ? 0 : std::min((size_t)(sc * scale_), bin_.size() - 1);
+  }
   double thr_, scale_;
   size_t cur_ = 0;
   std::vector<std::vector<Entry>> bin_;
@@ -163,12 +177,17 @@ std::vector<uint32_t> agglomerate(uint32_t n_frag, const std::vector<unsigned lo
       if (deg[i]) nbr[i].reserve(deg[i]);
   }
   BucketQueue heap(threshold, keys.size());
-  for (size_t i = 0; i < keys.size(); ++i) {
-    const uint32_t a = (uint32_t)(keys[i] >> 32), b = (uint32_t)(keys[i] & 0xffffffffu);
-    const Stat st{sums[i], (long long)counts[i]};
-    nbr[a].put(b, st);
-    nbr[b].put(a, st);
-    heap.push(Entry(1.0 - st.s / (double)st.c, a, b, st.c));
+  {
+    std::vector<Entry> init;
+    init.reserve(keys.size());
+    for (size_t i = 0; i < keys.size(); ++i) {
+      const uint32_t a = (uint32_t)(keys[i] >> 32), b = (uint32_t)(keys[i] & 0xffffffffu);
+      const Stat st{sums[i], (long long)counts[i]};
+      nbr[a].put(b, st);
+      nbr[b].put(a, st);
+      init.emplace_back(1.0 - st.s / (double)st.c, a, b, st.c);
+    }
+    heap.bulk_load(init);
   }
   std::vector<std::pair<uint32_t, Stat>> moved;
   Entry e;
