@@ -63,3 +63,33 @@ def test_merge_queue_rejects_bad_edges_and_handles_empty_graph():
         native_roots(3, keys, np.ones(1), np.ones(1, np.int32), 0.9)
     root = native_roots(4, np.zeros(0, np.uint64), np.zeros(0), np.zeros(0, np.int32), 0.9)
     assert np.array_equal(root, np.arange(5))
+
+
+def test_merge_queue_equals_oracle_on_random_graphs():
+    """Arbitrary (non-grid) region graphs with many exact score ties: few distinct affinity values,
+    small counts, dense and sparse graphs, thresholds inside and outside the score range."""
+    from oracle.watershed_ref import agglomerate
+
+    rng = np.random.default_rng(7)
+    for trial in range(60):
+        n = int(rng.integers(2, 60))
+        m = int(rng.integers(1, min(n * (n - 1) // 2, 4 * n) + 1))
+        pairs = set()
+        while len(pairs) < m:
+            a, b = (int(v) for v in rng.integers(1, n + 1, 2))
+            if a != b:
+                pairs.add((min(a, b), max(a, b)))
+        levels = rng.integers(2, 9)
+        stats = {}
+        for a, b in sorted(pairs):
+            c = int(rng.integers(1, 6))
+            # sums of float32 values that are multiples of 1/levels: exact in float64, many ties
+            vals = (rng.integers(0, levels + 1, c) / levels).astype(np.float32).astype(np.float64)
+            stats[(a, b)] = [float(vals.sum()), c]
+        keys = np.array([(a << 32) | b for a, b in stats], dtype=np.uint64)
+        sums = np.array([v[0] for v in stats.values()], dtype=np.float64)
+        cnts = np.array([v[1] for v in stats.values()], dtype=np.int32)
+        threshold = float(rng.choice([0.0, 0.25, 0.5, 0.75, 0.9, 1.0, 1.5]))
+        ref = agglomerate(n, {k: list(v) for k, v in stats.items()}, threshold)
+        got = native_roots(n, keys, sums, cnts, threshold)
+        assert np.array_equal(got.astype(np.int64), ref), (trial, n, m, threshold)
