@@ -80,7 +80,8 @@ def build(force=False, verbose=False):
             return LIB_PATH  # GPU box without a toolchain mismatch: use the prebuilt library
         raise RuntimeError("nvcc not found and libexaspim_b200.so is not built")
     cmd = [
-        nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+        nvcc, "--threads", "0", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
+        "-std=c++17",
         "-Xcompiler", "-fPIC", "-shared", "-o", LIB_PATH + ".tmp",
     ] + [os.path.join(_CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
