@@ -1,0 +1,49 @@
+"""bench.py contract pieces that need no GPU: the FLOP accounting behind the roofline numbers and
+the JSON line of the reference arm (the CPU oracle port timed on a bounded sample)."""
+
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def test_flop_accounting_matches_survey_figures():
+    import bench
+
+    assert bench.patch_flops_algorithmic(96) == 370_145_230_848
+    assert bench.patch_flops_algorithmic(128) == 877_381_287_936
+    assert bench.conv_flops_executed(96) == bench.F_CONV_96 < bench.F_PATCH_96
+    # trimmed layers: only the kept box (and that box grown by one voxel) is executed
+    assert bench.layer_flops(17, 96) == 2 * 80 ** 3 * 32 * 27 * 32
+    assert bench.layer_flops(16, 96) == 2 * 82 ** 3 * 32 * 27 * 64
+    assert bench.layer_flops(16, 128) == 2 * 114 ** 3 * 32 * 27 * 64
+    old = bench.PATCH
+    try:
+        bench.PATCH = (96,) * 3
+        assert bench.n_patches_of((512,) * 3) == 512 and bench.n_patches_of((1024,) * 3) == 4096
+        bench.PATCH = (128,) * 3
+        assert bench.n_patches_of((512,) * 3) == 125 and bench.n_patches_of((1024,) * 3) == 1331
+    finally:
+        bench.PATCH = old
+    assert bench.volume_shape(1) == (512, 512, 512) and bench.volume_shape(8) == (1024, 1024, 1024)
+
+
+def test_reference_arm_prints_one_contract_line():
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True,
+                         timeout=600, cwd=ROOT)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, res.stdout[-2000:]          # nothing but the JSON line on stdout
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["metric"] == "affinity voxels/sec"
+    assert line["unit"] == "voxels/s" and line["higher_is_better"] is True
+    assert line["n_gpus"] == 1 and line["steps"] == 1 and line["value"] > 0 and line["ms_per_step"] > 0
+    assert line["e2e"] == {"value": line["value"], "unit": "voxels/s", "h2d_bytes_per_step": 0,
+                           "d2h_bytes_per_step": 0}
+    base = line["cpu_baseline"]
+    assert base["kind"] == "port" and base["cores"] >= 1 and base["value"] == line["value"]
+    assert "sample" in base and line["config"]["workload"].startswith("predict() on a synthetic 512x512x512")
