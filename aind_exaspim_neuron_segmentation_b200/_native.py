@@ -93,6 +93,8 @@ def build(force=False, verbose=False):
     return LIB_PATH
 
 
+PROGRESS_FN = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64)
+
 _lib = None
 
 _SIGNATURES = {
@@ -109,6 +111,7 @@ _SIGNATURES = {
                                    ctypes.POINTER(ctypes.c_int32), ctypes.c_void_p]),
     "exa_predict": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                                    ctypes.c_int, ctypes.POINTER(PredictParams), ctypes.c_void_p]),
+    "exa_set_progress_callback": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "exa_predict_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                           ctypes.c_int, ctypes.c_int,
                                           ctypes.POINTER(PredictParams), ctypes.c_void_p,

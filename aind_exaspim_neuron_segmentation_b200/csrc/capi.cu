@@ -129,6 +129,13 @@ int exa_predict(exa_engine* e, const uint16_t* vol, int D, int H, int W,
   });
 }
 
+int exa_set_progress_callback(exa_engine* e, exa_progress_fn cb, void* user) {
+  return guarded(e, [&] {
+    e->impl.set_progress(cb, user);
+    return exa::Status::OK();
+  });
+}
+
 int exa_predict_device(exa_engine* e, const uint16_t* vol_dev, int D, int H, int W,
                        const exa_predict_params* p, float* out_dev, void* stream) {
   return guarded(e, [&] {

@@ -834,6 +834,21 @@ Status Engine::slab_run(const uint16_t* slab_dev, int D, int H, int W, const exa
     head.trim = t;
     head.apply_sigmoid = 1;  // inference.py:158
     EXA_TRY(run_network(src, nb, p.patch[0], p.patch[1], p.patch[2], head, s));
+    if (progress_cb_) {
+      progress_done_ += nb;
+      struct Rec {
+        exa_progress_fn cb;
+        void* user;
+        int64_t done, total;
+      };
+      Rec* rec = new Rec{progress_cb_, progress_user_, progress_done_,
+                         std::max(progress_total_, progress_done_)};
+      EXA_CUDA(cudaLaunchHostFunc(s, [](void* q) {
+        Rec* r = static_cast<Rec*>(q);
+        r->cb(r->user, r->done, r->total);
+        delete r;
+      }, rec));
+    }
     if (band_.on) {
       job_ready_ = true;  // the stitch below only reads patches that are complete
       EXA_TRY(stream_band(i0 + nb, n_slab, s));
@@ -1140,6 +1155,8 @@ Status Engine::predict_pipeline(const uint16_t* vol_dev, int D, int H, int W,
                                 cudaStream_t s) {
   Plan plan;
   EXA_TRY(make_plan(D, H, W, p, &plan));
+  progress_done_ = 0;
+  progress_total_ = plan.n_patches;
   const int bins = p.brightness_clip + 1;
   const size_t plane = (size_t)H * W, nvox = plane * D;
   if (!hist_dev_) EXA_CUDA(cudaMalloc(&hist_dev_, sizeof(unsigned long long) * 65536));

@@ -84,6 +84,13 @@ class Engine {
   // kind: 0 none, 1 K1 (conv_umma), 2 K1z (conv_zfold), 3 K1z2 (conv_zfold2, CTA pairs)
   Status profile_layers(double* ms, int64_t* launches, int32_t* kind, int n) const;
 
+  // progress of the current predict call: cb(user, done, total) from a CUDA host function each
+  // time a wave of patches has finished on the device (tqdm bar of predict(verbose=True))
+  void set_progress(exa_progress_fn cb, void* user) {
+    progress_cb_ = cb;
+    progress_user_ = user;
+  }
+
   std::string last_error;
   int64_t launches = 0;
 
@@ -108,6 +115,9 @@ class Engine {
   Status conv(const ConvLayer& L, const Act& in, const Act& out, const HeadParams* head,
               const ConvRegion* region, const Act* pool_out, cudaStream_t s);
 
+  exa_progress_fn progress_cb_ = nullptr;
+  void* progress_user_ = nullptr;
+  int64_t progress_done_ = 0, progress_total_ = 0;
   struct ProfRec {
     int cat;
     int tag;  // conv: layer index 1..17; other categories: -1 (EXA_LAYER_PROF=1 prints per-tag sums)

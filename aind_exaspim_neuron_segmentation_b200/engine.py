@@ -75,6 +75,14 @@ class Engine:
         except Exception:
             pass
 
+    def set_progress(self, fn):
+        """fn(user, patches_done, patches_total) from a CUDA host-function thread whenever a wave
+        of patches has finished on the device; None switches it off."""
+        self._progress = _native.PROGRESS_FN(fn) if fn is not None else None   # keep it alive
+        cb = ctypes.cast(self._progress, ctypes.c_void_p) if fn is not None else ctypes.c_void_p(0)
+        _native.check(self._lib.exa_set_progress_callback(self._h, cb, ctypes.c_void_p(0)), self._h,
+                      "exa_set_progress_callback")
+
     @property
     def launch_count(self):
         return int(self._lib.exa_launch_count(self._h))

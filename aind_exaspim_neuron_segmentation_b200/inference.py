@@ -26,7 +26,7 @@ import torch
 
 from . import _native
 from .engine import Engine, percentiles_from_hist, plan_slab
-from .machine_learning.unet3d import UNet3D
+from .machine_learning.unet3d import UNet3D, engine_for_module
 
 __all__ = ["predict", "predict_sharded", "predict_streamed", "load_model", "count_patches",
            "generate_patch_starts", "affinities_to_segmentation"]
@@ -72,16 +72,7 @@ def _engine_for(model, precision=None):
         return model
     if isinstance(model, torch.nn.Module):
         # e.g. the reference's own UNet3D instance: identical state_dict layout
-        cache = model.__dict__.setdefault("_exa_b200_engines", {})
-        device = next(model.parameters()).device
-        sd = model.state_dict()
-        fp = tuple((k, v.data_ptr(), v._version) for k, v in sd.items())
-        key = (precision or "bf16", str(device))
-        if key not in cache or cache[key][0] != fp:
-            if model.training:
-                raise RuntimeError("model must be in eval mode (inference.py:423)")
-            cache[key] = (fp, Engine(sd, device, precision or "bf16"))
-        return cache[key][1]
+        return engine_for_module(model, precision or "bf16")
     raise TypeError("model must be a torch.nn.Module with the reference UNet3D state_dict")
 
 
@@ -91,7 +82,9 @@ def _as_volume_u16(img, brightness_clip):
 
     The reference computes ``np.minimum(img, brightness_clip)`` in the image's own
     dtype (inference.py:79).  For integer images that is representable in uint16
-    whenever the clipped values are, which is what the kernels consume.
+    whenever the clipped values are, which is what the kernels consume.  Inputs whose clipped
+    values would NOT survive the conversion unchanged raise instead of being altered silently
+    (values above 65535 that the clip does not remove, negative values, floating-point images).
     """
     arr = np.asarray(img)
     if arr.ndim > 5 or arr.ndim < 3:
@@ -106,8 +99,12 @@ def _as_volume_u16(img, brightness_clip):
     if arr.dtype.kind in "ui":
         if arr.dtype.kind == "i" and arr.size and arr.min() < 0:
             raise TypeError("negative intensities are not supported by the uint16 kernels")
-        clip = min(max(int(brightness_clip), 0), 65535)
-        return np.minimum(arr, clip).astype(np.uint16)
+        clip = _check_clip(arr, brightness_clip)
+        if clip > 65535 and arr.size and arr.max() > 65535:
+            raise TypeError(
+                f"{arr.dtype} image with values above 65535 and brightness_clip={brightness_clip}: "
+                "the clipped volume does not fit the uint16 kernels (lower the clip to <= 65535)")
+        return np.minimum(arr, min(clip, 65535)).astype(np.uint16)
     raise TypeError(
         f"unsupported image dtype {arr.dtype}: the B200 path consumes integer (ExaSPIM uint16) "
         "volumes; there is no CPU fallback for floating-point images"
@@ -115,8 +112,14 @@ def _as_volume_u16(img, brightness_clip):
 
 
 def _check_clip(arr, brightness_clip):
+    """brightness_clip as the integer the kernels use; anything np.minimum would treat
+    differently (negative, non-integral: the clipped image would become float) raises."""
     if brightness_clip < 0:
         raise ValueError("brightness_clip must be >= 0")
+    if float(brightness_clip) != int(brightness_clip):
+        raise ValueError(f"brightness_clip={brightness_clip} is not an integer: np.minimum would turn "
+                         "the image into floats, which the uint16 kernels do not reproduce")
+    return int(brightness_clip)
 
 
 # --- the hot path ---------------------------------------------------------------------
@@ -156,17 +159,28 @@ def predict(
         )
     shape5 = (1, 1) + vol.shape
     n_patches = count_patches(shape5, patch_shape, overlap)
-    pbar = None
-    if verbose:
-        from tqdm import tqdm
-
-        pbar = tqdm(total=n_patches, desc="Predict")
     params = _native.make_params(patch_shape, overlap, trim, brightness_clip,
                                  normalization_percentiles, batch=max(int(batch_size), 32))
-    out = engine.predict_host(vol, params, out=out)
-    if pbar is not None:
-        pbar.update(n_patches)
-        pbar.close()
+    if not verbose:
+        out = engine.predict_host(vol, params, out=out)
+        return out if affinity_mode else out[0]
+    from tqdm import tqdm
+
+    # the bar advances as waves of patches FINISH on the device (exa_set_progress_callback), like
+    # the reference's per-batch update (inference.py:118-120)
+    with tqdm(total=n_patches, desc="Predict") as pbar:
+        state = {"done": 0}
+
+        def advance(_user, done, _total):
+            pbar.update(int(done) - state["done"])
+            state["done"] = int(done)
+
+        engine.set_progress(advance)
+        try:
+            out = engine.predict_host(vol, params, out=out)
+        finally:
+            engine.set_progress(None)
+        pbar.update(n_patches - state["done"])
     return out if affinity_mode else out[0]
 
 
@@ -312,6 +326,12 @@ def affinities_to_segmentation(affinities, agglomeration_thresholds=[0.6, 0.8, 0
 
 
 # --- multi-GPU: z-row slabs ---------------------------------------------------------------
+def world_size_of(group=None):
+    import torch.distributed as dist
+
+    return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+
 def split_rows(n_rows, world_size):
     """Contiguous, balanced [begin, end) row ranges, one per rank (earlier ranks get the extras)."""
     base, extra = divmod(n_rows, world_size)
@@ -364,12 +384,15 @@ class _EngineSlabBackend:
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm
 
-        # one buffer per (shape, device, group), kept for the life of the process: symmetric
-        # allocations are expensive to set up and every job of that shape can share it -- the
-        # gathered array a job returns is valid until the next gather of the same shape
+        # ONE buffer per process, re-used by every job of the same (shape, device, group) --
+        # symmetric allocations are expensive to set up -- and replaced (the old one freed) when
+        # a job of another shape comes along, so a stream of ragged block shapes cannot grow GPU
+        # memory without bound.  Consequence, documented on SlabJob.run: the gathered DEVICE array
+        # a job returns is only valid until the next gather (peers store into it remotely).
         pg = group if group is not None else dist.group.WORLD
         key = (tuple(shape), str(self.device), pg.group_name)
         if key not in _SYMMETRIC_OUTPUTS:
+            _SYMMETRIC_OUTPUTS.clear()   # every rank takes this branch for the same job: collective
             full = symm.empty(*shape, dtype=torch.float32, device=self.device)
             hdl = symm.rendezvous(full, pg)
             ptrs = [int(p) for r, p in enumerate(hdl.buffer_ptrs) if r != hdl.rank]
@@ -539,7 +562,11 @@ class SlabJob:
         return full
 
     def run(self, slab, gather=True):
-        """slab: device uint16 planes [in_z0, in_z1).  -> device float32 (C, D|own, H, W)."""
+        """slab: device uint16 planes [in_z0, in_z1).  -> device float32 (C, D|own, H, W).
+
+        The returned tensor is a buffer the job (or, for the fused gather, the process-wide
+        symmetric-memory allocation) re-uses: it is valid until the next ``run`` / gather --
+        copy it (``predict_sharded`` returns a host copy) if it must outlive that."""
         dist, be, p = self.dist, self.backend, self.params
         dev = be.device
         c, (d, h, w) = self.n_channels, self.shape
@@ -554,9 +581,13 @@ class SlabJob:
             be.partial(halo)
         seed = self._exchange_halo(halo)
         if not gather or self.world == 1:
-            own = torch.zeros((c, nz_own, h, w), dtype=torch.float32, device=dev)
+            own = self._own
+            if own is None or tuple(own.shape) != (c, nz_own, h, w) or own.device != dev:
+                own = self._own = torch.empty((c, nz_own, h, w), dtype=torch.float32, device=dev)
             if self.has_rows and nz_own > 0:
-                be.stitch(seed, own)
+                be.stitch(seed, own)   # writes every voxel of the owned planes (shell = 0.0)
+            else:
+                own.zero_()
             return own
         # C3: every rank ends up with the full (C, D, H, W) array.  The owned planes are stitched
         # straight into it and the other ranks' planes arrive in place: the output is channel-
@@ -621,9 +652,16 @@ def predict_sharded(
     float32 ``(C, z1 - z0, H, W)``, e.g. pinned memory; ``SlabJob.own_bounds`` gives the range).
     With a world size of 1 this is the same computation as ``predict``.
     """
+    _check_clip(img, brightness_clip)
     vol = _as_volume_u16(img, brightness_clip)
     if backend is None:
         backend = _EngineSlabBackend(_engine_for(model, precision))
+    if world_size_of(group) > 1 and patch_shape[0] - 2 * trim > 2 * (patch_shape[0] - overlap[0]):
+        raise ValueError(
+            "predict_sharded needs patch - 2*trim <= 2*(patch - overlap) along z: with more overlap a "
+            "plane is covered by three or more z rows and the pairwise partial-sum hand-over between "
+            "neighbouring ranks no longer reproduces the reference's summation order; use predict() "
+            "(single GPU) or a smaller z overlap")
     params = _native.make_params(patch_shape, overlap, trim, brightness_clip,
                                  normalization_percentiles, batch=max(int(batch_size), 32))
     job = SlabJob(vol.shape, params, 3 if affinity_mode else 1, backend, group)

@@ -11,10 +11,38 @@ into the convolutions and runs the CUDA kernels.  On a CPU tensor ``forward``
 raises: there is no fallback path.
 """
 
+import weakref
+
 import torch
 import torch.nn as nn
 
 from ..engine import Engine
+
+# Native engines per module, OUTSIDE the module's __dict__: ctypes handles cannot be pickled or
+# deep-copied, and a copy of a model must not share (or free) the original's device buffers.
+# {module: {(precision, device): (weights fingerprint, Engine)}}
+_ENGINES = weakref.WeakKeyDictionary()
+
+
+def engine_for_module(module, precision, state_dict=None):
+    """The native engine holding ``module``'s current weights (rebuilt when they change).
+
+    Works for any ``nn.Module`` with the reference UNet3D ``state_dict`` layout.  Eval mode is
+    checked on EVERY call: the engine folds eval-mode BatchNorm (inference.py:423)."""
+    if module.training:
+        raise RuntimeError("the native engine implements eval-mode BatchNorm only; "
+                           "call model.eval() first (inference.py:423)")
+    device = next(module.parameters()).device
+    sd = state_dict if state_dict is not None else module.state_dict()
+    fp = tuple((k, v.data_ptr(), v._version) for k, v in sd.items())
+    per_module = _ENGINES.setdefault(module, {})
+    key = (precision, str(device))
+    cached = per_module.get(key)
+    if cached is None or cached[0] != fp:
+        if cached is not None:
+            cached[1].close()
+        per_module[key] = (fp, Engine(sd, device, precision))
+    return per_module[key][1]
 
 _WIDTHS = (32, 64, 128, 256, 512)
 
@@ -89,27 +117,11 @@ class UNet3D(nn.Module):
         self.up3 = Up(c[2], c[1] // 2)
         self.up4 = Up(c[1], c[0])
         self.outc = OutConv(c[0], output_channels)
-        self._engines = {}
-
-    # -- engine cache -----------------------------------------------------------------
-    def _fingerprint(self):
-        return tuple((k, v.data_ptr(), v._version) for k, v in self.state_dict().items())
 
     def engine(self, precision=None):
-        """Native engine holding this module's current weights (rebuilt when they change)."""
-        precision = precision or self.precision
-        device = next(self.parameters()).device
-        key = (precision, str(device))
-        fp = self._fingerprint()
-        cached = self._engines.get(key)
-        if cached is None or cached[0] != fp:
-            if self.training:
-                raise RuntimeError("the native engine implements eval-mode BatchNorm only; "
-                                   "call model.eval() first (inference.py:423)")
-            if cached is not None:
-                cached[1].close()
-            self._engines[key] = (fp, Engine(self.state_dict(), device, precision))
-        return self._engines[key][1]
+        """Native engine holding this module's current weights (rebuilt when they change);
+        raises in training mode."""
+        return engine_for_module(self, precision or self.precision)
 
     def forward(self, x):
         """(B,1,D,H,W) float32 -> logits (B,C,D,H,W) float32, unet3d.py:77-105."""

@@ -9,6 +9,8 @@ histogram -> percentiles -> (gather+normalise, tensor-core stem, 17 tcgen05 conv
 fused head+sigmoid+trim) per wave of patches -> overlap stitch -> (N>1: halo exchange + all-gather).
 N=1 runs BASELINE config 2 (512^3, patch 96^3 -> 512 patches); N GPUs run N x 512^3 voxels
 (1024x512x512, 1024x1024x512, 1024^3 = BASELINE config 3), sharded by z patch-rows: weak scaling.
+`--volume 1024` fixes the volume at 1024^3 for every N instead (the STRONG scaling curve of
+SURVEY.md 8d-3; "scaling": "strong").
 
 `value`   : voxels/s with the rank's uint16 slab already resident in HBM, device-timed (CUDA
             events), max over ranks.
@@ -21,6 +23,11 @@ N=1 runs BASELINE config 2 (512^3, patch 96^3 -> 512 patches); N GPUs run N x 51
             and `per_layer` give the same for every conv launch.
 `cpu_baseline` / `--impl reference`: the CPU oracle port of the reference path (oracle/),
             all host threads, on a bounded sample (4 patches) of the same workload.
+`parity_check`: the bench's own output checked inside the run.  N=1: the corner block of the timed
+            output against the oracle run of `cpu_baseline` (same 4 windows, the whole volume's
+            percentiles).  N>1: a 512x160x160 volume predicted single-rank and sharded (fused
+            peer-store gather AND the NCCL send/recv gather) on every rank -> bit_identical, and its
+            corner against the oracle on rank 0 -> max_abs_vs_oracle.
 """
 
 import argparse
@@ -87,7 +94,12 @@ def n_patches_of(shape):
     return n
 
 
+STRONG_VOLUME = 0   # --volume: edge of the fixed cube for strong scaling (0 = weak scaling)
+
+
 def volume_shape(n_gpus):
+    if STRONG_VOLUME:
+        return (STRONG_VOLUME,) * 3
     shape = [512, 512, 512]
     k, axis = n_gpus, 0
     while k > 1:
@@ -207,8 +219,9 @@ def hbm_kernels(prof, n_patches, voxels, steps, peak_gbs):
         up_bytes += n ** 3 * c * 2 + (n // 2) ** 3 * c * 2
     up_bytes += 84 ** 3 * 32 * 2 + 42 ** 3 * 32 * 2       # up4: the 84^3 box the last convs need
     algo = {
-        # gather: 2 B read + 2 x 2 B (hi, lo) written, re-read by the stem; stem output 64 B per voxel
-        "stem": n_patches * 96 ** 3 * (2 + 4 + 4 + 64),
+        # 2 B of uint16 in + 64 B of bf16 activations out per patch voxel (the bf16
+        # (hi, lo) intermediate between the gather and the tensor-core stem is NOT algorithmic)
+        "stem": n_patches * 96 ** 3 * (2 + 64),
         "upsample": n_patches * up_bytes,
         # stitch: every trimmed patch voxel read once (3 x 4 B), every output voxel written once
         "stitch": n_patches * 3 * 80 ** 3 * 4 + voxels * 12,
@@ -237,16 +250,25 @@ def ncu_traffic():
 CPU_SAMPLE_SHAPE = (96, 160, 160)  # 1 x 2 x 2 patches of the same synthetic volume
 
 
-def cpu_oracle_step(sd, vol):
+# voxels of the corner covered by its own 1 x 2 x 2 windows only (the next windows' kept boxes
+# start at 64 + 8 along z and 128 + 8 along y, x): there the corner run equals the whole-volume run
+CPU_SAMPLE_VALID = (slice(None), slice(0, 72), slice(0, 136), slice(0, 136))
+
+
+def cpu_oracle_step(sd, vol, norm_range=None):
     from oracle.predict_ref import predict_ref
     from oracle.unet_ref import make_forward_fn
 
     t0 = time.perf_counter()
-    out = predict_ref(vol, make_forward_fn(sd), patch_shape=PATCH, overlap=OVERLAP, trim=TRIM)
+    out = predict_ref(vol, make_forward_fn(sd), patch_shape=PATCH, overlap=OVERLAP, trim=TRIM,
+                      norm_range=norm_range)
     return time.perf_counter() - t0, out
 
 
-def cpu_baseline(steps=1, warmup=0):
+def cpu_baseline(steps=1, warmup=0, norm_range=None, shape=None, want_output=False):
+    """The oracle port timed on a 4-patch corner of the workload volume.  With norm_range (the
+    whole volume's percentiles) its output is the reference's result for that corner of the whole
+    volume (CPU_SAMPLE_VALID) and is returned for the parity check."""
     import torch
 
     from oracle.unet_ref import rescaled_state_dict
@@ -254,19 +276,24 @@ def cpu_baseline(steps=1, warmup=0):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sd = rescaled_state_dict(0)
-    vol = synth_planes(volume_shape(1), 0, 96)[:, :160, :160].copy()
+    shape = shape or volume_shape(1)
+    vol = synth_planes(shape, 0, 96)[:, :160, :160].copy()
     for _ in range(warmup):
-        cpu_oracle_step(sd, vol)
-    times = [cpu_oracle_step(sd, vol)[0] for _ in range(max(steps, 1))]
+        cpu_oracle_step(sd, vol, norm_range)
+    times, out = [], None
+    for _ in range(max(steps, 1)):
+        sec, out = cpu_oracle_step(sd, vol, norm_range)
+        times.append(sec)
     sec = float(np.mean(times))
     n_patch = 4
-    vox_per_patch = 512 ** 3 / 512  # stitched output voxels per patch of the 512^3 workload
-    return {"value": n_patch * vox_per_patch / sec, "unit": "voxels/s", "cores": cores,
+    vox_per_patch = 64 ** 3  # stitched output voxels per patch at stride 64 (512^3 / 512 patches)
+    base = {"value": n_patch * vox_per_patch / sec, "unit": "voxels/s", "cores": cores,
             "kind": "port",
             "sample": (f"oracle/ CPU port of reference predict (torch fp32 convs, {cores} threads) on "
                        f"a {CPU_SAMPLE_SHAPE} corner of the same volume = 4 patches, "
                        f"{sec:.2f} s/step; scaled by the workload's 262144 output voxels per patch"),
-            "sec_per_patch": sec / n_patch}, sec
+            "sec_per_patch": sec / n_patch}
+    return (base, sec, out) if want_output else (base, sec)
 
 
 def run_reference(args):
@@ -277,7 +304,8 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "affinity voxels/sec", "value": base["value"],
         "unit": "voxels/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "strong" if STRONG_VOLUME else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.gpus),
         "cpu_baseline": base,
@@ -297,6 +325,75 @@ def workload_config(n):
             "sharding": f"z patch-rows over {n} GPU(s)" if n > 1 else "single GPU",
             "l2": "per-wave activations (~8 GB) and the volume are far larger than the 126 MB L2; "
                   "no flush needed between steps"}
+
+
+def recorded_checksum(n, shape):
+    """Checksums of outputs that tests/test_gpu_predict.py checks against the oracle."""
+    path = os.path.join(ROOT, "tests", "golden", "bench_checksum.json")
+    if not os.path.exists(path) or PATCH != (96, 96, 96):
+        return None
+    with open(path) as f:
+        rec = json.load(f)
+    if tuple(shape) == (512, 512, 512):
+        return rec.get("n1_512")
+    if tuple(shape) == (1024, 1024, 1024):
+        return rec.get("n8_1024")
+    return None
+
+
+PARITY_SHAPE = (512, 160, 160)   # 8 x 2 x 2 windows: every rank of up to 8 owns at least one z row
+
+
+def sharded_parity_check(model, dev, rank, world):
+    """N-GPU == 1-GPU, bit for bit, on every rank and for both gather paths; rank 0 also checks the
+    corner of that volume against the CPU oracle.  Runs before the timed region."""
+    import torch
+    import torch.distributed as dist
+
+    from aind_exaspim_neuron_segmentation_b200 import _native, predict
+    from aind_exaspim_neuron_segmentation_b200.inference import SlabJob, _EngineSlabBackend
+
+    vol = synth_planes(PARITY_SHAPE, 0, PARITY_SHAPE[0], seed=7)
+    single = predict(vol, model, verbose=False, patch_shape=PATCH, overlap=OVERLAP, trim=TRIM)
+    params = _native.make_params(PATCH, OVERLAP, TRIM, 1000, (1, 99.9), batch=32)
+    backend = _EngineSlabBackend(model.engine("bf16"))
+    same, modes = True, []
+    saved = os.environ.get("EXA_GATHER")
+    for gather_env in ("", "nccl"):
+        os.environ["EXA_GATHER"] = gather_env
+        job = SlabJob(PARITY_SHAPE, params, 3, backend)
+        for _ in range(2):   # the second run overwrites the peers' previous result in place
+            full = job.run(job.upload(vol), gather=True)
+            same = same and bool(np.array_equal(full.cpu().numpy(), single))
+        modes.append("fused peer-store" if job._fused else "nccl send/recv")
+        z0, z1 = job.own_bounds()
+        host_own = torch.empty((3, z1 - z0) + PARITY_SHAPE[1:], dtype=torch.float32).pin_memory()
+        job.run_pipelined(job.upload(vol), host_own)
+        same = same and bool(np.array_equal(host_own.numpy(), single[:, z0:z1]))
+        del job
+    if saved is None:
+        os.environ.pop("EXA_GATHER", None)
+    else:
+        os.environ["EXA_GATHER"] = saved
+    flag = torch.tensor([1 if same else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    out = {"bit_identical": bool(flag.item() == 1), "gather_modes": modes, "volume": list(PARITY_SHAPE),
+           "what": "predict() on one GPU vs SlabJob.run(gather) and run_pipelined on every rank"}
+    if rank == 0:
+        from oracle.predict_ref import predict_ref
+        from oracle.unet_ref import make_forward_fn, rescaled_state_dict
+
+        torch.set_num_threads(os.cpu_count() or 1)
+        mn, mx = (float(v) for v in np.percentile(np.minimum(vol, 1000), (1, 99.9)))
+        ref = predict_ref(vol[:96], make_forward_fn(rescaled_state_dict(0)), patch_shape=PATCH,
+                          overlap=OVERLAP, trim=TRIM, norm_range=(mn, mx))[:, :72]
+        out["max_abs_vs_oracle"] = float(np.abs(single[:, :72] - ref).max())
+        out["tolerance"] = 1e-2
+        out["ok"] = bool(out["bit_identical"] and out["max_abs_vs_oracle"] <= 1e-2)
+        print(f"SHARDED_OK world={world} {json.dumps(out)}" if out["ok"] else
+              f"SHARDED_MISMATCH world={world} {json.dumps(out)}", file=sys.stderr, flush=True)
+    dist.barrier()
+    return out
 
 
 # --- B200 arm ------------------------------------------------------------------------------
@@ -353,17 +450,19 @@ def run_b200(args):
         # uploads its slab and gets its owned planes in pinned host memory, D2H row-pipelined
         return job.run_pipelined(host.to(dev, non_blocking=True), host_out)
 
+    # ---- N>1: correctness of the sharded forms, inside the run the driver scales (SCALE_rNN) ----
+    parity = sharded_parity_check(model, dev, rank, world) if world > 1 else None
+
     for _ in range(max(args.warmup, 3)):
         out = step_device()
     del out
     barrier()
 
-    # ---- device-timed region: K steps ----
+    # ---- device-timed region: K steps, no per-launch instrumentation ----
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     launches0 = engine.launch_count
-    engine.profile_begin()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
@@ -372,11 +471,22 @@ def run_b200(args):
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
-    prof = engine.profile_end()
-    layers = engine.profile_layers()
     launches = engine.launch_count - launches0
     clocks = sampler.stop() if rank == 0 else None
+    # ---- per-kernel pass: the same K steps again with every launch bracketed by CUDA events
+    # (roofline, per_layer, kernel_ms_per_step); not part of `value` ----
+    engine.profile_begin()
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pe0.record()
+    for _ in range(args.steps):
+        out = step_device()
+    pe1.record()
+    barrier()
+    prof_ms_step = pe0.elapsed_time(pe1) / args.steps
+    prof = engine.profile_end()
+    layers = engine.profile_layers()
     checksum = float(out[:, ::37, ::41, ::43].double().sum().item())
+    corner = out[CPU_SAMPLE_VALID].cpu().numpy() if n == 1 else None   # for the parity check below
     del out
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -430,7 +540,8 @@ def run_b200(args):
         line = {
             "metric": "affinity voxels/sec", "value": voxels / (ms_step * 1e-3), "unit": "voxels/s",
             "n_gpus": n, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong" if STRONG_VOLUME else "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": workload_config(n),
             "e2e": {"value": voxels / (e2e_ms * 1e-3), "unit": "voxels/s",
@@ -447,9 +558,11 @@ def run_b200(args):
                 "peak_source": peaks["source"], "traffic": ncu_traffic(),
                 "launches": dom_launches, "avg_launch_ms": dom_ms / max(dom_launches, 1),
                 "flops_per_launch": dom_flops / max(dom_launches, 1),
-                "share_of_step": dom_ms / (ms_step * args.steps),
+                "share_of_step": dom_ms / (prof_ms_step * args.steps),
+                "timing": ("per-launch CUDA events in a separate pass of the same K steps "
+                           f"({prof_ms_step:.2f} ms/step instrumented vs {ms_step:.2f} timed)"),
                 "all_conv_kernels": {"achieved": achieved_all, "frac": achieved_all / peaks["bf16_tflops"],
-                                     "launches": conv_launches, "share_of_step": conv_ms / (ms_step * args.steps),
+                                     "launches": conv_launches, "share_of_step": conv_ms / (prof_ms_step * args.steps),
                                      "flops_per_patch": conv_flops_executed(PATCH[0]),
                                      "flops_per_patch_untrimmed": patch_flops_algorithmic(PATCH[0])},
                 "per_layer": per_layer,
@@ -459,8 +572,25 @@ def run_b200(args):
             "clocks": clocks,
             "checksum": checksum,
         }
+        want = recorded_checksum(n, shape)
+        if want is not None:
+            line["checksum_ok"] = bool(abs(checksum - want["value"]) <= want["tol"])
+        if parity is not None:
+            line["parity_check"] = parity
         if n == 1 and not args.no_cpu:
-            line["cpu_baseline"], _ = cpu_baseline(steps=1)
+            # the oracle run that is timed as the CPU baseline doubles as the parity check: same 4
+            # windows, the WHOLE volume's percentiles -> the reference's result for that corner
+            mn, mx = (float(v) for v in np.percentile(np.minimum(host.numpy(), 1000), (1, 99.9)))
+            line["cpu_baseline"], _, ref = cpu_baseline(steps=1, norm_range=(mn, mx), shape=shape,
+                                                        want_output=True)
+            ref = ref[CPU_SAMPLE_VALID]
+            line["parity_check"] = {
+                "max_abs_vs_oracle": float(np.abs(corner - ref).max()), "tolerance": 1e-2,
+                "zero_shell_identical": bool(np.array_equal(corner == 0, ref == 0)),
+                "region": "corner [0:72, 0:136, 0:136] of the timed output (1x2x2 windows) vs the oracle "
+                          "run of cpu_baseline with the whole volume's percentiles"}
+            line["parity_check"]["ok"] = bool(line["parity_check"]["max_abs_vs_oracle"] <= 1e-2 and
+                                              line["parity_check"]["zero_shell_identical"])
         emit(line)
     if world > 1:
         dist.barrier()
@@ -549,6 +679,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference", "library"])
     ap.add_argument("--batch", type=int, default=32, help="patches per wave")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--volume", type=int, default=0, choices=[0, 512, 1024],
+                    help="fix the volume at N^3 for every --gpus (strong scaling); 0 = N x 512^3 (weak)")
     ap.add_argument("--patch", type=int, default=96, choices=[96, 128],
                     help="patch edge: 96 = the headline workload; 128 = BASELINE config 4 (not a bench line)")
     args = ap.parse_args()
@@ -558,8 +690,9 @@ def main():
                f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1", "--master-port",
                "29531", os.path.abspath(__file__)] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
-    global PATCH
+    global PATCH, STRONG_VOLUME
     PATCH = (args.patch,) * 3
+    STRONG_VOLUME = args.volume
     capture_stdout()
     if args.impl == "reference":
         run_reference(args)

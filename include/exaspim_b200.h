@@ -81,6 +81,14 @@ int exa_forward(exa_engine* e, const float* x, float* logits, int batch, const i
 int exa_predict(exa_engine* e, const uint16_t* vol, int D, int H, int W,
                 const exa_predict_params* p, float* out);
 
+/* Progress reporting for the tqdm bar of predict(verbose=True) (inference.py:94-95,118-120):
+ * cb(user, patches_done, patches_total) is called from a CUDA host-function thread each time a
+ * wave of patches has actually FINISHED on the device (cudaLaunchHostFunc on the engine's
+ * stream), while exa_predict is still running.  cb must not call into this library or CUDA.
+ * NULL switches it off (default: no host functions are enqueued at all). */
+typedef void (*exa_progress_fn)(void* user, int64_t patches_done, int64_t patches_total);
+int exa_set_progress_callback(exa_engine* e, exa_progress_fn cb, void* user);
+
 /* Same with device-resident buffers (the bench's device-timed region). Asynchronous on
  * `stream` except for one small D2H of the 1001-bin histogram. */
 int exa_predict_device(exa_engine* e, const uint16_t* vol_dev, int D, int H, int W,

@@ -85,18 +85,34 @@ def predict_ref(
     overlap=(32, 32, 32),
     trim=8,
     apply_sigmoid=True,
+    norm_range=None,
+    only_starts=None,
 ):
     """Whole driver: REF/inference.py:29-126 for a 3-D ``vol``.
 
     ``forward_fn`` maps float32 (B, 1, P, P, P) -> float32 logits
     (B, C, P, P, P).  Returns float32 (C, D, H, W).
+
+    Two test-only extensions for checking sub-blocks of volumes the CPU cannot finish:
+    ``norm_range=(mn, mx)`` replaces the percentiles of ``vol`` (pass those of the WHOLE volume
+    when ``vol`` is a corner of it), and ``only_starts`` restricts the patch loop to the given
+    window starts (a voxel's result is then the reference's wherever every window covering it is
+    in the list; elsewhere it is a partial sum divided by a partial count).
     """
     vol = np.asarray(vol)
     while vol.ndim > 3:
         assert vol.shape[0] == 1
         vol = vol[0]
-    norm, _, _ = clip_and_normalize(vol, brightness_clip, normalization_percentiles)
+    if norm_range is None:
+        norm, _, _ = clip_and_normalize(vol, brightness_clip, normalization_percentiles)
+    else:
+        mn, mx = norm_range   # REF/utils/img_util.py:527-531 with the given scalars
+        norm = np.clip((np.minimum(vol, brightness_clip) - mn) / (mx - mn + 1e-8), 0, 1)
     starts = patch_starts(norm.shape, patch_shape, overlap)
+    if only_starts is not None:
+        wanted = {tuple(int(v) for v in s) for s in only_starts}
+        assert wanted <= set(starts), "only_starts must be window starts of this volume"
+        starts = [s for s in starts if s in wanted]
     acc = np.zeros((n_channels,) + norm.shape, dtype=np.float32)
     wgt = np.zeros(norm.shape, dtype=np.float16)
     for i in range(0, len(starts), batch_size):

@@ -56,6 +56,13 @@ CASES = {
     "small_p48_trim0ish": ((64, 80, 48), 5, ("rescaled", 3),
                            dict(patch_shape=(48, 32, 48), overlap=(16, 8, 24), trim=2,
                                 brightness_clip=700, normalization_percentiles=(5, 99))),
+    # round 2: axes shorter than half a patch -> np.pad(mode="reflect") wraps more than once
+    # (z: 10 voxels padded to 32; second y window: 16 voxels padded to 32)
+    "multireflect_p32": ((10, 40, 21), 6, ("rescaled", 4),
+                         dict(patch_shape=(32, 32, 32), overlap=(8, 8, 8), trim=4)),
+    # BASELINE config 4: one full 128^3 patch through the reference
+    "p128_single": ((128, 128, 128), 7, ("rescaled", 5),
+                    dict(patch_shape=(128, 128, 128), overlap=(32, 32, 32), trim=8)),
 }
 
 
@@ -80,10 +87,23 @@ def reduce_output(out):
 
 
 def main():
+    """``--only name[,name]``: (re)generate just those predict cases and merge them into the
+    existing golden_meta.json (np.savez stamps the archive with the wall clock, so untouched
+    fixtures are left alone to keep the history quiet)."""
+    only = None
+    if "--only" in sys.argv:
+        only = set(sys.argv[sys.argv.index("--only") + 1].split(","))
     inference, UNet3D = import_reference()
     torch.set_num_threads(os.cpu_count())
     meta = {}
+    meta_path = os.path.join(HERE, "golden_meta.json")
+    if only is not None:
+        with open(meta_path) as f:
+            old = json.load(f)
+        meta = old["cases"]
     for name, (shape, vseed, (wkind, wseed), kwargs) in CASES.items():
+        if only is not None and name not in only:
+            continue
         vol = make_volume(shape, vseed)
         if wkind == "default":
             torch.manual_seed(wseed)
@@ -99,6 +119,12 @@ def main():
         meta[name] = dict(shape=shape, vol_seed=vseed, weights=[wkind, wseed], kwargs=kwargs,
                           min=float(out.min()), max=float(out.max()))
         print(name, out.shape, float(out.min()), float(out.max()), red["bbox"].tolist())
+    if only is not None:
+        old["cases"] = meta
+        with open(meta_path, "w") as f:
+            json.dump(old, f, indent=1)
+        print("updated golden_meta.json:", sorted(only))
+        return
 
     # tiling helpers (inference.py:340-397)
     tiling = []

@@ -39,6 +39,12 @@ def test_config4_patch128_bf16_vs_fp32_validation_mode():
     print("P=128 bf16 vs fp32 validation mode: max abs", err)
     assert err <= BF16_TOL, err
     assert np.array_equal(out16 == 0, out32 == 0)
+    # the same full 128^3 patch through the CPU oracle (one patch, a few seconds): every voxel
+    ref128 = predict_ref(vol, make_forward_fn(state_dict_for("rescaled", 30)), **kw)
+    e16, e32 = float(np.abs(out16 - ref128).max()), float(np.abs(out32 - ref128).max())
+    print("P=128 vs CPU oracle: bf16", e16, "fp32 mode", e32)
+    assert e16 <= BF16_TOL and e32 <= FP32_TOL, (e16, e32)
+    assert np.array_equal(out16 == 0, ref128 == 0)
     # the fp32 mode against the CPU oracle on the same weights with a (128, 32, 32) patch
     small = lightsheet_volume((128, 32, 32), 32)
     kw2 = dict(patch_shape=(128, 32, 32), overlap=(32, 8, 8), trim=4)

@@ -165,3 +165,56 @@ def test_state_dict_layout_matches_reference(golden_meta):
             {k: v for k, v in sd.items() if k != "outc.conv.bias"}, strict=True)
     assert torch.equal(m.state_dict()["inc.double_conv.0.weight"],
                        rescaled_state_dict(0)["inc.double_conv.0.weight"])
+
+
+def test_input_checks_raise_instead_of_altering_the_image():
+    """Inputs the reference would treat differently from the uint16 kernels raise."""
+    vol = make_volume((8, 8, 8), 1)
+    assert inference._as_volume_u16(vol, 1000) is not None
+    assert inference._as_volume_u16(vol.astype(np.int64), 1000).dtype == np.uint16
+    assert inference._check_clip(vol, 1000.0) == 1000
+    with pytest.raises(ValueError):
+        inference._check_clip(vol, 1000.5)          # np.minimum would make the image float
+    with pytest.raises(ValueError):
+        inference._check_clip(vol, -1)
+    big = vol.astype(np.int64) + 70000
+    with pytest.raises(TypeError):
+        inference._as_volume_u16(big, 100000)       # values > 65535 survive the clip
+    assert inference._as_volume_u16(big, 60000).max() == 60000   # removed by the clip: exact
+    with pytest.raises(TypeError):
+        inference._as_volume_u16(-vol.astype(np.int32) - 1, 1000)
+    with pytest.raises(TypeError):
+        inference._as_volume_u16(vol.astype(np.float64), 1000)
+
+
+def test_model_copies_and_training_mode():
+    """Engines live outside the module: models deep-copy / pickle, and a model put back into
+    training mode never silently runs the folded eval-mode engine."""
+    import copy
+    import io
+
+    import torch
+
+    from aind_exaspim_neuron_segmentation_b200 import UNet3D
+
+    m = UNet3D(3).eval()
+    m2 = copy.deepcopy(m)
+    assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), m2.state_dict().values()))
+    buf = io.BytesIO()
+    torch.save(m, buf)
+    assert not hasattr(m, "_engines")
+    m.train()
+    with pytest.raises(RuntimeError, match="eval"):
+        m.engine()
+    with pytest.raises(RuntimeError, match="eval"):
+        inference._engine_for(m)
+
+
+def test_sharded_rejects_triple_z_overlap(monkeypatch):
+    """patch - 2*trim > 2*stride along z: a plane is covered by three z rows; predict() handles
+    it (one slab), predict_sharded on more than one rank raises a clear error."""
+    vol = make_volume((64, 32, 32), 2)
+    monkeypatch.setattr(inference, "world_size_of", lambda group=None: 2)
+    with pytest.raises(ValueError, match="three or more z rows"):
+        inference.predict_sharded(vol, None, patch_shape=(32, 32, 32), overlap=(24, 8, 8), trim=0,
+                                  backend=object())

@@ -19,7 +19,8 @@ def _run_oracle(meta):
     return pr.predict_ref(vol, make_forward_fn(sd), **kw)
 
 
-@pytest.mark.parametrize("name", ["small_p32", "small_p48_trim0ish", "c1_rescaled_96"])
+@pytest.mark.parametrize("name", ["small_p32", "small_p48_trim0ish", "c1_rescaled_96", "multireflect_p32",
+                                  "p128_single"])
 def test_oracle_matches_reference_golden(golden_meta, name):
     out = _run_oracle(golden_meta["cases"][name])
     # same fp32 arithmetic (torch CPU conv) -> only thread-count dependent reduction order differs
@@ -58,3 +59,22 @@ def test_reflect_padding_excludes_edge():
     patch = pr.extract_patch(vol, (0, 0, 0), (2, 2, 96))
     assert patch.shape == (2, 2, 96)
     assert patch[0, 0, 64:].tolist() == [float(v) for v in range(62, 30, -1)]
+
+
+def test_sub_block_extensions_reproduce_the_full_run():
+    """norm_range / only_starts (used to check 512^3 sub-blocks on the GPU box): a corner block
+    run with the whole volume's percentiles equals the full run wherever all covering windows
+    are among the selected ones."""
+    from oracle.unet_ref import rescaled_state_dict
+
+    sd = rescaled_state_dict(2)
+    vol = make_volume((72, 56, 40), 4)
+    kw = dict(patch_shape=(32, 32, 32), overlap=(8, 8, 8), trim=4)
+    full = pr.predict_ref(vol, make_forward_fn(sd), **kw)
+    _, mn, mx = pr.clip_and_normalize(vol, 1000, (1, 99.9))
+    # corner that holds the windows starting at z in {0, 24}, y in {0, 24}, x = 0 completely
+    corner = vol[:56, :, :32]
+    sel = [(z, y, 0) for z in (0, 24) for y in (0, 24)]
+    part = pr.predict_ref(corner, make_forward_fn(sd), norm_range=(mn, mx), only_starts=sel, **kw)
+    # voxels covered by the selected windows only: z < 48 + 4 (next z window starts at 48), x < 24 + 4
+    assert np.array_equal(part[:, :52, :, :28], full[:, :52, :, :28])
