@@ -149,9 +149,9 @@ _SIGNATURES = {
         ctypes.POINTER(ctypes.c_double), ctypes.c_int, ctypes.c_double, ctypes.c_double,
         ctypes.c_int64, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64),
         ctypes.POINTER(ctypes.c_int64)]),
-    "exa_region_agglomerate": (ctypes.c_int, [ctypes.c_uint32, ctypes.c_int64, ctypes.c_void_p,
-                                              ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double,
-                                              ctypes.c_void_p]),
+    "exa_region_agglomerate": (ctypes.c_int, [ctypes.c_int, ctypes.c_uint32, ctypes.c_int64,
+                                              ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                              ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p]),
     "exa_affinities_to_segmentation_device": (ctypes.c_int, [
         ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
         ctypes.POINTER(ctypes.c_double), ctypes.c_int, ctypes.c_double, ctypes.c_double,

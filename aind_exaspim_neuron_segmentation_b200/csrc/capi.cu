@@ -228,11 +228,12 @@ int exa_affinities_to_segmentation(int device, const float* aff_host, int D, int
   });
 }
 
-int exa_region_agglomerate(uint32_t n_fragments, int64_t n_edges, const uint64_t* pair_keys,
-                           const double* sums, const int32_t* counts, double threshold,
-                           uint32_t* root_out) {
+int exa_region_agglomerate(int device, uint32_t n_fragments, int64_t n_edges, const uint32_t* eu,
+                           const uint32_t* ev, const uint64_t* qsum, const uint32_t* count,
+                           double threshold, uint32_t* root_out) {
   return guarded_static([&] {
-    return exa::region_agglomerate(n_fragments, n_edges, pair_keys, sums, counts, threshold, root_out);
+    return exa::region_agglomerate(device, n_fragments, n_edges, eu, ev, qsum, count, threshold,
+                                   root_out);
   });
 }
 

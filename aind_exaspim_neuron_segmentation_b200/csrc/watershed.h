@@ -8,8 +8,8 @@
 
 namespace exa {
 
-// aff: device float32 (3, D, H, W); seg: device uint64 (D, H, W).  Synchronises `s` (the merge
-// queue over the region graph runs on the host).
+// aff: device float32 (3, D, H, W); seg: device uint64 (D, H, W).  Synchronises `s` (round counters
+// come back to the host, and the tail of the merge queue runs there).
 Status affinities_to_segmentation_device(const float* aff, int D, int H, int W,
                                          const double* thresholds, int n_thresholds, double aff_low,
                                          double aff_high, int64_t min_segment_size, uint64_t* seg,
@@ -20,10 +20,14 @@ Status affinities_to_segmentation_host(int device, const float* aff, int D, int 
                                        double aff_high, int64_t min_segment_size, uint64_t* seg,
                                        int64_t* n_fragments, int64_t* n_segments);
 
-// the host merge queue alone (no GPU): edges (a << 32 | b, a < b) with summed affinity and face
-// count -> root fragment of every fragment 0..n_fragments (root_out has n_fragments + 1 entries)
-Status region_agglomerate(uint32_t n_fragments, int64_t n_edges, const uint64_t* pair_keys,
-                          const double* sums, const int32_t* counts, double threshold,
-                          uint32_t* root_out);
+// The agglomeration step alone on a region graph given as host arrays: edges eu[i] < ev[i] (fragment
+// ids 1..n_fragments, every pair at most once, sorted by (eu, ev): the index is the tie-break rank),
+// qsum[i] = sum of the affinities between the two in 32.32 fixed point, count[i] = faces.
+// device < 0: the exact host queue only (no GPU needed); otherwise parallel rounds on that GPU and
+// the host queue for the rest, as affinities_to_segmentation_device does.  root_out[0..n_fragments]:
+// the smallest fragment id of the region every fragment ends up in.
+Status region_agglomerate(int device, uint32_t n_fragments, int64_t n_edges, const uint32_t* eu,
+                          const uint32_t* ev, const uint64_t* qsum, const uint32_t* count,
+                          double threshold, uint32_t* root_out);
 
 }  // namespace exa

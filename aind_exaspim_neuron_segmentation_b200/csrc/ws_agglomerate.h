@@ -1,36 +1,61 @@
-// Host merge queue of K7 (affinities -> segmentation): hierarchical agglomeration of the region
+// Exact merge queue of K7 (affinities -> segmentation): hierarchical agglomeration of a region
 // graph, reference inference.py:224-229 -> waterz.agglomerate with OneMinus<MeanAffinity> scoring.
-// Plain C++ (no CUDA): also exported as exa_region_agglomerate for CPU tests.
+// Plain C++ (no CUDA).  It finishes what the parallel GPU rounds of watershed.cu leave over (the
+// hub chains: one large region swallowing its neighbours one by one) and is exported on its own as
+// exa_region_agglomerate for CPU tests.
+//
+// Edge statistics are exact: q = sum of the affinities in 32.32 fixed point, c = number of faces,
+// key = smallest rank of the original region-graph edges the edge is made of.  The score
+// 1 - q / (c * 2^32) is never formed:  edge 1 comes before edge 2 iff q1 * c2 > q2 * c1 (128-bit
+// products), ties by key; "score < threshold" is q > c * T, T = llrint((1 - threshold) * 2^32).
+// Mean-affinity linkage is reducible, so with this strict total order the partition reached at
+// the threshold does not depend on the order in which independent merges are carried out.
 #pragma once
 
 #include <stdint.h>
 
 #include <algorithm>
-#include <tuple>
+#include <cmath>
+#include <utility>
 #include <vector>
 
 namespace exa {
 namespace ws {
 
-// Hierarchical agglomeration with OneMinus<MeanAffinity> scoring (waterz): merge the pair with the
-// smallest score while it is below the threshold; statistics of parallel edges add up.  Entries of
-// the heap are (score, a, b, count) compared lexicographically; an entry is stale when one of its
-// ends was merged away or the edge's count changed since it was pushed.
-struct Stat {
-  double s;
-  long long c;
+struct Stat {  // 16 bytes: the face count of a volume below 2^32 voxels fits 32 bits
+  uint64_t q;
+  uint32_t c;
+  uint32_t key;
 };
-using Entry = std::tuple<double, uint32_t, uint32_t, long long>;
 
-// neighbour table of one region: open addressing on fragment ids (>= 1), Fibonacci hashing
-// (the HIGH bits of k * 2^32/phi: neighbouring fragments have nearby ids), linear probing, at most
-// half full including tombstones
+inline bool stat_before(uint64_t q1, uint64_t c1, uint32_t k1, uint64_t q2, uint64_t c2,
+                        uint32_t k2) {
+  const unsigned __int128 l = (unsigned __int128)q1 * c2, r = (unsigned __int128)q2 * c1;
+  if (l != r) return l > r;
+  return k1 < k2;
+}
+
+// T of the header comment, clamped to what the comparison needs
+inline int64_t fixed_threshold(double threshold) {
+  const double t = (1.0 - threshold) * 4294967296.0;
+  if (!(t > -1.0)) return -1;                          // every edge is below the threshold
+  if (t > 4294967296.0) return (int64_t)1 << 33;       // no edge is (q <= c * 2^32)
+  return (int64_t)llrint(t);
+}
+inline bool below_threshold(uint64_t q, uint64_t c, int64_t T) {
+  if (T < 0) return true;
+  return (unsigned __int128)q > (unsigned __int128)c * (unsigned __int128)(uint64_t)T;
+}
+
+// neighbour table of one region: open addressing on region ids (>= 1), Fibonacci hashing (the
+// HIGH bits of k * 2^32/phi: neighbouring fragments have nearby ids), linear probing, at most
+// three quarters full including tombstones; 24-byte slots (a region with 9 neighbours: 384 bytes)
 class NbrMap {
  public:
   uint32_t size() const { return live_; }
   void reserve(uint32_t n) {
     uint32_t lg = 2;
-    while ((1u << lg) < 2 * (n + 1)) ++lg;
+    while (3ull * (1u << lg) < 4ull * (n + 1)) ++lg;
     if ((1u << lg) > slot_.size()) rehash(lg);
   }
   Stat* find(uint32_t k) {
@@ -41,14 +66,17 @@ class NbrMap {
       if (slot_[i].key == kEmpty) return nullptr;
     }
   }
+  void prefetch(uint32_t k) const {
+    if (!slot_.empty()) __builtin_prefetch(&slot_[index(k)]);
+  }
   void put(uint32_t k, const Stat& v) {
     if (Stat* p = find(k)) {
       *p = v;
       return;
     }
-    if (2 * ((uint64_t)used_ + 1) > slot_.size()) {
+    if (4 * ((uint64_t)used_ + 1) > 3 * (uint64_t)slot_.size()) {
       uint32_t lg = 2;
-      while ((1u << lg) < 4 * (live_ + 1)) ++lg;  // a quarter full after the clean-up
+      while ((1ull << lg) < 2ull * (live_ + 1)) ++lg;  // at most half full after the clean-up
       rehash(lg);
     }
     const uint32_t mask = (uint32_t)slot_.size() - 1;
@@ -92,7 +120,7 @@ class NbrMap {
   static constexpr uint32_t kEmpty = 0, kTomb = 0xffffffffu;
   uint32_t index(uint32_t k) const { return (k * 2654435769u) >> shift_; }
   void rehash(uint32_t lg) {
-    std::vector<Slot> old(1u << lg, Slot{Stat{0.0, 0}, kEmpty});
+    std::vector<Slot> old((size_t)1 << lg, Slot{Stat{0, 0, 0}, kEmpty});
     old.swap(slot_);
     shift_ = 32 - lg;
     live_ = used_ = 0;
@@ -110,120 +138,141 @@ class NbrMap {
   uint32_t live_ = 0, used_ = 0, shift_ = 30;
 };
 
-// Monotone bucket queue over Entry: scores only grow along the merge sequence (a merged edge's
-// mean affinity lies between those of its two parts, which were both >= the current minimum), so
-// entries are binned by score and only the small heap of the current bin is ever touched -- the
-// pop order is exactly that of one global min-heap.  Entries at or above the threshold are never
-// popped before the loop ends and are not stored at all.
+struct Entry {  // one queue entry: an edge as it was when pushed (stale once its count changed)
+                // a, b: the regions it joined then; they may have been merged into others since
+  uint64_t q;
+  uint32_t c, key, a, b;
+};
+struct EntryAfter {  // heap order: the top is the entry that comes first
+  bool operator()(const Entry& x, const Entry& y) const {
+    return stat_before(y.q, y.c, y.key, x.q, x.c, x.key);
+  }
+};
+
+// Monotone bucket queue: scores only grow along the merge sequence (a merged edge's mean affinity
+// lies between those of its parts, which were both not before the current minimum), so entries are
+// binned by floor(q / c) -- integer division, hence exactly monotone in the edge order -- and only
+// the small heap of the current bin is ever touched: the pop order is that of one global heap.
+// Entries at or above the threshold are never popped before the loop ends and are not stored.
 class BucketQueue {
  public:
-  BucketQueue(double threshold, size_t n_hint) : thr_(threshold) {
-    size_t nb = 64;
-    while (nb < (1u << 16) && nb * 8 < n_hint) nb <<= 1;
-    bin_.resize(nb);
-    scale_ = threshold > 0 ? (double)nb / threshold : 0.0;
+  explicit BucketQueue(int64_t T) : T_(T), bin_((size_t)1 << kBits) {}
+  static size_t bin_of(uint64_t q, uint64_t c) {
+    const uint64_t m = std::min<uint64_t>(q / c, 4294967295ull);  // mean affinity, 0.32 fixed point
+    return (size_t)((4294967295ull - m) >> (32 - kBits));
   }
-  // the initial edges at once: bins sized exactly, then heapified (no per-entry reallocation)
   void bulk_load(const std::vector<Entry>& all) {
     std::vector<uint32_t> n(bin_.size(), 0);
     for (const Entry& e : all)
-      if (std::get<0>(e) < thr_) ++n[bin_of(std::get<0>(e))];
-    for (size_t i = 0; i < bin_.size(); ++i) bin_[i].reserve(n[i] + n[i] / 2);
+      if (below_threshold(e.q, e.c, T_)) ++n[bin_of(e.q, e.c)];
+    for (size_t i = 0; i < bin_.size(); ++i)
+      if (n[i]) bin_[i].reserve(n[i] + n[i] / 2);
     for (const Entry& e : all)
-      if (std::get<0>(e) < thr_) bin_[bin_of(std::get<0>(e))].push_back(e);
-    for (std::vector<Entry>& h : bin_) std::make_heap(h.begin(), h.end(), std::greater<Entry>());
+      if (below_threshold(e.q, e.c, T_)) bin_[bin_of(e.q, e.c)].push_back(e);
+    for (std::vector<Entry>& h : bin_)
+      if (!h.empty()) std::make_heap(h.begin(), h.end(), EntryAfter());
     cur_ = 0;
   }
   void push(const Entry& e) {
-    const double sc = std::get<0>(e);
-    if (!(sc < thr_)) return;
-    const size_t i = bin_of(sc);
-    if (i < cur_) cur_ = i;  // rounding put a merged score one ulp under the minimum
+    if (!below_threshold(e.q, e.c, T_)) return;
+    const size_t i = bin_of(e.q, e.c);
+    if (i < cur_) cur_ = i;  // cannot happen for a reducible linkage; harmless
     bin_[i].push_back(e);
-    std::push_heap(bin_[i].begin(), bin_[i].end(), std::greater<Entry>());
+    std::push_heap(bin_[i].begin(), bin_[i].end(), EntryAfter());
   }
   bool pop(Entry* e) {
     while (cur_ < bin_.size() && bin_[cur_].empty()) ++cur_;
     if (cur_ == bin_.size()) return false;
     std::vector<Entry>& h = bin_[cur_];
-    std::pop_heap(h.begin(), h.end(), std::greater<Entry>());
+    std::pop_heap(h.begin(), h.end(), EntryAfter());
     *e = h.back();
     h.pop_back();
     return true;
   }
 
  private:
-  size_t bin_of(double sc) const {
-    return sc <= 0 ? 0 : std::min((size_t)(sc * scale_), bin_.size() - 1);
-  }
-  double thr_, scale_;
+  static constexpr int kBits = 14;
+  int64_t T_;
   size_t cur_ = 0;
   std::vector<std::vector<Entry>> bin_;
 };
 
-std::vector<uint32_t> agglomerate(uint32_t n_frag, const std::vector<unsigned long long>& keys,
-                                  const std::vector<double>& sums, const std::vector<int>& counts,
-                                  double threshold) {
-  std::vector<uint32_t> parent(n_frag + 1);
-  for (uint32_t i = 0; i <= n_frag; ++i) parent[i] = i;
-  std::vector<NbrMap> nbr(n_frag + 1);
+// Edges (a[i], b[i]) between regions 1..n_nodes (a != b, every pair at most once) with statistics
+// (q, c, key).  parent[1..n_nodes] must be the identity on entry; on return it is a forest (paths
+// partly compressed) whose roots are the regions left at the threshold.  Returns the number of merges.
+inline int64_t agglomerate(uint32_t n_nodes, size_t n_edges, const uint32_t* ea, const uint32_t* eb,
+                           const uint64_t* eq, const uint32_t* ec, const uint32_t* ekey,
+                           int64_t T, uint32_t* parent) {
+  std::vector<NbrMap> nbr((size_t)n_nodes + 1);
   {
-    std::vector<uint32_t> deg(n_frag + 1, 0);
-    for (unsigned long long k : keys) {
-      ++deg[(uint32_t)(k >> 32)];
-      ++deg[(uint32_t)(k & 0xffffffffu)];
+    std::vector<uint32_t> deg((size_t)n_nodes + 1, 0);
+    for (size_t i = 0; i < n_edges; ++i) {
+      ++deg[ea[i]];
+      ++deg[eb[i]];
     }
-    for (uint32_t i = 1; i <= n_frag; ++i)
+    for (uint32_t i = 1; i <= n_nodes; ++i)
       if (deg[i]) nbr[i].reserve(deg[i]);
   }
-  BucketQueue heap(threshold, keys.size());
+  BucketQueue heap(T);
   {
     std::vector<Entry> init;
-    init.reserve(keys.size());
-    for (size_t i = 0; i < keys.size(); ++i) {
-      const uint32_t a = (uint32_t)(keys[i] >> 32), b = (uint32_t)(keys[i] & 0xffffffffu);
-      const Stat st{sums[i], (long long)counts[i]};
-      nbr[a].put(b, st);
-      nbr[b].put(a, st);
-      init.emplace_back(1.0 - st.s / (double)st.c, a, b, st.c);
+    init.reserve(n_edges);
+    for (size_t i = 0; i < n_edges; ++i) {
+      const Stat st{eq[i], ec[i], ekey[i]};
+      nbr[ea[i]].put(eb[i], st);
+      nbr[eb[i]].put(ea[i], st);
+      init.push_back(Entry{st.q, st.c, st.key, ea[i], eb[i]});
     }
     heap.bulk_load(init);
   }
+  int64_t merges = 0;
   std::vector<std::pair<uint32_t, Stat>> moved;
+  // entries name the regions their edge joined when it was pushed; an edge that merely moves to
+  // the surviving region keeps its entry (resolved through the forest), so only combined edges
+  // are pushed again
+  auto find = [&](uint32_t x) {
+    while (parent[x] != x) {
+      parent[x] = parent[parent[x]];
+      x = parent[x];
+    }
+    return x;
+  };
   Entry e;
   while (heap.pop(&e)) {
-    uint32_t a = std::get<1>(e), b = std::get<2>(e);
-    if (parent[a] != a || parent[b] != b) continue;
+    uint32_t a = find(e.a), b = find(e.b);
+    if (a == b) continue;
     const Stat* cur_ab = nbr[a].find(b);
-    if (cur_ab == nullptr || cur_ab->c != std::get<3>(e)) continue;
-    if (nbr[a].size() < nbr[b].size()) std::swap(a, b);  // the node with fewer neighbours goes away
+    if (cur_ab == nullptr || cur_ab->c != e.c) continue;  // counts only grow: c identifies the state
+    if (nbr[a].size() < nbr[b].size()) std::swap(a, b);   // the region with fewer neighbours goes
     parent[b] = a;
+    ++merges;
     nbr[a].erase(b);
     moved.clear();
     nbr[b].for_each([&](uint32_t nb, const Stat& st) {
-      if (nb != a) moved.emplace_back(nb, st);
+      if (nb != a) {
+        moved.emplace_back(nb, st);
+        nbr[nb].prefetch(b);
+        nbr[a].prefetch(nb);
+      }
     });
     nbr[b].clear();
     for (const auto& kv : moved) {
       const uint32_t nb = kv.first;
       nbr[nb].erase(b);
       Stat cur = kv.second;
-      if (const Stat* f = nbr[a].find(nb)) {
-        cur.s = f->s + kv.second.s;
-        cur.c = f->c + kv.second.c;
+      const Stat* f = nbr[a].find(nb);
+      const bool combined = f != nullptr;
+      if (combined) {
+        cur.q += f->q;
+        cur.c += f->c;
+        cur.key = std::min(cur.key, f->key);
       }
       nbr[a].put(nb, cur);
       nbr[nb].put(a, cur);
-      heap.push(Entry(1.0 - cur.s / (double)cur.c, std::min(a, nb), std::max(a, nb), cur.c));
+      if (combined) heap.push(Entry{cur.q, cur.c, cur.key, a, nb});
     }
   }
-  std::vector<uint32_t> root(n_frag + 1);
-  for (uint32_t i = 0; i <= n_frag; ++i) {
-    uint32_t x = i;
-    while (parent[x] != x) x = parent[x];
-    root[i] = x;
-  }
-  return root;
+  return merges;
 }
 
 }  // namespace ws

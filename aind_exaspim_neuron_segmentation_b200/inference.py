@@ -286,9 +286,15 @@ def affinities_to_segmentation(affinities, agglomeration_thresholds=[0.6, 0.8, 0
 
     Same signature and defaults (``waterz.agglomerate`` with ``aff_threshold_low=0.1``,
     ``aff_threshold_high=0.9999``, the segmentation of the LAST threshold, then
-    ``remove_small_segments``).  Watershed fragments, the region graph and the relabelling run on
-    the GPU (``csrc/watershed.cu``); the merge queue over the region graph runs on the host.
-    numpy in -> new ``uint64 (D, H, W)`` array out, as waterz returns; a CUDA tensor in -> an
+    ``remove_small_segments``) and waterz's reading of the array: ``affinities[c][z,y,x]`` is the
+    edge between voxel (z,y,x) and its previous neighbour along axis c.  Watershed fragments (with
+    the breadth-first plateau division), the region graph, the agglomeration rounds and the
+    relabelling run on the GPU (``csrc/watershed.cu``); only the tail of the merge queue runs on
+    the host.  waterz itself is not available offline, so the behaviour is checked against a
+    restatement of its published algorithm (``oracle/ws_ref.cpp``; parity unpinned): edge
+    statistics are summed exactly in fixed point where waterz sums float32 values, and ties
+    between equal scores are broken by the rank of the region-graph edge.
+    numpy in -> new ``uint64 (D, H, W)`` array out, the dtype waterz returns; a CUDA tensor in -> an
     ``int64`` CUDA tensor out (no host round trip, e.g. straight from ``predict_sharded``).
     """
     import ctypes

@@ -162,8 +162,10 @@ int exa_set_peer_outputs(exa_engine* e, float* local_base, int64_t elems, float*
  * hierarchical merging by 1 - mean affinity up to the last threshold -- followed by
  * remove_small_segments (img_util.py:536-559: segments with more than min_segment_size voxels
  * are kept and renumbered from 1 in order of first appearance).  aff: float32 (3, D, H, W),
- * aff[c][z,y,x] = edge to the next voxel along axis c; seg: uint64 (D, H, W).  Voxel-sized steps
- * run on the GPU, the merge queue on the host.  n_fragments / n_segments may be NULL. */
+ * aff[c][z,y,x] = edge between voxel (z,y,x) and its PREVIOUS neighbour along axis c (waterz's
+ * reading of the array); seg: uint64 (D, H, W).  Fragments (with waterz's breadth-first plateau
+ * division), the region graph, the parallel agglomeration rounds and the relabelling run on the
+ * GPU; the tail of the merge queue runs on the host.  n_fragments / n_segments may be NULL. */
 int exa_affinities_to_segmentation(int device, const float* aff_host, int D, int H, int W,
                                    const double* thresholds, int n_thresholds, double aff_low,
                                    double aff_high, int64_t min_segment_size, uint64_t* seg_host,
@@ -175,13 +177,16 @@ int exa_affinities_to_segmentation_device(const float* aff_dev, int D, int H, in
                                           int64_t min_segment_size, uint64_t* seg_dev,
                                           int64_t* n_fragments, int64_t* n_segments, void* stream);
 
-/* the merge queue of the function above on its own (host, no GPU needed): region graph edges
- * pair_keys[i] = a << 32 | b with 1 <= a < b <= n_fragments, sums[i] = summed affinity and
- * counts[i] = number of faces between a and b; root_out[0..n_fragments] receives the surviving
- * fragment every fragment was merged into while the smallest 1 - sum/count was < threshold */
-int exa_region_agglomerate(uint32_t n_fragments, int64_t n_edges, const uint64_t* pair_keys,
-                           const double* sums, const int32_t* counts, double threshold,
-                           uint32_t* root_out);
+/* the agglomeration step of the function above on its own, on a region graph in host arrays:
+ * edges eu[i] < ev[i] (fragment ids 1..n_fragments, each pair once, sorted by (eu, ev) -- the index
+ * is the tie-break rank), qsum[i] = sum of the affinities on the faces between the two fragments in
+ * 32.32 fixed point (llrint(clamp(a, 0, 1) * 2^32) per face), count[i] = number of faces.
+ * device < 0: the exact host merge queue only (no GPU needed); device >= 0: parallel rounds on that
+ * GPU, host queue for the rest.  root_out[0..n_fragments] receives the smallest fragment id of the
+ * region every fragment is merged into while the smallest 1 - mean affinity is < threshold. */
+int exa_region_agglomerate(int device, uint32_t n_fragments, int64_t n_edges, const uint32_t* eu,
+                           const uint32_t* ev, const uint64_t* qsum, const uint32_t* count,
+                           double threshold, uint32_t* root_out);
 
 /* host helpers mirroring count_patches / generate_patch_starts (inference.py:340-397);
  * starts receives n_patches*3 int32 (z,y,x) in the reference's order */

@@ -1,169 +1,179 @@
 """CPU restatement of the reference's affinity -> segmentation step -- TEST INFRASTRUCTURE ONLY.
 
 Restates ``affinities_to_segmentation`` (REF/inference.py:196-237, REF =
-src/aind_exaspim_neuron_segmentation) for BASELINE config 5: the product's affinities and the
-oracle's affinities are both pushed through THIS function and the two segmentations are compared
-with the adapted-Rand score.  It is never imported by the product (tests/test_layout.py).
+src/aind_exaspim_neuron_segmentation): ``waterz.agglomerate(affinities, thresholds,
+aff_threshold_low=0.1, aff_threshold_high=0.9999)`` followed by ``remove_small_segments``
+(REF/utils/img_util.py:536-559).  Never imported by the product (tests/test_layout.py).
 
 **Parity unpinned.**  The arithmetic lives in a third-party dependency that is absent from
 /root/reference and from this image: ``waterz @ git+https://github.com/anna-grim/waterz.git@master``
-(pyproject.toml:32 -- a fork pinned to a branch, needs boost; call site REF/inference.py:224-229).
-Neither the reference's tests nor this container can produce golden vectors for it, so this file
-restates the published waterz algorithm:
+(pyproject.toml:32 -- a fork pinned to a branch, needs boost).  Neither the reference's tests nor
+this container can produce golden vectors for it, so ``oracle/ws_ref.cpp`` restates the published
+waterz algorithm step by step (see its header for the sources followed); this module binds it with
+ctypes, adds ``remove_small_segments`` and the adapted-Rand score, and keeps a literal pure-Python
+transcription of the watershed (``watershed_fragments_py``, small volumes only) that the compiled
+one is checked against.
 
-1. *Fragments* (``waterz.agglomerate`` -> ``watershed(aff, low=0.1, high=0.9999)``, Zlateski &
-   Seung's steepest-ascent watershed on the 6-neighbour affinity graph): edges with affinity
-   < low are removed; every voxel keeps its strongest incident edge(s); edges >= high are always
-   kept; the fragments are the connected components of the kept edges; voxels without any kept
-   edge are background (0).  Deviation: exact ties / plateaus are merged into one fragment
-   instead of being divided by the BFS of the original -- irrelevant for float32 sigmoid outputs
-   and applied identically to both volumes under comparison.
-2. *Region graph*: for every pair of touching fragments, the sum and count of the affinities on
-   the faces between them.
-3. *Agglomeration* with ``OneMinus<MeanAffinity<..>>`` scoring: repeatedly merge the pair with
-   the smallest score ``1 - sum/count`` while it is below the threshold, adding up the statistics
-   of parallel edges; the thresholds [0.6, 0.8, 0.9] are cumulative, so the last one decides.
-4. ``remove_small_segments`` (REF/utils/img_util.py:536-559): keep ids with more than
-   ``min_size`` voxels, zero the rest, renumber from 1 in order of first appearance.
+waterz conventions restated here (they differ from round 1 of this repository, which read
+``aff[c][z,y,x]`` as the edge to the NEXT voxel, kept edges with ``>= low`` and merged plateaus):
 
-Edge orientation: this repository trains ``aff[c][z,y,x]`` as the edge from voxel (z,y,x) to its
-NEXT neighbour along axis c (REF/utils/img_util.py:160,207-216); the same convention is used
-here.  Upstream waterz reads it as the edge to the PREVIOUS voxel -- a shift of the lattice by
-one voxel that is applied identically to both volumes under comparison.
+* ``aff[c][z,y,x]`` is the edge between voxel (z,y,x) and its PREVIOUS neighbour along axis c
+  (c = 0, 1, 2 for z, y, x); index 0 along c has no such edge.
+* A voxel joins the watershed only if its largest incident affinity is ``> low`` (strict); an
+  edge is followed if it equals that maximum or is ``>= high``.
+* Plateaus (voxels whose steepest edges point at each other) are divided breadth first from their
+  exits, in voxel scan order; every divided voxel keeps exactly one outgoing edge.
+* Scores are ``1 - mean affinity``; ``accumulate="float32"`` sums in float32 in scan / merge order
+  like waterz's MeanAffinityProvider, ``accumulate="exact"`` (default, what the CUDA path
+  implements) sums 32.32 fixed-point values, which makes the result independent of the order of
+  additions.  Equal scores are ordered by the smallest rank of the original edges involved
+  (waterz leaves ties to std::priority_queue).
 """
 
-import heapq
+import ctypes
 
 import numpy as np
-from scipy.sparse import coo_matrix
-from scipy.sparse.csgraph import connected_components
+
+from . import build as _build
+
+_lib = None
 
 
-def _edge_lists(aff):
-    """Flat (u, v, w) per axis for all in-volume edges u=(z,y,x) -> v=next voxel along the axis."""
-    shape = aff.shape[1:]
-    idx = np.arange(int(np.prod(shape)), dtype=np.int64).reshape(shape)
-    out = []
-    for c in range(3):
-        sl_u = [slice(None)] * 3
-        sl_v = [slice(None)] * 3
-        sl_u[c] = slice(0, shape[c] - 1)
-        sl_v[c] = slice(1, shape[c])
-        u = idx[tuple(sl_u)].ravel()
-        v = idx[tuple(sl_v)].ravel()
-        w = aff[c][tuple(sl_u)].ravel()
-        out.append((u, v, w))
-    return out
+def _ws():
+    global _lib
+    if _lib is None:
+        lib = ctypes.CDLL(_build.build())
+        vp, i64, f32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_float
+        lib.wsref_watershed.restype = i64
+        lib.wsref_watershed.argtypes = [vp, i64, i64, i64, f32, f32, vp]
+        lib.wsref_region_graph.restype = i64
+        lib.wsref_region_graph.argtypes = [vp, vp, i64, i64, i64, vp, vp, vp, vp, vp]
+        lib.wsref_agglomerate.restype = i64
+        lib.wsref_agglomerate.argtypes = [ctypes.c_uint32, i64, vp, vp, vp, vp, vp, ctypes.c_double,
+                                          ctypes.c_int, vp]
+        _lib = lib
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
 
 
 def watershed_fragments(aff, low=0.1, high=0.9999):
-    """Step 1.  aff: float32 (3, D, H, W) -> int64 fragment ids (0 = background), count."""
+    """Step 1 (ws_ref.cpp: wsref_watershed).  float32 (3, D, H, W) -> (int64 ids, count)."""
+    aff = np.ascontiguousarray(aff, dtype=np.float32)
+    d, h, w = aff.shape[1:]
+    seg = np.zeros((d, h, w), dtype=np.uint64)
+    n = _ws().wsref_watershed(_p(aff), d, h, w, low, high, _p(seg))
+    return seg.astype(np.int64), int(n)
+
+
+def watershed_fragments_py(aff, low=0.1, high=0.9999):
+    """The same algorithm transcribed literally in pure Python (small volumes only): the compiled
+    restatement is checked against it in tests/test_watershed_oracle.py."""
     aff = np.asarray(aff, dtype=np.float32)
-    n = int(np.prod(aff.shape[1:]))
-    edges = _edge_lists(aff)
-    # strongest incident affinity of every voxel (edges below `low` do not exist)
-    best = np.zeros(n, dtype=np.float32)
-    for u, v, w in edges:
-        wl = np.where(w >= low, w, 0).astype(np.float32)
-        np.maximum.at(best, u, wl)
-        np.maximum.at(best, v, wl)
-    rows, cols = [], []
-    for u, v, w in edges:
-        ok = w >= low
-        keep = ok & ((w >= high) | (w >= best[u]) | (w >= best[v]))
-        rows.append(u[keep])
-        cols.append(v[keep])
-    rows = np.concatenate(rows)
-    cols = np.concatenate(cols)
-    graph = coo_matrix((np.ones(rows.size, dtype=np.int8), (rows, cols)), shape=(n, n))
-    _, comp = connected_components(graph, directed=False)
-    linked = np.zeros(n, dtype=bool)
-    linked[rows] = True
-    linked[cols] = True
-    # isolated voxels are background; renumber the rest from 1
-    comp = np.where(linked, comp, -1)
-    ids, inv = np.unique(comp, return_inverse=True)
-    if ids[0] == -1:
-        frag = inv.astype(np.int64)          # -1 -> 0, others -> 1..
-        count = ids.size - 1
-    else:
-        frag = inv.astype(np.int64) + 1
-        count = ids.size
-    return frag.reshape(aff.shape[1:]), count
+    D, H, W = aff.shape[1:]
+    hw, n = H * W, D * H * W
+    low, high = np.float32(low), np.float32(high)
+    az, ay, ax = (aff[c].ravel() for c in range(3))
+    seg = [0] * n
+    for z in range(D):
+        for y in range(H):
+            for x in range(W):
+                i = z * hw + y * W + x
+                vals = [az[i] if z > 0 else low, ay[i] if y > 0 else low, ax[i] if x > 0 else low,
+                        az[i + hw] if z < D - 1 else low, ay[i + W] if y < H - 1 else low,
+                        ax[i + 1] if x < W - 1 else low]
+                m = max(vals)
+                if m > low:
+                    for d, v in enumerate(vals):
+                        if v == m or v >= high:
+                            seg[i] |= 1 << d
+    dirs = [-hw, -W, -1, hw, W, 1]
+    mask = [1, 2, 4, 8, 16, 32]
+    imask = [8, 16, 32, 1, 2, 4]
+    VIS, HIGH = 0x40, 1 << 63
+    bfs = []
+    for i in range(n):
+        for d in range(6):
+            if seg[i] & mask[d] and not seg[i + dirs[d]] & imask[d]:
+                seg[i] |= VIS
+                bfs.append(i)
+                break
+    k = 0
+    while k < len(bfs):
+        i = bfs[k]
+        to_set = 0
+        for d in range(6):
+            if seg[i] & mask[d]:
+                j = i + dirs[d]
+                if seg[j] & imask[d]:
+                    if not seg[j] & VIS:
+                        bfs.append(j)
+                        seg[j] |= VIS
+                else:
+                    to_set = mask[d]
+        seg[i] = to_set
+        k += 1
+    next_id = 1
+    for i in range(n):
+        if seg[i] == 0:
+            seg[i] |= HIGH
+        if not seg[i] & HIGH and seg[i]:
+            bfs = [i]
+            seg[i] |= VIS
+            k = 0
+            while k < len(bfs):
+                me = bfs[k]
+                joined = False
+                for d in range(6):
+                    if seg[me] & mask[d]:
+                        him = me + dirs[d]
+                        if seg[him] & HIGH:
+                            for v in bfs:
+                                seg[v] = seg[him]
+                            bfs = []
+                            joined = True
+                            break
+                        if not seg[him] & VIS:
+                            seg[him] |= VIS
+                            bfs.append(him)
+                if joined:
+                    break
+                k += 1
+            if bfs:
+                for v in bfs:
+                    seg[v] = HIGH | next_id
+                next_id += 1
+    out = np.array([s & ~HIGH for s in seg], dtype=np.int64).reshape(D, H, W)
+    return out, next_id - 1
 
 
 def region_graph(aff, frag):
-    """Step 2.  -> dict {(a, b) with a < b: [sum_affinity, n_faces]} over touching fragments."""
-    aff = np.asarray(aff, dtype=np.float32)
-    f = frag.ravel()
-    stats = {}
-    for u, v, w in _edge_lists(aff):
-        a, b = f[u], f[v]
-        m = (a != b) & (a != 0) & (b != 0)
-        a, b, w = a[m], b[m], w[m].astype(np.float64)
-        lo, hi = np.minimum(a, b), np.maximum(a, b)
-        key = lo * (int(f.max()) + 1) + hi
-        order = np.argsort(key, kind="stable")
-        key, w = key[order], w[order]
-        uniq, start = np.unique(key, return_index=True)
-        sums = np.add.reduceat(w, start) if key.size else np.array([])
-        cnts = np.diff(np.append(start, key.size))
-        base = int(f.max()) + 1
-        for k, s, c in zip(uniq.tolist(), sums.tolist(), cnts.tolist()):
-            e = (k // base, k % base)
-            if e in stats:
-                stats[e][0] += s
-                stats[e][1] += c
-            else:
-                stats[e] = [s, c]
-    return stats
+    """Step 2 (wsref_region_graph).  -> dict of arrays: u, v (u < v, sorted), fsum (float32 sums in
+    scan order), qsum (exact 32.32 fixed-point sums), count."""
+    aff = np.ascontiguousarray(aff, dtype=np.float32)
+    seg = np.ascontiguousarray(frag, dtype=np.uint64)
+    d, h, w = seg.shape
+    m = _ws().wsref_region_graph(_p(aff), _p(seg), d, h, w, None, None, None, None, None)
+    out = dict(u=np.zeros(m, np.uint32), v=np.zeros(m, np.uint32), fsum=np.zeros(m, np.float32),
+               qsum=np.zeros(m, np.uint64), count=np.zeros(m, np.uint32))
+    got = _ws().wsref_region_graph(_p(aff), _p(seg), d, h, w, _p(out["u"]), _p(out["v"]),
+                                   _p(out["fsum"]), _p(out["qsum"]), _p(out["count"]))
+    assert got == m
+    return out
 
 
-def agglomerate(n_frag, stats, threshold):
-    """Step 3.  Hierarchical merging with score 1 - mean affinity.  -> root id per fragment (1..n)."""
-    parent = list(range(n_frag + 1))
-
-    def find(x):
-        while parent[x] != x:
-            parent[x] = parent[parent[x]]
-            x = parent[x]
-        return x
-
-    nbr = {i: {} for i in range(1, n_frag + 1)}   # node -> {neighbour: [sum, count]}
-    heap = []
-    for (a, b), (s, c) in stats.items():
-        nbr[a][b] = [s, c]
-        nbr[b][a] = nbr[a][b]
-        heapq.heappush(heap, (1.0 - s / c, a, b, c))
-    while heap:
-        score, a, b, c = heapq.heappop(heap)
-        if score >= threshold:
-            break
-        if parent[a] != a or parent[b] != b or b not in nbr[a] or nbr[a][b][1] != c:
-            continue  # stale entry (an endpoint was merged away or the edge was updated)
-        # merge the node with fewer neighbours into the other
-        if len(nbr[a]) < len(nbr[b]):
-            a, b = b, a
-        parent[b] = a
-        del nbr[a][b]
-        for nb, st in nbr[b].items():
-            if nb == a:
-                continue
-            del nbr[nb][b]
-            if nb in nbr[a]:
-                cur = nbr[a][nb]
-                cur[0] += st[0]
-                cur[1] += st[1]
-            else:
-                cur = [st[0], st[1]]
-                nbr[a][nb] = cur
-                nbr[nb][a] = cur
-            heapq.heappush(heap, (1.0 - cur[0] / cur[1], min(a, nb), max(a, nb), cur[1]))
-        nbr[b] = {}
-    roots = np.arange(n_frag + 1, dtype=np.int64)
-    for i in range(1, n_frag + 1):
-        roots[i] = find(i)
-    return roots
+def agglomerate(n_frag, graph, threshold, accumulate="exact"):
+    """Step 3 (wsref_agglomerate).  -> int64 root id per fragment (index 0 = background)."""
+    mode = {"float32": 0, "exact": 1}[accumulate]
+    m = int(graph["u"].size)
+    order = np.lexsort((graph["v"], graph["u"]))
+    assert np.array_equal(order, np.arange(m)), "edges must be sorted by (u, v)"
+    root = np.zeros(n_frag + 1, dtype=np.uint32)
+    _ws().wsref_agglomerate(n_frag, m, _p(graph["u"]), _p(graph["v"]), _p(graph["fsum"]),
+                            _p(graph["qsum"]), _p(graph["count"]), float(threshold), mode, _p(root))
+    return root.astype(np.int64)
 
 
 def remove_small_segments(seg, min_size):
@@ -181,14 +191,14 @@ def remove_small_segments(seg, min_size):
 
 
 def affinities_to_segmentation_ref(affinities, agglomeration_thresholds=(0.6, 0.8, 0.9),
-                                   min_segment_size=100):
-    """REF/inference.py:196-237 with the waterz call restated (see module docstring)."""
+                                   min_segment_size=100, accumulate="exact"):
+    """REF/inference.py:196-237 with the waterz call restated (see module docstring).  The
+    thresholds are cumulative and the segmentation of the LAST one is kept (inference.py:232)."""
     aff = np.asarray(affinities, dtype=np.float32)
     frag, n = watershed_fragments(aff, low=0.1, high=0.9999)
-    stats = region_graph(aff, frag)
-    roots = agglomerate(n, stats, max(agglomeration_thresholds))
-    seg = roots[frag]
-    return remove_small_segments(seg, min_segment_size)
+    graph = region_graph(aff, frag)
+    roots = agglomerate(n, graph, max(agglomeration_thresholds), accumulate)
+    return remove_small_segments(roots[frag], min_segment_size)
 
 
 def adapted_rand_agreement(seg, ref):

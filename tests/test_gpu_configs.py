@@ -56,12 +56,14 @@ def test_config4_patch128_bf16_vs_fp32_validation_mode():
 
 
 def test_config5_watershed_adapted_rand_agreement():
-    """predict -> affinities_to_segmentation (waterz restated in oracle/watershed_ref.py, parity
-    unpinned) on the product's and on the oracle's affinities: adapted-Rand agreement >= 0.99
-    with the reference's default thresholds (north_star).  With random-init weights the default
-    thresholds merge almost everything (SURVEY.md 8c caveat), so the fragment-level agreement
-    (before agglomeration, where bf16 noise does move voxels) is checked as well."""
-    from aind_exaspim_neuron_segmentation_b200 import predict
+    """predict -> affinities_to_segmentation, the product end to end, against the oracle end to end
+    (oracle predict -> waterz restated in oracle/watershed_ref.py, parity unpinned): adapted-Rand
+    agreement >= 0.99 with the reference's default thresholds (north_star); the product's
+    segmentation of its own affinities equals the oracle's segmentation of the same array exactly.
+    With random-init weights the default thresholds merge almost everything (SURVEY.md 8c caveat),
+    so the fragment-level agreement (before agglomeration, where bf16 noise does move voxels) is
+    checked as well."""
+    from aind_exaspim_neuron_segmentation_b200 import affinities_to_segmentation, predict
     from oracle.predict_ref import predict_ref
     from oracle.unet_ref import make_forward_fn
     from oracle.watershed_ref import (adapted_rand_agreement, affinities_to_segmentation_ref,
@@ -73,7 +75,8 @@ def test_config5_watershed_adapted_rand_agreement():
     ref = predict_ref(vol, make_forward_fn(sd))
     assert float(np.abs(out - ref).max()) <= BF16_TOL
     crop = (slice(None), slice(8, 88), slice(40, 120), slice(40, 120))
-    seg_out = affinities_to_segmentation_ref(out[crop])
+    seg_out = affinities_to_segmentation(out[crop]).astype(np.int64)
+    assert np.array_equal(seg_out, affinities_to_segmentation_ref(out[crop]))
     seg_ref = affinities_to_segmentation_ref(ref[crop])
     score = adapted_rand_agreement(seg_out, seg_ref)
     frag_out, _ = watershed_fragments(out[crop])
