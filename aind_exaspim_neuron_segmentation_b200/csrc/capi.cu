@@ -228,6 +228,12 @@ int exa_affinities_to_segmentation(int device, const float* aff_host, int D, int
   });
 }
 
+int exa_ws_last_profile(double* out, int n) {
+  if (!out || n < 0) return EXA_ERR_INVALID;
+  exa::ws_last_profile(out, n);
+  return EXA_OK;
+}
+
 int exa_region_agglomerate(int device, uint32_t n_fragments, int64_t n_edges, const uint32_t* eu,
                            const uint32_t* ev, const uint64_t* qsum, const uint32_t* count,
                            double threshold, uint32_t* root_out) {

@@ -8,8 +8,9 @@ namespace exa {
 
 Status launch_stem_tc(const __nv_bfloat16* xs, const __nv_bfloat16* w_band, const float* bias,
                       const Act& out, int num_sms, cudaStream_t s) {
-  EXA_CHECK(!out.fp32 && out.C == 32 && out.cstride == 32 && out.coff == 0,
-            "stem_tc: output must be dense bf16 C=32");
+  EXA_CHECK(!out.fp32 && out.C == 32 && out.cstride % 16 == 0 && out.coff % 16 == 0 &&
+                out.coff + 32 <= out.cstride,
+            "stem_tc: output must be a 32-channel bf16 slot aligned to 16 channels");
   EXA_CHECK(out.D % 16 == 0 && out.H % 8 == 0 && out.W % 4 == 0, "stem_tc: patch dims");
   StemTcArgs a{};
   a.B = out.B;
@@ -18,6 +19,8 @@ Status launch_stem_tc(const __nv_bfloat16* xs, const __nv_bfloat16* w_band, cons
   a.tiles_total = out.B * a.ntz * a.nty * a.ntx;
   a.bias = bias;
   a.out = (__nv_bfloat16*)out.ptr;
+  a.cstride = out.cstride;
+  a.coff = out.coff;
   CUtensorMap tx, tw;
   {
     // normalised input as interleaved (hi, lo) bf16 pairs, x innermost, rows padded to W + 8

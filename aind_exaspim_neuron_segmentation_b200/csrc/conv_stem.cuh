@@ -38,7 +38,8 @@ struct StemTcArgs {
   int ntz, nty, ntx;         // super-tiles: 16 (z) x 8 (y) x 24 (x) output voxels (last x one ragged)
   int tiles_total;
   const float* bias;         // [32] folded
-  __nv_bfloat16* out;        // NDHWC, C = 32 dense
+  __nv_bfloat16* out;        // NDHWC: 32 channels at offset coff of voxels cstride elements apart
+  int cstride, coff;         // multiples of 16 (32-byte stores)
 };
 
 struct StemTcSmem {
@@ -198,10 +199,11 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       const int nsub = min(STEM_SUBS, (p.P[2] - tx * (4 * STEM_SUBS)) >> 2);
       const int z = tz * 16 + zz, y = ty * 8 + yy;
       __nv_bfloat16* row_dst =
-          p.out + ((((size_t)b * p.P[0] + z) * p.P[1] + y) * p.P[2] + tx * (4 * STEM_SUBS)) * 32;
+          p.out + p.coff +
+          ((((size_t)b * p.P[0] + z) * p.P[1] + y) * p.P[2] + tx * (4 * STEM_SUBS)) * p.cstride;
       for (int j = 0; j < nsub; ++j, ++seq) {
         if ((seq & 1) == hs) {
-          __nv_bfloat16* dst = row_dst + j * 4 * 32;
+          __nv_bfloat16* dst = row_dst + (size_t)j * 4 * p.cstride;
           mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
           tc_fence_after();
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 128);
@@ -229,7 +231,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                   const float c = leaky_relu(__uint_as_float(uc) + bias[16 * g + 2 * jj + 1]);
                   pk[jj] = pack_bf16x2(a, c);
                 }
-                st_global_256(dst + (half * 2 + xo) * 32 + g * 16, pk);
+                st_global_256(dst + (size_t)(half * 2 + xo) * p.cstride + g * 16, pk);
               }
             }
           }

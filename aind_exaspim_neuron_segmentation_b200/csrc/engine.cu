@@ -153,6 +153,10 @@ Engine::~Engine() {
     free_dev(L.w_zfold);
     free_dev(L.bias);
   }
+  for (auto& u : upconv_) {
+    free_dev(u.w);
+    free_dev(u.bias);
+  }
   free_dev(head_w_);
   free_dev(head_b_);
   free_dev(stem_band_);
@@ -172,6 +176,13 @@ Engine::~Engine() {
     cudaEventDestroy(alt_free_);
   }
   if (copy_event_) cudaEventDestroy(copy_event_);
+  if (peer_ready_) {
+    cudaEventDestroy(peer_ready_);
+    for (int i = 0; i < kPeerStreams; ++i) {
+      cudaStreamDestroy(peer_stream_[i]);
+      cudaEventDestroy(peer_done_[i]);
+    }
+  }
   free_dev(vol_stage_);
   free_dev(out_stage_);
   if (copy_stream_) cudaStreamDestroy(copy_stream_);
@@ -317,27 +328,29 @@ struct LayerSpec {
   int conv_idx, bn_idx;
   int cin, cout;
 };
-// unet3d.py:64-74 with trilinear=True, width_multiplier=1 (inference.py:419-420)
-const LayerSpec kLayers[18] = {
-    {"inc.double_conv", 0, 1, 1, 32},
-    {"inc.double_conv", 3, 4, 32, 32},
-    {"down1.maxpool_conv.1.double_conv", 0, 1, 32, 64},
-    {"down1.maxpool_conv.1.double_conv", 3, 4, 64, 64},
-    {"down2.maxpool_conv.1.double_conv", 0, 1, 64, 128},
-    {"down2.maxpool_conv.1.double_conv", 3, 4, 128, 128},
-    {"down3.maxpool_conv.1.double_conv", 0, 1, 128, 256},
-    {"down3.maxpool_conv.1.double_conv", 3, 4, 256, 256},
-    {"down4.maxpool_conv.1.double_conv", 0, 1, 256, 256},
-    {"down4.maxpool_conv.1.double_conv", 3, 4, 256, 256},
-    {"up1.conv.double_conv", 0, 1, 512, 256},
-    {"up1.conv.double_conv", 3, 4, 256, 128},
-    {"up2.conv.double_conv", 0, 1, 256, 128},
-    {"up2.conv.double_conv", 3, 4, 128, 64},
-    {"up3.conv.double_conv", 0, 1, 128, 64},
-    {"up3.conv.double_conv", 3, 4, 64, 32},
-    {"up4.conv.double_conv", 0, 1, 64, 32},
-    {"up4.conv.double_conv", 3, 4, 32, 32},
-};
+// unet3d.py:56-74: channels c[k] = int(32 * 2^k * width_multiplier); trilinear upsampling halves the
+// deep widths (factor 2) and gives the decoder's DoubleConv a mid width of in/2 (unet3d.py:248-258).
+// width_multiplier = 1, trilinear = True is what load_model builds (inference.py:419-420).
+void layer_table(const int c[5], bool trilinear, LayerSpec out[18]) {
+  const int f = trilinear ? 2 : 1;
+  static const char* kPrefix[9] = {
+      "inc.double_conv",
+      "down1.maxpool_conv.1.double_conv", "down2.maxpool_conv.1.double_conv",
+      "down3.maxpool_conv.1.double_conv", "down4.maxpool_conv.1.double_conv",
+      "up1.conv.double_conv", "up2.conv.double_conv", "up3.conv.double_conv", "up4.conv.double_conv"};
+  // (in, mid, out) of the nine DoubleConv blocks
+  int io[9][3] = {{1, c[0], c[0]},
+                  {c[0], c[1], c[1]}, {c[1], c[2], c[2]}, {c[2], c[3], c[3]},
+                  {c[3], c[4] / f, c[4] / f},
+                  {c[4], trilinear ? c[4] / 2 : c[3] / f, c[3] / f},
+                  {c[3], trilinear ? c[3] / 2 : c[2] / f, c[2] / f},
+                  {c[2], trilinear ? c[2] / 2 : c[1] / f, c[1] / f},
+                  {c[1], trilinear ? c[1] / 2 : c[0], c[0]}};
+  for (int b = 0; b < 9; ++b) {
+    out[2 * b] = LayerSpec{kPrefix[b], 0, 1, io[b][0], io[b][1]};
+    out[2 * b + 1] = LayerSpec{kPrefix[b], 3, 4, io[b][1], io[b][2]};
+  }
+}
 
 uint16_t f32_to_bf16_rn(float f) {
   uint32_t u;
@@ -364,11 +377,26 @@ Status Engine::finalize_weights() {
     return Status::OK();
   };
 
-  // head first: its shape decides affinity (3) vs foreground (1) mode  (unet3d.py:75,318)
+  // configuration from the entries themselves: width of the first conv (32 * width_multiplier) and
+  // the presence of transposed-conv weights (trilinear=False, unet3d.py:254-256)
+  {
+    auto it = raw_.find("inc.double_conv.0.weight");
+    EXA_CHECK(it != raw_.end(), "missing state_dict entry: inc.double_conv.0.weight");
+    EXA_CHECK(it->second.shape.size() == 5 && it->second.shape[0] >= 32 &&
+                  it->second.shape[0] <= 128 && it->second.shape[0] % 32 == 0,
+              "unsupported width: inc.double_conv.0.weight must have 32, 64, 96 or 128 output channels "
+              "(width_multiplier 1..4)");
+    for (int k = 0; k < 5; ++k) chan_[k] = (int)it->second.shape[0] << k;
+    trilinear_ = raw_.find("up1.up.weight") == raw_.end();
+  }
+  LayerSpec specs[18];
+  layer_table(chan_, trilinear_, specs);
+  const int c0 = chan_[0];
+  // head: its shape decides affinity (3) vs foreground (1) mode  (unet3d.py:75,318)
   {
     auto it = raw_.find("outc.conv.weight");
     EXA_CHECK(it != raw_.end(), "missing state_dict entry: outc.conv.weight");
-    EXA_CHECK(it->second.shape.size() == 5 && it->second.shape[1] == 32 &&
+    EXA_CHECK(it->second.shape.size() == 5 && it->second.shape[1] == c0 &&
                   it->second.shape[2] == 1 && it->second.shape[3] == 1 &&
                   it->second.shape[4] == 1 && it->second.shape[0] >= 1 &&
                   it->second.shape[0] <= 8,
@@ -376,22 +404,54 @@ Status Engine::finalize_weights() {
     out_channels_ = (int)it->second.shape[0];
   }
   const HostTensor *hw = nullptr, *hb = nullptr;
-  EXA_TRY(get("outc.conv.weight", {out_channels_, 32, 1, 1, 1}, EXA_DTYPE_F32, &hw));
+  EXA_TRY(get("outc.conv.weight", {out_channels_, c0, 1, 1, 1}, EXA_DTYPE_F32, &hw));
   EXA_TRY(get("outc.conv.bias", {out_channels_}, EXA_DTYPE_F32, &hb));
   free_dev(head_w_);
   free_dev(head_b_);
   head_w_ = head_b_ = nullptr;
   head_w_host_ = hw->f32;
   head_b_host_ = hb->f32;
-  EXA_CUDA(cudaMalloc(&head_w_, sizeof(float) * out_channels_ * 32));
+  EXA_CUDA(cudaMalloc(&head_w_, sizeof(float) * out_channels_ * c0));
   EXA_CUDA(cudaMalloc(&head_b_, sizeof(float) * out_channels_));
-  EXA_CUDA(cudaMemcpy(head_w_, hw->f32.data(), sizeof(float) * out_channels_ * 32,
+  EXA_CUDA(cudaMemcpy(head_w_, hw->f32.data(), sizeof(float) * out_channels_ * c0,
                       cudaMemcpyHostToDevice));
   EXA_CUDA(cudaMemcpy(head_b_, hb->f32.data(), sizeof(float) * out_channels_,
                       cudaMemcpyHostToDevice));
 
+  // transposed convs of the decoder (trilinear=False): ConvTranspose3d(in, in/2, k=2, s=2), weight
+  // (in, in/2, 2, 2, 2) -> [tap = dz*4+dy*2+dx][cin][cout], bf16-rounded once in bf16 mode
+  for (int u = 0; u < 4; ++u) {
+    free_dev(upconv_[u].w);
+    free_dev(upconv_[u].bias);
+    upconv_[u] = UpConv{};
+    if (trilinear_) continue;
+    const int cin = chan_[4 - u], cout = cin / 2;
+    const std::string key = "up" + std::to_string(u + 1) + ".up";
+    const HostTensor *w, *b;
+    EXA_TRY(get(key + ".weight", {cin, cout, 2, 2, 2}, EXA_DTYPE_F32, &w));
+    EXA_TRY(get(key + ".bias", {cout}, EXA_DTYPE_F32, &b));
+    upconv_[u].cin = cin;
+    upconv_[u].cout = cout;
+    const size_t n = (size_t)8 * cin * cout;
+    std::vector<float> pk(n);
+    for (int ci = 0; ci < cin; ++ci)
+      for (int co = 0; co < cout; ++co)
+        for (int tap = 0; tap < 8; ++tap) {
+          float v = w->f32[((size_t)ci * cout + co) * 8 + tap];
+          if (precision_ == EXA_PRECISION_BF16) {
+            const uint32_t bits = (uint32_t)f32_to_bf16_rn(v) << 16;
+            memcpy(&v, &bits, 4);
+          }
+          pk[((size_t)tap * cin + ci) * cout + co] = v;
+        }
+    EXA_CUDA(cudaMalloc(&upconv_[u].w, n * 4));
+    EXA_CUDA(cudaMemcpy(upconv_[u].w, pk.data(), n * 4, cudaMemcpyHostToDevice));
+    EXA_CUDA(cudaMalloc(&upconv_[u].bias, sizeof(float) * cout));
+    EXA_CUDA(cudaMemcpy(upconv_[u].bias, b->f32.data(), sizeof(float) * cout, cudaMemcpyHostToDevice));
+  }
+
   for (int li = 0; li < 18; ++li) {
-    const LayerSpec& sp = kLayers[li];
+    const LayerSpec& sp = specs[li];
     ConvLayer& L = layers_[li];
     L.conv_key = std::string(sp.prefix) + "." + std::to_string(sp.conv_idx);
     L.bn_key = std::string(sp.prefix) + "." + std::to_string(sp.bn_idx);
@@ -430,29 +490,36 @@ Status Engine::finalize_weights() {
       return (double)w->f32[((size_t)co * sp.cin + ci) * 27 + tap] * scale[co];
     };
     if (li == 0) {
-      for (int tap = 0; tap < 27; ++tap)
-        for (int co = 0; co < 32; ++co) stem_.w[tap][co] = (float)wsrc(co, 0, tap);
-      for (int co = 0; co < 32; ++co) stem_.b[co] = bias[co];
+      // the stem kernels produce 32 channels per pass: one weight group per 32 output channels
+      const int groups = sp.cout / 32;
+      stem_.assign(groups, StemWeights{});
+      for (int g = 0; g < groups; ++g) {
+        for (int tap = 0; tap < 27; ++tap)
+          for (int co = 0; co < 32; ++co) stem_[g].w[tap][co] = (float)wsrc(g * 32 + co, 0, tap);
+        for (int co = 0; co < 32; ++co) stem_[g].b[co] = bias[g * 32 + co];
+      }
       if (precision_ == EXA_PRECISION_BF16) {
         // Toeplitz (band) form for the tensor-core stem (conv_stem.cuh): B[kz,ky][n = xo*32 + c]
         // [k = 2*x' + part] = w[c][kz][ky][kx = x' - xo] for both the hi and the lo part of the
         // input, bf16-rounded once like every other layer's weights
-        std::vector<uint16_t> band((size_t)9 * 128 * 16, 0);
-        for (int t9 = 0; t9 < 9; ++t9)
-          for (int xo = 0; xo < 4; ++xo)
-            for (int c = 0; c < 32; ++c)
-              for (int kx = 0; kx < 3; ++kx)
-                for (int part = 0; part < 2; ++part)
-                  band[((size_t)t9 * 128 + xo * 32 + c) * 16 + 2 * (xo + kx) + part] =
-                      f32_to_bf16_rn(stem_.w[t9 * 3 + kx][c]);
+        const size_t per_group = (size_t)9 * 128 * 16;
+        std::vector<uint16_t> band(per_group * groups, 0);
+        for (int g = 0; g < groups; ++g)
+          for (int t9 = 0; t9 < 9; ++t9)
+            for (int xo = 0; xo < 4; ++xo)
+              for (int c = 0; c < 32; ++c)
+                for (int kx = 0; kx < 3; ++kx)
+                  for (int part = 0; part < 2; ++part)
+                    band[g * per_group + ((size_t)t9 * 128 + xo * 32 + c) * 16 + 2 * (xo + kx) + part] =
+                        f32_to_bf16_rn(stem_[g].w[t9 * 3 + kx][c]);
         free_dev(stem_band_);
         free_dev(stem_bias_);
         stem_band_ = nullptr;
         stem_bias_ = nullptr;
         EXA_CUDA(cudaMalloc(&stem_band_, band.size() * 2));
         EXA_CUDA(cudaMemcpy(stem_band_, band.data(), band.size() * 2, cudaMemcpyHostToDevice));
-        EXA_CUDA(cudaMalloc(&stem_bias_, sizeof(float) * 32));
-        EXA_CUDA(cudaMemcpy(stem_bias_, stem_.b, sizeof(float) * 32, cudaMemcpyHostToDevice));
+        EXA_CUDA(cudaMalloc(&stem_bias_, sizeof(float) * sp.cout));
+        EXA_CUDA(cudaMemcpy(stem_bias_, bias.data(), sizeof(float) * sp.cout, cudaMemcpyHostToDevice));
       }
       continue;
     }
@@ -504,8 +571,9 @@ struct WsLayout {
   size_t xhi, xlo, a0, cat4, p1, d1a, cat3, p2, d2a, cat2, p3, d3a, cat1, p4, d4a, x5, u1a, u1, u2a, u2, u3a,
       u3, total;
 };
-WsLayout layout(int B, int pz, int py, int px) {
+WsLayout layout(int B, int pz, int py, int px, const int c[5], bool trilinear) {
   auto vox = [&](int lvl) { return (size_t)B * (pz >> lvl) * (py >> lvl) * (px >> lvl); };
+  const int f = trilinear ? 2 : 1;
   WsLayout L{};
   size_t off = 0;
   auto take = [&](size_t n) {
@@ -516,26 +584,26 @@ WsLayout layout(int B, int pz, int py, int px) {
   // normalised input as interleaved bf16 (hi, lo) pairs, rows padded to px + 8 voxels
   L.xhi = take((size_t)B * pz * py * (px + 8) * 2);
   L.xlo = 0;
-  L.a0 = take(vox(0) * 32);    // inc.0 output; re-used for up4.0 output (A0 is dead by then)
-  L.cat4 = take(vox(0) * 64);  // [x1 | up(u3)]
-  L.p1 = take(vox(1) * 32);
-  L.d1a = take(vox(1) * 64);
-  L.cat3 = take(vox(1) * 128);  // [x2 | up(u2)]
-  L.p2 = take(vox(2) * 64);
-  L.d2a = take(vox(2) * 128);
-  L.cat2 = take(vox(2) * 256);  // [x3 | up(u1)]
-  L.p3 = take(vox(3) * 128);
-  L.d3a = take(vox(3) * 256);
-  L.cat1 = take(vox(3) * 512);  // [x4 | up(x5)]
-  L.p4 = take(vox(4) * 256);
-  L.d4a = take(vox(4) * 256);
-  L.x5 = take(vox(4) * 256);
-  L.u1a = take(vox(3) * 256);
-  L.u1 = take(vox(3) * 128);
-  L.u2a = take(vox(2) * 128);
-  L.u2 = take(vox(2) * 64);
-  L.u3a = take(vox(1) * 64);
-  L.u3 = take(vox(1) * 32);
+  L.a0 = take(vox(0) * c[0]);        // inc.0 output; re-used for up4.0 output (A0 is dead by then)
+  L.cat4 = take(vox(0) * 2 * c[0]);  // [x1 | up(u3)]
+  L.p1 = take(vox(1) * c[0]);
+  L.d1a = take(vox(1) * c[1]);
+  L.cat3 = take(vox(1) * 2 * c[1]);  // [x2 | up(u2)]
+  L.p2 = take(vox(2) * c[1]);
+  L.d2a = take(vox(2) * c[2]);
+  L.cat2 = take(vox(2) * 2 * c[2]);  // [x3 | up(u1)]
+  L.p3 = take(vox(3) * c[2]);
+  L.d3a = take(vox(3) * c[3]);
+  L.cat1 = take(vox(3) * 2 * c[3]);  // [x4 | up(x5)]
+  L.p4 = take(vox(4) * c[3]);
+  L.d4a = take(vox(4) * (c[4] / f));
+  L.x5 = take(vox(4) * (c[4] / f));
+  L.u1a = take(vox(3) * (trilinear ? c[4] / 2 : c[3]));
+  L.u1 = take(vox(3) * (c[3] / f));
+  L.u2a = take(vox(2) * (trilinear ? c[3] / 2 : c[2]));
+  L.u2 = take(vox(2) * (c[2] / f));
+  L.u3a = take(vox(1) * (trilinear ? c[2] / 2 : c[1]));
+  L.u3 = take(vox(1) * (c[1] / f));
   L.total = off;
   return L;
 }
@@ -543,7 +611,7 @@ WsLayout layout(int B, int pz, int py, int px) {
 
 Status Engine::ensure_workspace(int batch, int pz, int py, int px) {
   const size_t esz = precision_ == EXA_PRECISION_BF16 ? 2 : 4;
-  const size_t need = layout(batch, pz, py, px).total * esz;
+  const size_t need = layout(batch, pz, py, px, chan_, trilinear_).total * esz;
   if (need > ws_bytes_) {
     free_dev(ws_);
     ws_ = nullptr;
@@ -584,7 +652,7 @@ Status Engine::conv(const ConvLayer& L, const Act& in, const Act& out, const Hea
   }
   if (head) {
     Scope sc(this, CAT_HEAD, s);
-    EXA_TRY(launch_head_fp32(out, *head, s));
+    EXA_TRY(launch_head(out, *head, s));
   }
   if (pool_out) {
     Scope sc(this, CAT_POOL, s);
@@ -600,7 +668,7 @@ Status Engine::run_network(const PatchSource& src, int batch, int pz, int py, in
   EXA_TRY(ensure_workspace(batch, pz, py, px));
   const bool f32 = precision_ == EXA_PRECISION_FP32;
   const size_t esz = f32 ? 4 : 2;
-  const WsLayout L = layout(batch, pz, py, px);
+  const WsLayout L = layout(batch, pz, py, px, chan_, trilinear_);
   auto act = [&](size_t off, int lvl, int C, int cstride, int coff) {
     Act a;
     a.ptr = (char*)ws_ + off * esz;
@@ -614,30 +682,40 @@ Status Engine::run_network(const PatchSource& src, int batch, int pz, int py, in
     a.fp32 = f32;
     return a;
   };
-  const Act a0 = act(L.a0, 0, 32, 32, 0);
-  const Act x1 = act(L.cat4, 0, 32, 64, 0), up4_slot = act(L.cat4, 0, 32, 64, 32),
-            cat4 = act(L.cat4, 0, 64, 64, 0);
-  const Act p1 = act(L.p1, 1, 32, 32, 0), d1a = act(L.d1a, 1, 64, 64, 0);
-  const Act x2 = act(L.cat3, 1, 64, 128, 0), up3_slot = act(L.cat3, 1, 64, 128, 64),
-            cat3 = act(L.cat3, 1, 128, 128, 0);
-  const Act p2 = act(L.p2, 2, 64, 64, 0), d2a = act(L.d2a, 2, 128, 128, 0);
-  const Act x3 = act(L.cat2, 2, 128, 256, 0), up2_slot = act(L.cat2, 2, 128, 256, 128),
-            cat2 = act(L.cat2, 2, 256, 256, 0);
-  const Act p3 = act(L.p3, 3, 128, 128, 0), d3a = act(L.d3a, 3, 256, 256, 0);
-  const Act x4 = act(L.cat1, 3, 256, 512, 0), up1_slot = act(L.cat1, 3, 256, 512, 256),
-            cat1 = act(L.cat1, 3, 512, 512, 0);
-  const Act p4 = act(L.p4, 4, 256, 256, 0), d4a = act(L.d4a, 4, 256, 256, 0),
-            x5 = act(L.x5, 4, 256, 256, 0);
-  const Act u1a = act(L.u1a, 3, 256, 256, 0), u1 = act(L.u1, 3, 128, 128, 0);
-  const Act u2a = act(L.u2a, 2, 128, 128, 0), u2 = act(L.u2, 2, 64, 64, 0);
-  const Act u3a = act(L.u3a, 1, 64, 64, 0), u3 = act(L.u3, 1, 32, 32, 0);
-  const Act u4a = a0;  // alias: A0 is dead after inc.3
-  // fp32 mode needs a real buffer for the last conv's activations before the head
-  const Act u4 = act(L.cat4, 0, 32, 32, 0);  // cat4 is dead once up4.0 has run
+  // channel counts (unet3d.py:56-74); at every level the concat buffer is [skip c_k | upsampled c_k]
+  const int c0 = chan_[0], c1 = chan_[1], c2 = chan_[2], c3 = chan_[3], c4 = chan_[4];
+  const int fdiv = trilinear_ ? 2 : 1;
+  const int cb = c4 / fdiv;                                   // bottleneck width
+  const int m1 = trilinear_ ? c4 / 2 : c3, o1 = c3 / fdiv;    // up1 DoubleConv: mid, out
+  const int m2 = trilinear_ ? c3 / 2 : c2, o2 = c2 / fdiv;
+  const int m3 = trilinear_ ? c2 / 2 : c1, o3 = c1 / fdiv;
+  const Act a0 = act(L.a0, 0, c0, c0, 0);
+  const Act x1 = act(L.cat4, 0, c0, 2 * c0, 0), up4_slot = act(L.cat4, 0, c0, 2 * c0, c0),
+            cat4 = act(L.cat4, 0, 2 * c0, 2 * c0, 0);
+  const Act p1 = act(L.p1, 1, c0, c0, 0), d1a = act(L.d1a, 1, c1, c1, 0);
+  const Act x2 = act(L.cat3, 1, c1, 2 * c1, 0), up3_slot = act(L.cat3, 1, c1, 2 * c1, c1),
+            cat3 = act(L.cat3, 1, 2 * c1, 2 * c1, 0);
+  const Act p2 = act(L.p2, 2, c1, c1, 0), d2a = act(L.d2a, 2, c2, c2, 0);
+  const Act x3 = act(L.cat2, 2, c2, 2 * c2, 0), up2_slot = act(L.cat2, 2, c2, 2 * c2, c2),
+            cat2 = act(L.cat2, 2, 2 * c2, 2 * c2, 0);
+  const Act p3 = act(L.p3, 3, c2, c2, 0), d3a = act(L.d3a, 3, c3, c3, 0);
+  const Act x4 = act(L.cat1, 3, c3, 2 * c3, 0), up1_slot = act(L.cat1, 3, c3, 2 * c3, c3),
+            cat1 = act(L.cat1, 3, 2 * c3, 2 * c3, 0);
+  const Act p4 = act(L.p4, 4, c3, c3, 0), d4a = act(L.d4a, 4, cb, cb, 0),
+            x5 = act(L.x5, 4, cb, cb, 0);
+  const Act u1a = act(L.u1a, 3, m1, m1, 0), u1 = act(L.u1, 3, o1, o1, 0);
+  const Act u2a = act(L.u2a, 2, m2, m2, 0), u2 = act(L.u2, 2, o2, o2, 0);
+  const Act u3a = act(L.u3a, 1, m3, m3, 0), u3 = act(L.u3, 1, o3, o3, 0);
+  const Act u4a = a0;  // alias: A0 is dead after inc.3 (up4's mid width is c0 in both modes)
+  // the last conv's activations before an unfused head (fp32 mode, or widths above 32)
+  const Act u4 = act(L.cat4, 0, c0, c0, 0);  // cat4 is dead once up4.0 has run
 
-  auto up = [&](const Act& i, const Act& o, const ConvRegion* rg) {
+  // x2 upsampling into the concat slot: trilinear interpolation (unet3d.py:248-250) or the
+  // block's ConvTranspose3d (unet3d.py:254-256); `which` = 0..3 for up1..up4
+  auto up = [&](int which, const Act& i, const Act& o, const ConvRegion* rg) {
     Scope sc(this, CAT_UPSAMPLE, s);
-    return launch_upsample(i, o, rg, s);
+    if (trilinear_) return launch_upsample(i, o, rg, s);
+    return launch_upconv(i, o, upconv_[which].w, upconv_[which].bias, rg, s);
   };
   // Only the inner [trim, P-trim) box of the last conv is ever read (inference.py:161-162), so
   // the last two convs and the last upsample are restricted to that box grown by their
@@ -659,6 +737,8 @@ Status Engine::run_network(const PatchSource& src, int batch, int pz, int py, in
     p_ups = &r_ups;
   }
 
+  // the stem kernels write 32 channels per pass into channel slots of A0
+  const int stem_groups = c0 / 32;
   if (!f32 && use_tc_stem_ && pz % 16 == 0 && py % 8 == 0 && px % 4 == 0) {
     // inc.0 on the tensor cores: gather/normalise into bf16 (hi, lo) pairs, then the Toeplitz-form conv
     __nv_bfloat16* xs = (__nv_bfloat16*)((char*)ws_ + L.xhi * esz);
@@ -666,14 +746,19 @@ Status Engine::run_network(const PatchSource& src, int batch, int pz, int py, in
       Scope sc(this, CAT_STEM, s);
       EXA_TRY(launch_stem_split(src, batch, pz, py, px, xs, s));
     }
-    {
+    for (int g = 0; g < stem_groups; ++g) {
       Scope sc(this, CAT_STEM, s);
-      EXA_TRY(launch_stem_tc(xs, stem_band_, stem_bias_, a0, num_sms_, s));
+      EXA_TRY(launch_stem_tc(xs, stem_band_ + (size_t)g * 9 * 128 * 16, stem_bias_ + g * 32,
+                             act(L.a0, 0, 32, c0, g * 32), num_sms_, s));
     }
   } else {
-    Scope sc(this, CAT_STEM, s);
-    EXA_TRY(launch_stem(src, stem_, a0, s));                // inc.0 (+gather/normalise)
+    for (int g = 0; g < stem_groups; ++g) {
+      Scope sc(this, CAT_STEM, s);
+      EXA_TRY(launch_stem(src, stem_[g], act(L.a0, 0, 32, c0, g * 32), s));  // inc.0 (+gather/normalise)
+    }
   }
+  // the 1x1x1 head rides in the last conv's epilogue when that conv has 32 channels (bf16 mode)
+  const bool fused_head = !f32 && c0 == 32;
   EXA_TRY(conv(layers_[1], a0, x1, nullptr, nullptr, &p1, s));   // inc.3 -> skip slot of CAT4 (+pool)
   EXA_TRY(conv(layers_[2], p1, d1a, nullptr, nullptr, nullptr, s));
   EXA_TRY(conv(layers_[3], d1a, x2, nullptr, nullptr, &p2, s));
@@ -683,18 +768,24 @@ Status Engine::run_network(const PatchSource& src, int batch, int pz, int py, in
   EXA_TRY(conv(layers_[7], d3a, x4, nullptr, nullptr, &p4, s));
   EXA_TRY(conv(layers_[8], p4, d4a, nullptr, nullptr, nullptr, s));
   EXA_TRY(conv(layers_[9], d4a, x5, nullptr, nullptr, nullptr, s));
-  EXA_TRY(up(x5, up1_slot, nullptr));                       // cat([x4, up(x5)])  unet3d.py:288
+  EXA_TRY(up(0, x5, up1_slot, nullptr));                    // cat([x4, up(x5)])  unet3d.py:288
   EXA_TRY(conv(layers_[10], cat1, u1a, nullptr, nullptr, nullptr, s));
   EXA_TRY(conv(layers_[11], u1a, u1, nullptr, nullptr, nullptr, s));
-  EXA_TRY(up(u1, up2_slot, nullptr));
+  EXA_TRY(up(1, u1, up2_slot, nullptr));
   EXA_TRY(conv(layers_[12], cat2, u2a, nullptr, nullptr, nullptr, s));
   EXA_TRY(conv(layers_[13], u2a, u2, nullptr, nullptr, nullptr, s));
-  EXA_TRY(up(u2, up3_slot, nullptr));
+  EXA_TRY(up(2, u2, up3_slot, nullptr));
   EXA_TRY(conv(layers_[14], cat3, u3a, nullptr, nullptr, nullptr, s));
   EXA_TRY(conv(layers_[15], u3a, u3, nullptr, nullptr, nullptr, s));
-  EXA_TRY(up(u3, up4_slot, p_ups));
+  EXA_TRY(up(3, u3, up4_slot, p_ups));
   EXA_TRY(conv(layers_[16], cat4, u4a, nullptr, p_up40, nullptr, s));
-  EXA_TRY(conv(layers_[17], u4a, u4, &head, p_last, nullptr, s));  // + 1x1x1 head, sigmoid, trim
+  if (fused_head || f32) {
+    EXA_TRY(conv(layers_[17], u4a, u4, &head, p_last, nullptr, s));  // + 1x1x1 head, sigmoid, trim
+  } else {
+    EXA_TRY(conv(layers_[17], u4a, u4, nullptr, p_last, nullptr, s));
+    Scope sc(this, CAT_HEAD, s);
+    EXA_TRY(launch_head(u4, head, s));
+  }
   return Status::OK();
 }
 
@@ -937,13 +1028,65 @@ Status Engine::stitch_planes(const float* seed_dev, float* out_dev, size_t out_c
     a.seed_z0 = slab_.seed_z0;
     a.seed_z1 = slab_.seed_z1;
   }
-  if (peer_local_ && out_dev >= peer_local_ && out_dev < peer_local_ + peer_elems_) {
+  const bool to_peers = peer_local_ && !peer_bases_.empty() && out_dev >= peer_local_ &&
+                        out_dev < peer_local_ + peer_elems_;
+  if (to_peers && !peer_ce_) {
     const ptrdiff_t off = out_dev - peer_local_;
     a.n_peers = (int)peer_bases_.size();
     for (int i = 0; i < a.n_peers; ++i) a.peer_out[i] = peer_bases_[i] + off;
   }
-  Scope sc(this, CAT_STITCH, s);
-  return launch_stitch(a, s);
+  {
+    Scope sc(this, CAT_STITCH, s);
+    EXA_TRY(launch_stitch(a, s));
+  }
+  if (to_peers && peer_ce_) EXA_TRY(copy_planes_to_peers(out_dev, out_cstride, z1 - z0, y0, y1, s));
+  return Status::OK();
+}
+
+// Copy-engine form of the fused gather: rows [y0, y1) (all rows when y1 <= y0) of the nz planes at
+// out_dev, every channel, to the same offsets of every peer's copy.  The transfers run on side
+// streams, ordered after the stitch just queued on s; join_peer_copies() orders s after them.
+Status Engine::copy_planes_to_peers(const float* out_dev, size_t out_cstride, int nz, int y0, int y1,
+                                    cudaStream_t s) {
+  if (!peer_ready_) {
+    EXA_CUDA(cudaEventCreateWithFlags(&peer_ready_, cudaEventDisableTiming));
+    for (int i = 0; i < kPeerStreams; ++i) {
+      EXA_CUDA(cudaStreamCreateWithFlags(&peer_stream_[i], cudaStreamNonBlocking));
+      EXA_CUDA(cudaEventCreateWithFlags(&peer_done_[i], cudaEventDisableTiming));
+    }
+  }
+  const size_t plane = (size_t)plan_.H * plan_.W;
+  const ptrdiff_t off = out_dev - peer_local_;
+  const bool band = y1 > y0 && !(y0 == 0 && (size_t)y1 * plan_.W == plane);
+  EXA_CUDA(cudaEventRecord(peer_ready_, s));
+  for (int i = 0; i < kPeerStreams; ++i) EXA_CUDA(cudaStreamWaitEvent(peer_stream_[i], peer_ready_, 0));
+  for (size_t i = 0; i < peer_bases_.size(); ++i) {
+    cudaStream_t ps = peer_stream_[i % kPeerStreams];
+    for (int c = 0; c < out_channels_; ++c) {
+      const float* src = out_dev + c * out_cstride;
+      float* dst = peer_bases_[i] + off + c * out_cstride;
+      if (!band) {
+        EXA_CUDA(cudaMemcpyAsync(dst, src, (size_t)nz * plane * 4, cudaMemcpyDeviceToDevice, ps));
+      } else {
+        const size_t yoff = (size_t)y0 * plan_.W;
+        EXA_CUDA(cudaMemcpy2DAsync(dst + yoff, plane * 4, src + yoff, plane * 4,
+                                   (size_t)(y1 - y0) * plan_.W * 4, (size_t)nz,
+                                   cudaMemcpyDeviceToDevice, ps));
+      }
+    }
+  }
+  peer_pending_ = true;
+  return Status::OK();
+}
+
+Status Engine::join_peer_copies(cudaStream_t s) {
+  if (!peer_pending_) return Status::OK();
+  for (int i = 0; i < kPeerStreams; ++i) {
+    EXA_CUDA(cudaEventRecord(peer_done_[i], peer_stream_[i]));
+    EXA_CUDA(cudaStreamWaitEvent(s, peer_done_[i], 0));
+  }
+  peer_pending_ = false;
+  return Status::OK();
 }
 
 Status Engine::set_peer_outputs(float* local_base, int64_t elems, float* const* peer_bases,
@@ -953,6 +1096,10 @@ Status Engine::set_peer_outputs(float* local_base, int64_t elems, float* const* 
   peer_bases_.clear();
   peer_local_ = n_peers > 0 ? local_base : nullptr;
   peer_elems_ = n_peers > 0 ? elems : 0;
+  {
+    const char* g = getenv("EXA_GATHER");
+    peer_ce_ = g && std::string(g) == "ce";
+  }
   for (int i = 0; i < n_peers; ++i) {
     EXA_CHECK(peer_bases[i] != nullptr, "set_peer_outputs: null peer pointer");
     peer_bases_.push_back(peer_bases[i]);
@@ -1019,7 +1166,9 @@ Status Engine::pipeline_rows(const uint16_t* vol_dev, int vol_z0, int D, int H, 
     probs_busy = false;
     // one-row groups with a host destination stream finished y-bands while the row still runs
     band_ = BandSink();
-    if (out_host && r1 - r0 == 1 && ss == s) {
+    const bool ce_peers = peer_ce_ && peer_local_ && !peer_bases_.empty() && out_dev >= peer_local_ &&
+                          out_dev < peer_local_ + peer_elems_;
+    if ((out_host || ce_peers) && r1 - r0 == 1 && ss == s) {
       exa_slab_plan g;
       st = plan_slab(plan, r0, r1, &g);
       if (!st.ok) break;
@@ -1147,6 +1296,7 @@ Status Engine::pipeline_finish(const float* seed_in, float* out_dev, size_t out_
     if (e != cudaSuccess && st.ok)
       st = Status::Err(std::string("predict: D2H failed: ") + cudaGetErrorString(e));
   }
+  if (st.ok) st = join_peer_copies(s);   // the peers' copies are complete before later work on s
   return st;
 }
 

@@ -145,7 +145,15 @@ class Engine {
   int out_channels_ = 0;
   std::map<std::string, HostTensor> raw_;
   ConvLayer layers_[18];
-  StemWeights stem_{};
+  // model configuration, read off the state_dict in finalize_weights (unet3d.py:37-75)
+  int chan_[5] = {32, 64, 128, 256, 512};
+  bool trilinear_ = true;
+  struct UpConv {  // ConvTranspose3d(k=2, s=2) of an Up block when trilinear=False
+    int cin = 0, cout = 0;
+    float* w = nullptr;     // [8 taps][cin][cout] float32 (bf16-rounded values in bf16 mode)
+    float* bias = nullptr;  // [cout]
+  } upconv_[4];
+  std::vector<StemWeights> stem_;  // one group of 32 output channels each
   __nv_bfloat16* stem_band_ = nullptr;  // [9 (kz,ky)][128 (xo,c)][16 (x',hi|lo)] Toeplitz weights (conv_stem.cuh)
   float* stem_bias_ = nullptr;          // [32]
   bool use_tc_stem_ = true;             // EXA_NO_TC_STEM=1: SIMT fp32 stem also in bf16 mode
@@ -209,6 +217,16 @@ class Engine {
   float* peer_local_ = nullptr;
   int64_t peer_elems_ = 0;
   std::vector<float*> peer_bases_;
+  // EXA_GATHER=ce: finished planes go to the peers' copies by copy-engine transfers on side
+  // streams (no SM time, overlapped with the next waves) instead of stores from the stitch kernel
+  bool peer_ce_ = false;
+  static constexpr int kPeerStreams = 4;
+  cudaStream_t peer_stream_[kPeerStreams] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t peer_ready_ = nullptr, peer_done_[kPeerStreams] = {nullptr, nullptr, nullptr, nullptr};
+  bool peer_pending_ = false;
+  Status copy_planes_to_peers(const float* out_dev, size_t out_cstride, int nz, int y0, int y1,
+                              cudaStream_t s);
+  Status join_peer_copies(cudaStream_t s);
 };
 
 }  // namespace exa

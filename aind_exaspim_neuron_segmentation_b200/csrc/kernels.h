@@ -40,7 +40,7 @@ struct PatchSource {
 };
 
 struct HeadParams {
-  const float* w = nullptr;  // device [C][32]
+  const float* w = nullptr;  // device [C][c0] (c0 = channels of the last conv; 32 for the fused head)
   const float* b = nullptr;  // device [C]
   const float* w_host = nullptr;  // host copies (passed to K1z as kernel parameters)
   const float* b_host = nullptr;
@@ -94,7 +94,11 @@ Status launch_conv_zfold(const Act& in, const Act& out, const __nv_bfloat16* w_z
                          const Act* pool_out, int num_sms, bool pair, cudaStream_t s);
 Status launch_conv_fp32(const Act& in, const Act& out, const float* w_packed, const float* bias,
                         cudaStream_t s);
-Status launch_head_fp32(const Act& in, const HeadParams& head, cudaStream_t s);
+// 1x1x1 head + sigmoid + trim as a kernel of its own (fp32 mode; bf16 models wider than 32)
+Status launch_head(const Act& in, const HeadParams& head, cudaStream_t s);
+// ConvTranspose3d(k=2, s=2) into a concat slot; w: [8 taps][cin][cout] float32, bias [cout]
+Status launch_upconv(const Act& in, const Act& out, const float* w, const float* bias,
+                     const ConvRegion* region, cudaStream_t s);
 Status launch_maxpool(const Act& in, const Act& out, cudaStream_t s);
 // region (optional): only output voxels inside the box are produced
 Status launch_upsample(const Act& in, const Act& out, const ConvRegion* region, cudaStream_t s);

@@ -146,6 +146,7 @@ struct StemArgs {
   PatchSource src;
   int B, Pz, Py, Px;
   void* out;
+  int cstride, coff;  // the 32 output channels sit at offset coff of voxels cstride elements apart
 };
 
 constexpr int ST_TX = 16, ST_TY = 8, ST_TZ = 8;
@@ -223,7 +224,7 @@ stem_kernel(const __grid_constant__ StemWeights wt, const StemArgs a) {
     for (int h = 0; h < 2; ++h) {
       const size_t vox =
           (((size_t)b * a.Pz + (z0 + tz + h)) * a.Py + (y0 + ty)) * a.Px + (x0 + tx);
-      T* dst = outp + vox * 32;
+      T* dst = outp + vox * a.cstride + a.coff;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         float f[8];
@@ -243,7 +244,8 @@ stem_kernel(const __grid_constant__ StemWeights wt, const StemArgs a) {
 }
 
 Status launch_stem(const PatchSource& src, const StemWeights& w, const Act& out, cudaStream_t s) {
-  EXA_CHECK(out.C == 32 && out.cstride == 32 && out.coff == 0, "stem output must be dense C=32");
+  EXA_CHECK(out.C == 32 && out.cstride % 8 == 0 && out.coff % 8 == 0 && out.coff + 32 <= out.cstride,
+            "stem output must be a 32-channel slot aligned to 8 channels");
   EXA_CHECK(out.W % ST_TX == 0 && out.H % ST_TY == 0 && out.D % ST_TZ == 0,
             "patch dims must be multiples of 16");
   StemArgs a;
@@ -253,6 +255,8 @@ Status launch_stem(const PatchSource& src, const StemWeights& w, const Act& out,
   a.Py = out.H;
   a.Px = out.W;
   a.out = out.ptr;
+  a.cstride = out.cstride;
+  a.coff = out.coff;
   dim3 grid((out.W / ST_TX) * (out.H / ST_TY), out.D / ST_TZ, out.B);
   const bool from_vol = src.vol != nullptr;
   EXA_CHECK(from_vol || src.x != nullptr, "stem: no input source");
@@ -767,12 +771,14 @@ Status launch_upsample(const Act& in, const Act& out, const ConvRegion* region, 
 }
 
 // ---------------------------------------------------------------------------
-// K5' (fp32 validation mode): 1x1x1 head + sigmoid + trim
+// K5' (fp32 validation mode, and bf16 models wider than 32 channels where the head cannot ride
+// in the last conv's epilogue): 1x1x1 head + sigmoid + trim  (unet3d.py:318, inference.py:158-162)
 // ---------------------------------------------------------------------------
+template <typename T>
 __global__ void __launch_bounds__(256)
-head_fp32_kernel(const float* __restrict__ in, int cstride, int coff, int B, int D, int H, int W,
-                 const float* __restrict__ hw, const float* __restrict__ hb, float* __restrict__ out,
-                 int C, int trim, int apply_sigmoid) {
+head_kernel(const T* __restrict__ in, int cstride, int coff, int cin, int B, int D, int H, int W,
+            const float* __restrict__ hw, const float* __restrict__ hb, float* __restrict__ out,
+            int C, int trim, int apply_sigmoid) {
   const int Dz = D - 2 * trim, Hy = H - 2 * trim, Wx = W - 2 * trim;
   const size_t total = (size_t)B * Dz * Hy * Wx;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -784,30 +790,133 @@ head_fp32_kernel(const float* __restrict__ in, int cstride, int coff, int B, int
   const int z = (int)(v % Dz);
   const int b = (int)(v / Dz);
   const size_t vox = (((size_t)b * D + z + trim) * H + y + trim) * W + x + trim;
-  const float* src = in + vox * cstride + coff;
-  float f[32];
+  const T* src = in + vox * cstride + coff;
+  float s[8];
 #pragma unroll
-  for (int g = 0; g < 8; ++g) {
-    const float4 q = *reinterpret_cast<const float4*>(src + 4 * g);
-    f[4 * g] = q.x; f[4 * g + 1] = q.y; f[4 * g + 2] = q.z; f[4 * g + 3] = q.w;
+  for (int oc = 0; oc < 8; ++oc) s[oc] = oc < C ? __ldg(hb + oc) : 0.f;
+  // channels in ascending order, eight at a time (the accumulation order of the fp32 reference
+  // is not specified; 32-term fp32 sums agree to ~1e-7)
+  for (int c8 = 0; c8 < cin; c8 += 8) {
+    float f[8];
+    Vec8<T> q;
+    q.load(src + c8);
+    q.to_float(f);
+    for (int oc = 0; oc < C; ++oc) {
+      float acc = s[oc];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc = fmaf(__ldg(hw + oc * cin + c8 + j), f[j], acc);
+      s[oc] = acc;
+    }
   }
   for (int oc = 0; oc < C; ++oc) {
-    float s = __ldg(hb + oc);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) s = fmaf(__ldg(hw + oc * 32 + j), f[j], s);
-    if (apply_sigmoid) s = 1.f / (1.f + expf(-s));
-    out[((((size_t)b * C + oc) * Dz + z) * Hy + y) * Wx + x] = s;
+    float r = s[oc];
+    if (apply_sigmoid) r = 1.f / (1.f + expf(-r));
+    out[((((size_t)b * C + oc) * Dz + z) * Hy + y) * Wx + x] = r;
   }
 }
 
-Status launch_head_fp32(const Act& in, const HeadParams& h, cudaStream_t s) {
-  EXA_CHECK(in.fp32 && in.C == 32, "head_fp32 expects 32 fp32 channels");
+Status launch_head(const Act& in, const HeadParams& h, cudaStream_t s) {
+  EXA_CHECK(in.C % 8 == 0 && in.cstride % 8 == 0 && in.coff % 8 == 0 && h.C >= 1 && h.C <= 8,
+            "head: channels must be multiples of 8 and at most 8 outputs");
   const size_t total =
       (size_t)in.B * (in.D - 2 * h.trim) * (in.H - 2 * h.trim) * (in.W - 2 * h.trim);
   const int blocks = (int)ceil_div64((int64_t)total, 256);
-  head_fp32_kernel<<<blocks, 256, 0, s>>>((const float*)in.ptr, in.cstride, in.coff, in.B, in.D,
-                                           in.H, in.W, h.w, h.b, h.out, h.C, h.trim,
-                                           h.apply_sigmoid);
+  if (in.fp32) {
+    head_kernel<float><<<blocks, 256, 0, s>>>((const float*)in.ptr, in.cstride, in.coff, in.C, in.B,
+                                               in.D, in.H, in.W, h.w, h.b, h.out, h.C, h.trim,
+                                               h.apply_sigmoid);
+  } else {
+    head_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)in.ptr, in.cstride,
+                                                       in.coff, in.C, in.B, in.D, in.H, in.W, h.w,
+                                                       h.b, h.out, h.C, h.trim, h.apply_sigmoid);
+  }
+  EXA_CUDA(cudaGetLastError());
+  return Status::OK();
+}
+
+// ---------------------------------------------------------------------------
+// ConvTranspose3d(k = 2, s = 2) of an Up block built with trilinear=False (unet3d.py:254-256):
+// out[b, 2z+dz, 2y+dy, 2x+dx, co] = bias[co] + sum_ci in[b, z, y, x, ci] * w[ci][co][dz][dy][dx],
+// written into the concat slot.  fp32 accumulation in ascending ci; bf16 mode rounds the result
+// once.  One thread: one output voxel x 8 output channels.
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+upconv_kernel(const T* __restrict__ in, int in_cstride, int in_coff, int cin, T* __restrict__ out,
+              int out_cstride, int out_coff, int cout, int B, int Di, int Hi, int Wi,
+              const float* __restrict__ w, const float* __restrict__ bias, const ConvRegion rg) {
+  const int c8n = cout / 8;
+  const int rz = rg.hi[0] - rg.lo[0], ry = rg.hi[1] - rg.lo[1], rx = rg.hi[2] - rg.lo[2];
+  const size_t total = (size_t)B * rz * ry * rx * c8n;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c8 = (int)(i % c8n);
+  size_t v = i / c8n;
+  const int xo = rg.lo[2] + (int)(v % rx);
+  v /= rx;
+  const int yo = rg.lo[1] + (int)(v % ry);
+  v /= ry;
+  const int zo = rg.lo[0] + (int)(v % rz);
+  const int b = (int)(v / rz);
+  const int tap = (zo & 1) * 4 + (yo & 1) * 2 + (xo & 1);
+  const T* src = in + in_coff +
+                 ((((size_t)b * Di + (zo >> 1)) * Hi + (yo >> 1)) * Wi + (xo >> 1)) * in_cstride;
+  const float* wt = w + (size_t)tap * cin * cout + 8 * c8;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = __ldg(bias + 8 * c8 + j);
+  for (int ci8 = 0; ci8 < cin; ci8 += 8) {
+    float f[8];
+    Vec8<T> q;
+    q.load(src + ci8);
+    q.to_float(f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(wt + (size_t)(ci8 + k) * cout));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(wt + (size_t)(ci8 + k) * cout + 4));
+      acc[0] = fmaf(f[k], w0.x, acc[0]); acc[1] = fmaf(f[k], w0.y, acc[1]);
+      acc[2] = fmaf(f[k], w0.z, acc[2]); acc[3] = fmaf(f[k], w0.w, acc[3]);
+      acc[4] = fmaf(f[k], w1.x, acc[4]); acc[5] = fmaf(f[k], w1.y, acc[5]);
+      acc[6] = fmaf(f[k], w1.z, acc[6]); acc[7] = fmaf(f[k], w1.w, acc[7]);
+    }
+  }
+  const int Ho = 2 * Hi, Wo = 2 * Wi, Do = 2 * Di;
+  T* dst = out + out_coff + ((((size_t)b * Do + zo) * Ho + yo) * Wo + xo) * out_cstride + 8 * c8;
+  Vec8<T> o;
+  o.from_float(acc);
+  o.store(dst);
+}
+
+Status launch_upconv(const Act& in, const Act& out, const float* w, const float* bias,
+                     const ConvRegion* region, cudaStream_t s) {
+  EXA_CHECK(w && bias, "upconv: the model has no transposed-conv weights");
+  EXA_CHECK(in.fp32 == out.fp32 && in.C % 8 == 0 && out.C % 8 == 0 && in.cstride % 8 == 0 &&
+                in.coff % 8 == 0 && out.cstride % 8 == 0 && out.coff % 8 == 0,
+            "upconv: type/channel mismatch");
+  EXA_CHECK(out.D == 2 * in.D && out.H == 2 * in.H && out.W == 2 * in.W && in.B == out.B,
+            "upconv: shape mismatch");
+  ConvRegion rg;
+  rg.lo[0] = rg.lo[1] = rg.lo[2] = 0;
+  rg.hi[0] = out.D; rg.hi[1] = out.H; rg.hi[2] = out.W;
+  if (region) {
+    rg = *region;
+    EXA_CHECK(rg.lo[0] >= 0 && rg.lo[1] >= 0 && rg.lo[2] >= 0 && rg.hi[0] <= out.D &&
+                  rg.hi[1] <= out.H && rg.hi[2] <= out.W && rg.lo[0] < rg.hi[0] &&
+                  rg.lo[1] < rg.hi[1] && rg.lo[2] < rg.hi[2],
+              "upconv: bad output region");
+  }
+  const size_t total = (size_t)out.B * (rg.hi[0] - rg.lo[0]) * (rg.hi[1] - rg.lo[1]) *
+                       (rg.hi[2] - rg.lo[2]) * (out.C / 8);
+  const unsigned blocks = (unsigned)ceil_div64((int64_t)total, 256);
+  if (in.fp32) {
+    upconv_kernel<float><<<blocks, 256, 0, s>>>((const float*)in.ptr, in.cstride, in.coff, in.C,
+                                                 (float*)out.ptr, out.cstride, out.coff, out.C, in.B,
+                                                 in.D, in.H, in.W, w, bias, rg);
+  } else {
+    upconv_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(
+        (const __nv_bfloat16*)in.ptr, in.cstride, in.coff, in.C, (__nv_bfloat16*)out.ptr,
+        out.cstride, out.coff, out.C, in.B, in.D, in.H, in.W, w, bias, rg);
+  }
   EXA_CUDA(cudaGetLastError());
   return Status::OK();
 }

@@ -55,16 +55,43 @@ namespace {
 
 constexpr uint32_t kNone = 0xffffffffu;
 
-// stream-ordered allocations from the device's default pool: repeated calls reuse the memory
-// instead of paying cudaMalloc/cudaFree every time (the pool keeps what it is given, see
-// keep_pool_memory)
 double g_alloc_ms = 0.0;  // host time inside the allocator calls (EXA_WS_PROF)
+// wall milliseconds of the phases of the last affinities_to_segmentation call of this process
+// (exa_ws_last_profile): fragments, region graph, parallel rounds, host queue, sizes + relabel,
+// then counts: parallel rounds, region-graph edges, edges handed to the host queue
+double g_last_profile[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 struct AllocTimer {
   std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
   ~AllocTimer() {
     g_alloc_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   }
 };
+
+// Stream-ordered allocations from a pool of our own (cudaMemPoolCreate): it never gives memory back
+// to the driver (release threshold = max), so after the first call at a given size the ~30
+// allocations of a call cost microseconds.  (The device's default pool was measured to hand
+// memory back between calls now and then: 250-900 ms of allocator time per call at 256^3-512^3.)
+cudaMemPool_t g_pool[64] = {};
+
+Status ws_pool(cudaMemPool_t* out) {
+  int dev = 0;
+  EXA_CUDA(cudaGetDevice(&dev));
+  EXA_CHECK(dev >= 0 && dev < 64, "affinities_to_segmentation: device index out of range");
+  if (!g_pool[dev]) {
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    cudaMemPool_t pool;
+    EXA_CUDA(cudaMemPoolCreate(&pool, &props));
+    uint64_t keep = ~0ull;
+    EXA_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    g_pool[dev] = pool;
+  }
+  *out = g_pool[dev];
+  return Status::OK();
+}
 
 struct DevBuf {
   void* p = nullptr;
@@ -81,7 +108,9 @@ struct DevBuf {
   Status alloc(size_t bytes) {
     release();
     AllocTimer t;
-    EXA_CUDA(cudaMallocAsync(&p, bytes ? bytes : 1, s));
+    cudaMemPool_t pool;
+    EXA_TRY(ws_pool(&pool));
+    EXA_CUDA(cudaMallocFromPoolAsync(&p, bytes ? bytes : 1, pool, s));
     return Status::OK();
   }
   template <typename T>
@@ -89,16 +118,6 @@ struct DevBuf {
     return static_cast<T*>(p);
   }
 };
-
-Status keep_pool_memory() {
-  int dev = 0;
-  EXA_CUDA(cudaGetDevice(&dev));
-  cudaMemPool_t pool;
-  EXA_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
-  uint64_t keep = ~0ull;
-  EXA_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-  return Status::OK();
-}
 
 struct Vol {
   int D, H, W;
@@ -580,6 +599,33 @@ agg_compact_kernel(uint32_t m, Edges src, const uint32_t* __restrict__ off, Edge
   dst.k[o] = src.k[e];
 }
 
+// hand-over to the host queue: regions that still have edges get dense ids (ascending with the
+// region id) on the GPU
+__global__ void __launch_bounds__(256)
+agg_mark_nodes_kernel(uint32_t m, const uint32_t* __restrict__ eu, const uint32_t* __restrict__ ev,
+                      uint32_t* __restrict__ used) {
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= m || eu[e] == 0) return;
+  used[eu[e]] = 1;
+  used[ev[e]] = 1;
+}
+
+__global__ void __launch_bounds__(256)
+agg_dense_kernel(uint32_t m, uint32_t* __restrict__ eu, uint32_t* __restrict__ ev,
+                 const uint32_t* __restrict__ dense) {
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= m) return;
+  eu[e] = dense[eu[e]] + 1u;
+  ev[e] = dense[ev[e]] + 1u;
+}
+
+__global__ void __launch_bounds__(256)
+agg_dense_ids_kernel(uint32_t n, const uint32_t* __restrict__ used, const uint32_t* __restrict__ dense,
+                     uint32_t* __restrict__ ids) {
+  const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f < n && used[f]) ids[dense[f]] = f;
+}
+
 __global__ void __launch_bounds__(256)
 agg_set_parent_kernel(uint32_t n, const uint32_t* __restrict__ node, const uint32_t* __restrict__ to,
                       uint32_t* __restrict__ parent) {
@@ -693,8 +739,8 @@ int env_int(const char* name, int fallback) {
 // root (device, n_frag + 1): the smallest fragment id of the region every fragment ends up in.
 //   EXA_WS_GPU_ROUNDS   upper bound on the parallel rounds (default 1 << 30; 0 = host queue only)
 //   EXA_WS_HOST_TAIL    1 (default): hand over to the host queue once at most EXA_WS_TAIL_EDGES
-//                       (default 32768) edges are alive, or when the rounds degenerate into a
-//                       chain (fewer than live / 65536 merges after 256 rounds);
+//                       (default 32768) edges are alive, or when a round merges fewer than
+//                       8 + live / 40000 edges (the host queue is then the cheaper way to finish);
 //                       0: parallel rounds to the end
 Status agglomerate_rounds(EdgeStore& es, uint32_t m0, uint32_t n_frag, int64_t T, uint32_t* root,
                           cudaStream_t s, bool prof, int* rounds_out, uint32_t* tail_edges_out) {
@@ -723,6 +769,25 @@ Status agglomerate_rounds(EdgeStore& es, uint32_t m0, uint32_t n_frag, int64_t T
     EXA_CUDA(cudaMemsetAsync(stamp.p, 0, (size_t)n_nodes * 4, s));
     EXA_CUDA(cudaMemsetAsync(counters.p, 0, 8, s));
     uint32_t table_slots = 0;
+    auto compact = [&]() -> Status {
+      EXA_TRY(flag.alloc((size_t)m * 4));
+      EXA_TRY(off.alloc((size_t)m * 4));
+      const unsigned gb = grid_for(m);
+      Edges E = es.view();
+      agg_alive_kernel<<<gb, 256, 0, s>>>(m, E.u, flag.as<uint32_t>());
+      EXA_CUDA(cudaGetLastError());
+      EXA_TRY(exclusive_scan_u32(flag.as<uint32_t>(), off.as<uint32_t>(), m, tmp, s));
+      EXA_TRY(spare.alloc(live));
+      agg_compact_kernel<<<gb, 256, 0, s>>>(m, E, off.as<uint32_t>(), spare.view());
+      EXA_CUDA(cudaGetLastError());
+      std::swap(es.u.p, spare.u.p);
+      std::swap(es.v.p, spare.v.p);
+      std::swap(es.q.p, spare.q.p);
+      std::swap(es.c.p, spare.c.p);
+      std::swap(es.k.p, spare.k.p);
+      m = live;
+      return Status::OK();
+    };
     uint32_t* h = nullptr;  // pinned: {merges of the round, dead slots in total}
     EXA_CUDA(cudaMallocHost(&h, 8));
     struct Unpin {
@@ -770,26 +835,15 @@ Status agglomerate_rounds(EdgeStore& es, uint32_t m0, uint32_t n_frag, int64_t T
       if (prof && (rounds <= 4 || (rounds & (rounds - 1)) == 0))
         fprintf(stderr, "[exa watershed]   round %d: %u merges, %u live edges\n", rounds, merges, live);
       // compact the slots when more than half are dead
-      if ((m - live) * 2u > m && m > 4096) {
-        EXA_TRY(flag.alloc((size_t)m * 4));
-        EXA_TRY(off.alloc((size_t)m * 4));
-        agg_alive_kernel<<<gb, 256, 0, s>>>(m, E.u, flag.as<uint32_t>());
-        EXA_CUDA(cudaGetLastError());
-        EXA_TRY(exclusive_scan_u32(flag.as<uint32_t>(), off.as<uint32_t>(), m, tmp, s));
-        EXA_TRY(spare.alloc(live));
-        agg_compact_kernel<<<gb, 256, 0, s>>>(m, E, off.as<uint32_t>(), spare.view());
-        EXA_CUDA(cudaGetLastError());
-        std::swap(es.u.p, spare.u.p);
-        std::swap(es.v.p, spare.v.p);
-        std::swap(es.q.p, spare.q.p);
-        std::swap(es.c.p, spare.c.p);
-        std::swap(es.k.p, spare.k.p);
-        m = live;
-      }
-      // hand-over: the rest is small enough for the host queue, or the rounds have degenerated
-      // into a chain (a path of strictly ordered scores merges one edge per round)
-      if (host_tail && (live <= tail_edges || (rounds >= 256 && merges < std::max(2u, live >> 16)))) break;
+      if ((m - live) * 2u > m && m > 4096) EXA_TRY(compact());
+      // hand-over to the host queue when it is the cheaper way to finish.  Measured on a B200 box
+      // (512^3 smooth field, 8-9 M live edges): a round costs about 50 us + 0.19 ns per live edge
+      // here, a merge about 6 us there (hub merges move long neighbour lists), so the rounds pay
+      // while they merge more than ~8 + live / 40000 edges each; they end in hub chains (one large
+      // region swallowing its neighbours a few per round)
+      if (host_tail && (live <= tail_edges || (rounds >= 64 && merges < 8u + live / 40000u))) break;
     }
+    if (!finished && m != live) EXA_TRY(compact());
   }
   if (rounds_out) *rounds_out = rounds;
   if (tail_edges_out) *tail_edges_out = 0;
@@ -804,45 +858,39 @@ Status agglomerate_rounds(EdgeStore& es, uint32_t m0, uint32_t n_frag, int64_t T
     t_phase = now;
   };
   if (!finished) {
-    // ---- exact host queue on what is left ----
+    // ---- exact host queue on what is left (all m slots are alive here) ----
     Edges E = es.view();
-    std::vector<uint32_t> hu(m), hv(m), hc(m), hk(m);
-    std::vector<unsigned long long> hq(m);
-    EXA_CUDA(cudaMemcpyAsync(hu.data(), E.u, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
-    EXA_CUDA(cudaMemcpyAsync(hv.data(), E.v, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
-    EXA_CUDA(cudaMemcpyAsync(hq.data(), E.q, (size_t)m * 8, cudaMemcpyDeviceToHost, s));
-    EXA_CUDA(cudaMemcpyAsync(hc.data(), E.c, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
-    EXA_CUDA(cudaMemcpyAsync(hk.data(), E.k, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
+    DevBuf used(s), dense(s), ids_dev(s);
+    EXA_TRY(used.alloc((size_t)n_nodes * 4));
+    EXA_TRY(dense.alloc((size_t)n_nodes * 4));
+    EXA_CUDA(cudaMemsetAsync(used.p, 0, (size_t)n_nodes * 4, s));
+    agg_mark_nodes_kernel<<<grid_for(m), 256, 0, s>>>(m, E.u, E.v, used.as<uint32_t>());
+    EXA_CUDA(cudaGetLastError());
+    EXA_TRY(exclusive_scan_u32(used.as<uint32_t>(), dense.as<uint32_t>(), n_nodes, tmp, s));
+    uint32_t n_live = 0;
+    EXA_TRY(scan_total_u32(used.as<uint32_t>(), dense.as<uint32_t>(), n_nodes, &n_live, s));
+    EXA_TRY(ids_dev.alloc((size_t)n_live * 4));
+    agg_dense_ids_kernel<<<grid_for(n_nodes), 256, 0, s>>>(n_nodes, used.as<uint32_t>(),
+                                                            dense.as<uint32_t>(), ids_dev.as<uint32_t>());
+    agg_dense_kernel<<<grid_for(m), 256, 0, s>>>(m, E.u, E.v, dense.as<uint32_t>());
+    EXA_CUDA(cudaGetLastError());
+    std::vector<uint32_t> a(m), b(m), c(m), k(m), ids(n_live);
+    std::vector<uint64_t> q(m);
+    EXA_CUDA(cudaMemcpyAsync(a.data(), E.u, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
+    EXA_CUDA(cudaMemcpyAsync(b.data(), E.v, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
+    EXA_CUDA(cudaMemcpyAsync(q.data(), E.q, (size_t)m * 8, cudaMemcpyDeviceToHost, s));
+    EXA_CUDA(cudaMemcpyAsync(c.data(), E.c, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
+    EXA_CUDA(cudaMemcpyAsync(k.data(), E.k, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
+    EXA_CUDA(cudaMemcpyAsync(ids.data(), ids_dev.p, (size_t)n_live * 4, cudaMemcpyDeviceToHost, s));
     EXA_CUDA(cudaStreamSynchronize(s));
-    // regions that still have edges -> dense ids 1..n_live (in ascending region id)
-    std::vector<uint32_t> ids;
-    ids.reserve((size_t)m * 2);
-    for (uint32_t e = 0; e < m; ++e)
-      if (hu[e] != 0) {
-        ids.push_back(hu[e]);
-        ids.push_back(hv[e]);
-      }
-    std::sort(ids.begin(), ids.end());
-    ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
-    const uint32_t n_live = (uint32_t)ids.size();
-    auto dense = [&](uint32_t id) {
-      return (uint32_t)(std::lower_bound(ids.begin(), ids.end(), id) - ids.begin()) + 1u;
-    };
-    std::vector<uint32_t> a, b, k, c;
-    std::vector<uint64_t> q;
-    for (uint32_t e = 0; e < m; ++e)
-      if (hu[e] != 0) {
-        a.push_back(dense(hu[e]));
-        b.push_back(dense(hv[e]));
-        q.push_back(hq[e]);
-        c.push_back(hc[e]);
-        k.push_back(hk[e]);
-      }
     if (tail_edges_out) *tail_edges_out = (uint32_t)a.size();
     std::vector<uint32_t> hp((size_t)n_live + 1);
     for (uint32_t i = 0; i <= n_live; ++i) hp[i] = i;
     sublap("tail to the host");
+    const auto t_queue = std::chrono::steady_clock::now();
     ws::agglomerate(n_live, a.size(), a.data(), b.data(), q.data(), c.data(), k.data(), T, hp.data());
+    g_last_profile[3] =
+        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_queue).count();
     sublap("host queue");
     // every merged region points at the smallest region id of its group (dense ids ascend with
     // region ids, and a region id is the smallest fragment id of the region)
@@ -895,19 +943,21 @@ Status affinities_to_segmentation_device(const float* aff, int D, int H, int W,
   const double threshold = *std::max_element(thresholds, thresholds + n_thresholds);
   const int64_t T = ws::fixed_threshold(threshold);
   const unsigned blocks = grid_for(g.n);
-  EXA_TRY(keep_pool_memory());
   // EXA_WS_PROF=1: wall time of the phases on stderr (every phase ends with a stream sync)
   const bool prof = env_int("EXA_WS_PROF", 0) == 1;
   auto t_last = std::chrono::steady_clock::now();
-  auto lap = [&](const char* what) {
-    if (!prof) return;
+  auto lap = [&](const char* what, int slot) {
     cudaStreamSynchronize(s);
     const auto now = std::chrono::steady_clock::now();
-    fprintf(stderr, "[exa watershed] %-28s %9.3f ms  (allocator calls %.3f ms)\n", what,
-            std::chrono::duration<double, std::milli>(now - t_last).count(), g_alloc_ms);
+    const double ms = std::chrono::duration<double, std::milli>(now - t_last).count();
+    g_last_profile[slot] = ms;
+    if (prof)
+      fprintf(stderr, "[exa watershed] %-28s %9.3f ms  (allocator calls %.3f ms)\n", what, ms,
+              g_alloc_ms);
     g_alloc_ms = 0.0;
     t_last = now;
   };
+  for (double& v : g_last_profile) v = 0.0;
 
   auto t_sub = std::chrono::steady_clock::now();
   auto sub = [&](const char* what) {
@@ -994,7 +1044,7 @@ Status affinities_to_segmentation_device(const float* aff, int D, int H, int W,
   pos.release();
   parent.release();
   bits.release();
-  lap("fragments (GPU)");
+  lap("fragments (GPU)", 0);
 
   // ---- region graph ----
   const uint32_t n_nodes = n_frag + 1;
@@ -1087,7 +1137,7 @@ Status affinities_to_segmentation_device(const float* aff, int D, int H, int W,
       std::swap(es.c.p, ucnt.p);
     }
     sub("reduce by pair");
-    lap("region graph (GPU)");
+    lap("region graph (GPU)", 1);
 
     // ---- agglomeration ----
     EXA_TRY(agglomerate_rounds(es, n_region_edges, n_frag, T, root.as<uint32_t>(), s, prof, &rounds,
@@ -1096,7 +1146,11 @@ Status affinities_to_segmentation_device(const float* aff, int D, int H, int W,
   if (prof)
     fprintf(stderr, "[exa watershed] %u fragments, %u region edges, %d parallel rounds, %u edges to the host queue\n",
             n_frag, n_region_edges, rounds, tail_edges);
-  lap("agglomeration");
+  lap("agglomeration", 2);
+  g_last_profile[2] -= g_last_profile[3];   // slot 3 (host queue) was filled by agglomerate_rounds
+  g_last_profile[5] = rounds;
+  g_last_profile[6] = n_region_edges;
+  g_last_profile[7] = tail_edges;
 
   // ---- small segments out, ids in order of first appearance (img_util.py:536-559) ----
   {
@@ -1126,8 +1180,12 @@ Status affinities_to_segmentation_device(const float* aff, int D, int H, int W,
     if (n_segments) *n_segments = kept;
   }
   EXA_CUDA(cudaStreamSynchronize(s));
-  lap("sizes + relabel (GPU)");
+  lap("sizes + relabel (GPU)", 4);
   return Status::OK();
+}
+
+void ws_last_profile(double* out, int n) {
+  for (int i = 0; i < n && i < 8; ++i) out[i] = g_last_profile[i];
 }
 
 Status region_agglomerate(int device, uint32_t n_fragments, int64_t n_edges, const uint32_t* eu,
@@ -1163,7 +1221,6 @@ Status region_agglomerate(int device, uint32_t n_fragments, int64_t n_edges, con
     return Status::OK();
   }
   EXA_CUDA(cudaSetDevice(device));
-  EXA_TRY(keep_pool_memory());
   cudaStream_t s = nullptr;
   EdgeStore es(s);
   DevBuf root(s);

@@ -20,6 +20,11 @@ Status affinities_to_segmentation_host(int device, const float* aff, int D, int 
                                        double aff_high, int64_t min_segment_size, uint64_t* seg,
                                        int64_t* n_fragments, int64_t* n_segments);
 
+// wall milliseconds of the phases of the last affinities_to_segmentation call in this process:
+// [0] fragments, [1] region graph, [2] parallel agglomeration rounds, [3] host queue, [4] sizes +
+// relabel, then counts: [5] parallel rounds, [6] region-graph edges, [7] edges given to the host queue
+void ws_last_profile(double* out, int n);
+
 // The agglomeration step alone on a region graph given as host arrays: edges eu[i] < ev[i] (fragment
 // ids 1..n_fragments, every pair at most once, sorted by (eu, ev): the index is the tie-break rank),
 // qsum[i] = sum of the affinities between the two in 32.32 fixed point, count[i] = faces.

@@ -209,7 +209,9 @@ def predict_streamed(
     percentiles need every voxel (exact 1001-bin histogram, accumulated per chunk), then the
     chunks run one after the other exactly like the ranks of ``predict_sharded`` -- each hands the
     partial sums of the planes it shares with the next one forward -- so the result is bit-identical
-    to ``predict``.  Returns ``out``.
+    to ``predict``.  Reading chunk i+1 from the source, computing chunk i (upload, kernels,
+    row-pipelined download) and writing chunk i-1 to the sink overlap (two pinned staging buffers
+    on either side, one reader and one writer thread).  Returns ``out``.
     """
     _check_clip(img, brightness_clip)
     shape = tuple(int(v) for v in img.shape)
@@ -231,11 +233,22 @@ def predict_streamed(
         rows_per_chunk = nz   # planes covered by three rows cannot be handed over pairwise
     stride_z = patch_shape[0] - overlap[0]
 
-    def planes(z0, z1):
-        arr = np.asarray(_as_volume_u16(img[z0:z1], clip))
-        if not arr.flags.writeable:   # e.g. a read-only memory map
-            arr = arr.copy()
-        return torch.from_numpy(arr).to(dev)
+    # Three stages run concurrently (they were sequential in the first version): a reader thread
+    # slices the source into one of two pinned staging buffers, this thread uploads and computes,
+    # and a writer thread stores the previous chunk's planes into the sink.  numpy copies, file
+    # I/O and the engine calls all release the GIL.
+    from concurrent.futures import ThreadPoolExecutor
+
+    step = max(rows_per_chunk * stride_z, 1)
+    plans = [plan_slab(shape, params, r0, min(r0 + rows_per_chunk, nz))
+             for r0 in range(0, nz, rows_per_chunk)]
+    max_in = max([step] + [pl["in_z1"] - pl["in_z0"] for pl in plans])
+    in_host = [torch.empty((max_in, h, w), dtype=torch.uint16).pin_memory() for _ in range(2)]
+
+    def load(z0, z1, k):
+        view = in_host[k][:z1 - z0]
+        np.copyto(view.numpy(), _as_volume_u16(img[z0:z1], clip))
+        return view
 
     def store(z0, z1, host):
         if affinity_mode:
@@ -243,39 +256,57 @@ def predict_streamed(
         else:
             out[z0:z1] = host[0]
 
-    # pass 1: exact global percentiles from per-chunk histograms
-    hist = torch.zeros(clip + 1, dtype=torch.int64, device=dev)
-    step = max(rows_per_chunk * stride_z, 1)
-    for z0 in range(0, d, step):
-        hist += engine.histogram(planes(z0, min(z0 + step, d)), clip)
-    mn, mx = percentiles_from_hist(hist.cpu().numpy().astype(np.uint64), params.pct_lo, params.pct_hi)
-    if nz == 0 or count_patches((1, 1) + shape, patch_shape, overlap) == 0:
-        zero = np.zeros((c, min(step, d), h, w), dtype=np.float32)
-        for z0 in range(0, d, step):
-            store(z0, min(z0 + step, d), zero[:, :min(z0 + step, d) - z0])
-        return out
-    # pass 2: row chunks; the halo of one chunk seeds the next
-    engine.set_normalization(mn, mx, clip)
-    plans = [plan_slab(shape, params, r0, min(r0 + rows_per_chunk, nz))
-             for r0 in range(0, nz, rows_per_chunk)]
-    max_own = max(p["out_z1"] - p["out_z0"] for p in plans)
-    own_dev = torch.empty((c, max_own, h, w), dtype=torch.float32, device=dev)
-    own_host = torch.empty((c, max_own, h, w), dtype=torch.float32).pin_memory()
-    seed = None
-    for i, pl in enumerate(plans):
-        r0 = i * rows_per_chunk
-        r1 = min(r0 + rows_per_chunk, nz)
-        n_own = pl["out_z1"] - pl["out_z0"]
-        n_halo = pl["halo_z1"] - pl["halo_z0"]
-        halo = torch.empty((c, n_halo, h, w), dtype=torch.float32, device=dev) if n_halo > 0 else None
-        slab = planes(pl["in_z0"], pl["in_z1"])
-        # dense (C, n_own, H, W) views of the re-used buffers
-        od = own_dev.view(-1)[:c * n_own * h * w].view(c, n_own, h, w)
-        oh = own_host.view(-1)[:c * n_own * h * w].view(c, n_own, h, w)
-        engine.slab_predict(slab, shape, params, r0, r1, od, oh, halo)
-        engine.slab_finish(seed, od, oh)
-        store(pl["out_z0"], pl["out_z1"], oh.numpy())
-        seed = halo
+    with ThreadPoolExecutor(1) as reader, ThreadPoolExecutor(1) as writer:
+        # pass 1: exact global percentiles from per-chunk histograms
+        hist = torch.zeros(clip + 1, dtype=torch.int64, device=dev)
+        spans = [(z0, min(z0 + step, d)) for z0 in range(0, d, step)]
+        fut = reader.submit(load, spans[0][0], spans[0][1], 0)
+        for i in range(len(spans)):
+            host_in = fut.result()
+            if i + 1 < len(spans):
+                fut = reader.submit(load, spans[i + 1][0], spans[i + 1][1], (i + 1) % 2)
+            hist += engine.histogram(host_in.to(dev, non_blocking=True), clip)
+            torch.cuda.current_stream(dev).synchronize()   # the staging buffer is free again
+        mn, mx = percentiles_from_hist(hist.cpu().numpy().astype(np.uint64), params.pct_lo,
+                                       params.pct_hi)
+        if nz == 0 or count_patches((1, 1) + shape, patch_shape, overlap) == 0:
+            zero = np.zeros((c, min(step, d), h, w), dtype=np.float32)
+            for z0, z1 in spans:
+                store(z0, z1, zero[:, :z1 - z0])
+            return out
+        # pass 2: row chunks; the halo of one chunk seeds the next
+        engine.set_normalization(mn, mx, clip)
+        max_own = max(pl["out_z1"] - pl["out_z0"] for pl in plans)
+        own_dev = torch.empty((c, max_own, h, w), dtype=torch.float32, device=dev)
+        own_host = [torch.empty((c, max_own, h, w), dtype=torch.float32).pin_memory() for _ in range(2)]
+        writes = [None, None]
+        seed = None
+        fut = reader.submit(load, plans[0]["in_z0"], plans[0]["in_z1"], 0)
+        for i, pl in enumerate(plans):
+            r0 = i * rows_per_chunk
+            r1 = min(r0 + rows_per_chunk, nz)
+            n_own = pl["out_z1"] - pl["out_z0"]
+            n_halo = pl["halo_z1"] - pl["halo_z0"]
+            halo = (torch.empty((c, n_halo, h, w), dtype=torch.float32, device=dev)
+                    if n_halo > 0 else None)
+            host_in = fut.result()
+            if i + 1 < len(plans):
+                fut = reader.submit(load, plans[i + 1]["in_z0"], plans[i + 1]["in_z1"], (i + 1) % 2)
+            slab = host_in.to(dev, non_blocking=True)
+            k = i % 2
+            if writes[k] is not None:
+                writes[k].result()        # the writer is done with this host buffer (chunk i-2)
+            # dense (C, n_own, H, W) views of the re-used buffers
+            od = own_dev.view(-1)[:c * n_own * h * w].view(c, n_own, h, w)
+            oh = own_host[k].view(-1)[:c * n_own * h * w].view(c, n_own, h, w)
+            engine.slab_predict(slab, shape, params, r0, r1, od, oh, halo)
+            engine.slab_finish(seed, od, oh)
+            torch.cuda.current_stream(dev).synchronize()
+            writes[k] = writer.submit(store, pl["out_z0"], pl["out_z1"], oh.numpy())
+            seed = halo
+        for wfut in writes:
+            if wfut is not None:
+                wfut.result()
     return out
 
 
@@ -401,7 +432,10 @@ class _EngineSlabBackend:
             _SYMMETRIC_OUTPUTS.clear()   # every rank takes this branch for the same job: collective
             full = symm.empty(*shape, dtype=torch.float32, device=self.device)
             hdl = symm.rendezvous(full, pg)
-            ptrs = [int(p) for r, p in enumerate(hdl.buffer_ptrs) if r != hdl.rank]
+            # peers in ring order starting after this rank: when every rank walks its list in step
+            # (copy-engine gather), no two ranks send to the same destination at the same time
+            n = len(hdl.buffer_ptrs)
+            ptrs = [int(hdl.buffer_ptrs[(hdl.rank + k) % n]) for k in range(1, n)]
             _SYMMETRIC_OUTPUTS[key] = (full, hdl, ptrs)
         return _SYMMETRIC_OUTPUTS[key]
 
@@ -535,8 +569,10 @@ class SlabJob:
 
     def _fused_gather_ready(self):
         """C3 without a gather pass: the output lives in symmetric memory and the stitch kernel
-        stores every finished element to all ranks' copies (exa_set_peer_outputs).  Falls back to
-        the grouped NCCL send/recv gather when the backend has no peer mapping (CPU test backend),
+        stores every finished element to all ranks' copies (exa_set_peer_outputs); with
+        ``EXA_GATHER=ce`` the finished planes travel by copy-engine transfers on side streams
+        instead (no SM time, overlapped with the following waves).  Falls back to the grouped NCCL
+        send/recv gather when the backend has no peer mapping (CPU test backend),
         ``EXA_GATHER=nccl`` is set, or the symmetric-memory rendezvous is not possible here."""
         if self._fused is None:
             self._fused = False

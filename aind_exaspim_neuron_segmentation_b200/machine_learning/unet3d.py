@@ -1,10 +1,11 @@
 """3D U-Net whose forward pass runs in the native sm_100a engine.
 
-Drop-in for reference machine_learning/unet3d.py:16-336 on the configuration
-``inference.load_model`` builds (``trilinear=True, width_multiplier=1``): the
-module tree exists to hold parameters under exactly the reference's
-``state_dict`` names (128 entries), so checkpoints written by
-the reference's Trainer load with ``strict=True`` and vice versa.  The
+Drop-in for reference machine_learning/unet3d.py:16-336: the module tree exists to hold
+parameters under exactly the reference's ``state_dict`` names (128 entries for the
+configuration ``inference.load_model`` builds, ``trilinear=True, width_multiplier=1``;
+SURVEY.md 8a-1), so checkpoints written by the reference's Trainer load with
+``strict=True`` and vice versa.  ``trilinear=False`` (transposed-conv upsampling) and integer
+``width_multiplier`` 1..4 are supported by the engine as well.  The
 arithmetic is not done by these torch modules -- ``forward`` hands the input to
 ``Engine.forward`` (C ABI ``exa_forward``), which folds the eval-mode BatchNorm
 into the convolutions and runs the CUDA kernels.  On a CPU tensor ``forward``
@@ -71,12 +72,17 @@ class Down(nn.Module):
 
 
 class Up(nn.Module):
-    """Trilinear x2 upsample, concat [skip, upsampled], DoubleConv, unet3d.py:215-289."""
+    """x2 upsample (trilinear, or ConvTranspose3d(k=2, s=2) when ``trilinear=False``), concat
+    [skip, upsampled], DoubleConv, unet3d.py:215-289."""
 
-    def __init__(self, in_channels, out_channels):
+    def __init__(self, in_channels, out_channels, trilinear=True):
         super().__init__()
-        self.up = nn.Upsample(scale_factor=2, mode="trilinear", align_corners=True)
-        self.conv = DoubleConv(in_channels, out_channels, mid_channels=in_channels // 2)
+        if trilinear:
+            self.up = nn.Upsample(scale_factor=2, mode="trilinear", align_corners=True)
+            self.conv = DoubleConv(in_channels, out_channels, mid_channels=in_channels // 2)
+        else:
+            self.up = nn.ConvTranspose3d(in_channels, in_channels // 2, kernel_size=2, stride=2)
+            self.conv = DoubleConv(in_channels, out_channels)
 
 
 class OutConv(nn.Module):
@@ -90,20 +96,24 @@ class OutConv(nn.Module):
 class UNet3D(nn.Module):
     """Same constructor and state_dict as the reference ``UNet3D`` (unet3d.py:16-105).
 
-    Only ``trilinear=True, width_multiplier=1`` is implemented natively (that is what
-    ``load_model`` constructs, inference.py:419-420); other values raise.
-    ``precision`` selects the engine arithmetic: ``"bf16"`` (tcgen05 tensor cores, fp32
+    ``load_model`` constructs ``trilinear=True, width_multiplier=1`` (inference.py:419-420), the
+    configuration the kernels are tuned for.  ``trilinear=False`` and ``width_multiplier`` 2, 3, 4
+    run on the same engine (generic tcgen05 conv kernel where the tuned ones do not fit, a SIMT
+    transposed conv, the head as a kernel of its own above 32 channels).  Widths that make a
+    channel count a non-multiple of 32 (fractional multipliers) raise: the tensor-core kernels
+    work in 32-channel slices.  ``precision`` selects the engine arithmetic: ``"bf16"`` (tcgen05 tensor cores, fp32
     accumulation) or ``"fp32"`` (validation mode).
     """
 
     def __init__(self, output_channels=1, trilinear=True, width_multiplier=1, precision="bf16"):
         super().__init__()
-        if not trilinear or width_multiplier != 1:
+        c = [int(w * width_multiplier) for w in _WIDTHS]    # unet3d.py:60
+        if c[0] not in (32, 64, 96, 128) or c != [c[0] << k for k in range(5)]:
             raise NotImplementedError(
-                "the B200 engine implements the load_model configuration only "
-                "(trilinear=True, width_multiplier=1)"
+                f"width_multiplier={width_multiplier} gives channels {c}: the B200 engine needs "
+                "32, 64, 96 or 128 channels in the first block (width_multiplier 1, 2, 3 or 4)"
             )
-        c = list(_WIDTHS)
+        factor = 2 if trilinear else 1
         self.channels = c
         self.trilinear = trilinear
         self.precision = precision
@@ -111,11 +121,11 @@ class UNet3D(nn.Module):
         self.down1 = Down(c[0], c[1])
         self.down2 = Down(c[1], c[2])
         self.down3 = Down(c[2], c[3])
-        self.down4 = Down(c[3], c[4] // 2)
-        self.up1 = Up(c[4], c[3] // 2)
-        self.up2 = Up(c[3], c[2] // 2)
-        self.up3 = Up(c[2], c[1] // 2)
-        self.up4 = Up(c[1], c[0])
+        self.down4 = Down(c[3], c[4] // factor)
+        self.up1 = Up(c[4], c[3] // factor, trilinear)
+        self.up2 = Up(c[3], c[2] // factor, trilinear)
+        self.up3 = Up(c[2], c[1] // factor, trilinear)
+        self.up4 = Up(c[1], c[0], trilinear)
         self.outc = OutConv(c[0], output_channels)
 
     def engine(self, precision=None):

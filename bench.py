@@ -359,13 +359,14 @@ def sharded_parity_check(model, dev, rank, world):
     backend = _EngineSlabBackend(model.engine("bf16"))
     same, modes = True, []
     saved = os.environ.get("EXA_GATHER")
-    for gather_env in ("", "nccl"):
+    for gather_env in ("", "ce", "nccl"):
         os.environ["EXA_GATHER"] = gather_env
         job = SlabJob(PARITY_SHAPE, params, 3, backend)
         for _ in range(2):   # the second run overwrites the peers' previous result in place
             full = job.run(job.upload(vol), gather=True)
             same = same and bool(np.array_equal(full.cpu().numpy(), single))
-        modes.append("fused peer-store" if job._fused else "nccl send/recv")
+        modes.append(("copy-engine peer copies" if gather_env == "ce" else "fused peer-store")
+                     if job._fused else "nccl send/recv")
         z0, z1 = job.own_bounds()
         host_own = torch.empty((3, z1 - z0) + PARITY_SHAPE[1:], dtype=torch.float32).pin_memory()
         job.run_pipelined(job.upload(vol), host_own)
@@ -395,6 +396,129 @@ def sharded_parity_check(model, dev, rank, world):
     dist.barrier()
     return out
 
+
+
+# --- config 5: predict -> affinities_to_segmentation -----------------------
+SEG_THRESHOLDS = [0.6, 0.8, 0.9]      # reference defaults (inference.py:198-199)
+SEG_MIN_SIZE = 100
+
+
+def ws_profile():
+    import ctypes
+
+    from aind_exaspim_neuron_segmentation_b200 import _native
+
+    buf = (ctypes.c_double * 8)()
+    _native.check(_native.lib().exa_ws_last_profile(buf, 8), None, "exa_ws_last_profile")
+    v = list(buf)
+    return {"fragments_ms": v[0], "region_graph_ms": v[1], "parallel_rounds_ms": v[2],
+            "host_queue_ms": v[3], "sizes_relabel_ms": v[4], "parallel_rounds": int(v[5]),
+            "region_edges": int(v[6]), "edges_to_host_queue": int(v[7])}
+
+
+def run_segment(args):
+    """`--workload segment`: BASELINE config 5 on one GPU.  predict() on the synthetic volume
+    (`--volume` edge, default 512), then a step = affinities_to_segmentation on the affinities.
+    `value`: voxels/s with the float32 affinities resident in HBM (label volume left in HBM);
+    `e2e`: host float32 affinities in -> host uint64 labels out through the public call;
+    `cpu_baseline`: the compiled restatement of waterz (oracle/ws_ref.cpp, one core) on a 128^3
+    corner of the same affinities, whose labels the product must reproduce exactly
+    (`parity_check`); `adapted_rand`: the product's segmentation of its bf16 affinities against
+    its segmentation of the FP32-validation-mode affinities (north_star: >= 0.99)."""
+    import torch
+
+    from aind_exaspim_neuron_segmentation_b200 import UNet3D, affinities_to_segmentation, predict
+    from oracle.unet_ref import rescaled_state_dict  # weights recipe only (seeded random init)
+
+    torch.cuda.set_device(0)
+    edge = args.volume or 512
+    shape = (edge,) * 3
+    model = UNet3D(output_channels=3)
+    model.load_state_dict(rescaled_state_dict(0), strict=True)
+    model = model.cuda().eval()
+    vol = synth_planes(shape, 0, edge)
+    t0 = time.perf_counter()
+    aff = predict(vol, model, verbose=False, patch_shape=PATCH, overlap=OVERLAP, trim=TRIM)
+    predict_s = time.perf_counter() - t0
+    dev = torch.from_numpy(aff).cuda()
+    voxels = float(edge) ** 3
+
+    def step():
+        return affinities_to_segmentation(dev, SEG_THRESHOLDS, SEG_MIN_SIZE)
+
+    for _ in range(max(args.warmup, 1)):
+        seg = step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    phases = []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        seg = step()
+        phases.append(ws_profile())
+    torch.cuda.synchronize()
+    sec = (time.perf_counter() - t0) / args.steps
+    clocks = sampler.stop()
+    n_segments = int(seg.max().item())
+    frags = affinities_to_segmentation(dev, [0.0], 0)
+    n_fragments = int(frags.max().item())
+    del frags
+
+    # e2e: numpy in, numpy out
+    affinities_to_segmentation(aff, SEG_THRESHOLDS, SEG_MIN_SIZE)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        seg_host = affinities_to_segmentation(aff, SEG_THRESHOLDS, SEG_MIN_SIZE)
+    e2e_sec = (time.perf_counter() - t0) / args.steps
+    same = bool(np.array_equal(seg_host.astype(np.int64), seg.cpu().numpy()))
+
+    line = {
+        "metric": "segmentation voxels/sec", "value": voxels / sec, "unit": "voxels/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 fixed point",
+        "data": "synthetic",
+        "config": {"workload": f"affinities_to_segmentation(predict(synthetic {edge}^3 uint16 volume)), "
+                               f"thresholds {SEG_THRESHOLDS}, min_segment_size {SEG_MIN_SIZE}",
+                   "volume": list(shape), "n_fragments": n_fragments, "n_segments": n_segments,
+                   "predict_s": predict_s,
+                   "l2": "12 B of affinities per voxel (1.6 GB at 512^3) are far larger than the L2"},
+        "e2e": {"value": voxels / e2e_sec, "unit": "voxels/s", "ms_per_step": e2e_sec * 1e3,
+                "h2d_bytes_per_step": int(voxels) * 12, "d2h_bytes_per_step": int(voxels) * 8,
+                "equal_to_device_path": same,
+                "note": "numpy float32 (3,D,H,W) in -> numpy uint64 (D,H,W) out (pageable buffers)"},
+        "gpu_launches": None,
+        "phases_last_step": phases[-1],
+        "clocks": clocks,
+    }
+    # wall share of the host queue: what bounds this row (DESIGN.md K7)
+    line["roofline"] = {"bound": "host queue / hbm", "achieved": None, "peak": None, "unit": "GB/s",
+                        "frac": None, "traffic": None,
+                        "note": "the voxel-sized kernels are HBM-class work; the step is bounded by "
+                                "the sequential tail of the merge queue (host_queue_ms)"}
+    if not args.no_cpu:
+        from oracle.watershed_ref import adapted_rand_agreement, affinities_to_segmentation_ref
+
+        c = min(128, edge)
+        corner = np.ascontiguousarray(aff[:, :c, :c, :c])
+        t0 = time.perf_counter()
+        ref = affinities_to_segmentation_ref(corner, SEG_THRESHOLDS, SEG_MIN_SIZE)
+        cpu_s = time.perf_counter() - t0
+        got = affinities_to_segmentation(corner, SEG_THRESHOLDS, SEG_MIN_SIZE).astype(np.int64)
+        line["cpu_baseline"] = {"value": c ** 3 / cpu_s, "unit": "voxels/s", "cores": 1, "kind": "port",
+                                "sample": f"oracle/ws_ref.cpp (compiled restatement of waterz) on the "
+                                          f"{c}^3 corner of the same affinities, {cpu_s:.2f} s"}
+        line["parity_check"] = {"labels_identical_to_oracle": bool(np.array_equal(got, ref)),
+                                "volume": [c, c, c], "n_segments": int(ref.max())}
+        # config 5's agreement: bf16 vs FP32-validation affinities through the same segmentation
+        aff32 = predict(vol, model, verbose=False, patch_shape=PATCH, overlap=OVERLAP, trim=TRIM,
+                        precision="fp32")
+        seg32 = affinities_to_segmentation(torch.from_numpy(aff32).cuda(), SEG_THRESHOLDS, SEG_MIN_SIZE)
+        line["adapted_rand"] = {
+            "agreement": adapted_rand_agreement(seg.cpu().numpy(), seg32.cpu().numpy()),
+            "max_abs_affinity_diff": float(np.abs(aff - aff32).max()),
+            "what": "segmentation of the bf16 affinities vs segmentation of the FP32-validation "
+                    "affinities (both by the product), ignoring voxels that are background in the latter"}
+    emit(line)
 
 # --- B200 arm ------------------------------------------------------------------------------
 def run_b200(args):
@@ -679,8 +803,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference", "library"])
     ap.add_argument("--batch", type=int, default=32, help="patches per wave")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--volume", type=int, default=0, choices=[0, 512, 1024],
+    ap.add_argument("--volume", type=int, default=0, choices=[0, 256, 512, 1024],
                     help="fix the volume at N^3 for every --gpus (strong scaling); 0 = N x 512^3 (weak)")
+    ap.add_argument("--workload", default="predict", choices=["predict", "segment"],
+                    help="predict = the headline hot path; segment = BASELINE config 5 (predict, then "
+                         "affinities_to_segmentation timed; one GPU)")
     ap.add_argument("--patch", type=int, default=96, choices=[96, 128],
                     help="patch edge: 96 = the headline workload; 128 = BASELINE config 4 (not a bench line)")
     args = ap.parse_args()
@@ -694,7 +821,9 @@ def main():
     PATCH = (args.patch,) * 3
     STRONG_VOLUME = args.volume
     capture_stdout()
-    if args.impl == "reference":
+    if args.workload == "segment":
+        run_segment(args)
+    elif args.impl == "reference":
         run_reference(args)
     elif args.impl == "library":
         run_library_bar(args)

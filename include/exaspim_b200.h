@@ -177,6 +177,12 @@ int exa_affinities_to_segmentation_device(const float* aff_dev, int D, int H, in
                                           int64_t min_segment_size, uint64_t* seg_dev,
                                           int64_t* n_fragments, int64_t* n_segments, void* stream);
 
+/* measurement (no reference analogue): wall milliseconds of the phases of the last
+ * exa_affinities_to_segmentation[_device] call of this process -- [0] fragments, [1] region graph,
+ * [2] parallel agglomeration rounds, [3] host queue, [4] sizes + relabel -- then counts:
+ * [5] parallel rounds, [6] region-graph edges, [7] edges handed to the host queue.  n <= 8. */
+int exa_ws_last_profile(double* out, int n);
+
 /* the agglomeration step of the function above on its own, on a region graph in host arrays:
  * edges eu[i] < ev[i] (fragment ids 1..n_fragments, each pair once, sorted by (eu, ev) -- the index
  * is the tie-break rank), qsum[i] = sum of the affinities on the faces between the two fragments in

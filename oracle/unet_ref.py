@@ -75,8 +75,14 @@ def unet_forward(x, sd, emulate_bf16=False):
             skips.append(h)
         skips.pop()  # x5 is not a skip
         for i, (prefix, _) in enumerate(BLOCKS[5:]):
-            # unet3d.py:248-250 (trilinear, align_corners=True) and :288 (cat [skip, upsampled])
-            up = F.interpolate(h, scale_factor=2, mode="trilinear", align_corners=True)
+            # unet3d.py:248-250 (trilinear, align_corners=True) or :254-256 (ConvTranspose3d k=2 s=2
+            # when the model was built with trilinear=False), and :288 (cat [skip, upsampled])
+            up_w = sd.get(f"up{i + 1}.up.weight")
+            if up_w is None:
+                up = F.interpolate(h, scale_factor=2, mode="trilinear", align_corners=True)
+            else:
+                w = _bf16(up_w.float()) if emulate_bf16 else up_w.float()
+                up = F.conv_transpose3d(h, w, sd[f"up{i + 1}.up.bias"].float(), stride=2)
             if emulate_bf16:
                 up = _bf16(up)
             h = torch.cat([skips.pop(), up], dim=1)
@@ -93,8 +99,9 @@ def make_forward_fn(sd, emulate_bf16=False):
     return fn
 
 
-def rescaled_state_dict(seed, out_channels=3):
-    """'Well-scaled' random-init weights of the reference architecture (SURVEY.md 8c caveat).
+def rescaled_state_dict(seed, out_channels=3, trilinear=True, width_multiplier=1):
+    """'Well-scaled' random-init weights of the reference architecture (SURVEY.md 8c caveat), for
+    any constructor arguments of REF/machine_learning/unet3d.py:37-75.
 
     PyTorch's default init collapses activations (logits std ~0.13) and leaves BatchNorm an
     identity, which hides deep-layer and BN-folding bugs.  This builds a state_dict with the
@@ -103,17 +110,28 @@ def rescaled_state_dict(seed, out_channels=3):
     """
     gen = torch.Generator().manual_seed(seed)
     sd = {}
+    c = [int(w * width_multiplier) for w in (32, 64, 128, 256, 512)]
+    f = 2 if trilinear else 1
+
+    def up(cin, cout):   # DoubleConv of an Up block: mid = in/2 with trilinear, = out otherwise
+        return (cin, cin // 2 if trilinear else cout, cout)
+
     chans = {
-        "inc.double_conv": (1, 32, 32),
-        "down1.maxpool_conv.1.double_conv": (32, 64, 64),
-        "down2.maxpool_conv.1.double_conv": (64, 128, 128),
-        "down3.maxpool_conv.1.double_conv": (128, 256, 256),
-        "down4.maxpool_conv.1.double_conv": (256, 256, 256),
-        "up1.conv.double_conv": (512, 256, 128),
-        "up2.conv.double_conv": (256, 128, 64),
-        "up3.conv.double_conv": (128, 64, 32),
-        "up4.conv.double_conv": (64, 32, 32),
+        "inc.double_conv": (1, c[0], c[0]),
+        "down1.maxpool_conv.1.double_conv": (c[0], c[1], c[1]),
+        "down2.maxpool_conv.1.double_conv": (c[1], c[2], c[2]),
+        "down3.maxpool_conv.1.double_conv": (c[2], c[3], c[3]),
+        "down4.maxpool_conv.1.double_conv": (c[3], c[4] // f, c[4] // f),
+        "up1.conv.double_conv": up(c[4], c[3] // f),
+        "up2.conv.double_conv": up(c[3], c[2] // f),
+        "up3.conv.double_conv": up(c[2], c[1] // f),
+        "up4.conv.double_conv": up(c[1], c[0]),
     }
+    if not trilinear:
+        for i, cin in enumerate((c[4], c[3], c[2], c[1])):
+            # ConvTranspose3d(k=2, s=2): every output voxel sees cin inputs once
+            sd[f"up{i + 1}.up.weight"] = torch.randn((cin, cin // 2, 2, 2, 2), generator=gen) / cin ** 0.5
+            sd[f"up{i + 1}.up.bias"] = torch.randn((cin // 2,), generator=gen) * 0.1
     for prefix, (cin, mid, cout) in chans.items():
         for conv_idx, bn_idx, ci, co in ((0, 1, cin, mid), (3, 4, mid, cout)):
             fan_in = ci * 27
@@ -125,6 +143,6 @@ def rescaled_state_dict(seed, out_channels=3):
             sd[f"{prefix}.{bn_idx}.running_mean"] = torch.randn((co,), generator=gen) * 0.1
             sd[f"{prefix}.{bn_idx}.running_var"] = torch.rand((co,), generator=gen) * 1.5 + 0.5
             sd[f"{prefix}.{bn_idx}.num_batches_tracked"] = torch.tensor(0, dtype=torch.int64)
-    sd["outc.conv.weight"] = torch.randn((out_channels, 32, 1, 1, 1), generator=gen) * (1.0 / 32 ** 0.5)
+    sd["outc.conv.weight"] = torch.randn((out_channels, c[0], 1, 1, 1), generator=gen) * (1.0 / c[0] ** 0.5)
     sd["outc.conv.bias"] = torch.randn((out_channels,), generator=gen) * 0.1
     return sd

@@ -63,6 +63,14 @@ CASES = {
     # BASELINE config 4: one full 128^3 patch through the reference
     "p128_single": ((128, 128, 128), 7, ("rescaled", 5),
                     dict(patch_shape=(128, 128, 128), overlap=(32, 32, 32), trim=8)),
+    # round 2: the constructor's other arguments (unet3d.py:37): weights kind
+    # "rescaled/<trilinear>/<width_multiplier>" builds UNet3D(3, trilinear, width_multiplier)
+    "variant_convT": ((48, 56, 40), 8, ("rescaled/0/1", 6),
+                      dict(patch_shape=(32, 32, 32), overlap=(8, 8, 8), trim=4)),
+    "variant_w2": ((48, 56, 40), 8, ("rescaled/1/2", 6),
+                   dict(patch_shape=(32, 32, 32), overlap=(8, 8, 8), trim=4)),
+    "variant_convT_w2": ((48, 56, 40), 8, ("rescaled/0/2", 6),
+                         dict(patch_shape=(32, 32, 32), overlap=(8, 8, 8), trim=4)),
 }
 
 
@@ -108,6 +116,11 @@ def main():
         if wkind == "default":
             torch.manual_seed(wseed)
             model = UNet3D(output_channels=3).eval()
+        elif wkind.startswith("rescaled/"):
+            tri, width = (int(v) for v in wkind.split("/")[1:])
+            model = UNet3D(output_channels=3, trilinear=bool(tri), width_multiplier=width)
+            model.load_state_dict(rescaled_state_dict(wseed, 3, bool(tri), width), strict=True)
+            model.eval()
         else:
             model = UNet3D(output_channels=3)
             model.load_state_dict(rescaled_state_dict(wseed), strict=True)

@@ -44,6 +44,9 @@ def state_dict_for(kind, seed, out_channels=3):
 
     if kind == "rescaled":
         return rescaled_state_dict(seed, out_channels)
+    if kind.startswith("rescaled/"):   # "rescaled/<trilinear>/<width_multiplier>"
+        tri, width = (int(v) for v in kind.split("/")[1:])
+        return rescaled_state_dict(seed, out_channels, bool(tri), width)
     from aind_exaspim_neuron_segmentation_b200.machine_learning.unet3d import UNet3D
 
     torch.manual_seed(seed)

@@ -2,7 +2,8 @@
 
 Every rank computes the single-GPU result itself (small volume) and checks that the sharded
 forms are bit-identical to it: the fused peer-store gather (symmetric memory + stitch kernel
-stores to all ranks' copies), the grouped NCCL send/recv gather, and the row-pipelined
+stores to all ranks' copies), its copy-engine form (EXA_GATHER=ce), the grouped NCCL send/recv
+gather, and the row-pipelined
 ``run_pipelined`` / ``predict_sharded(gather=False)`` with host buffers.
 """
 
@@ -40,13 +41,13 @@ def main():
     params = _native.make_params(kw["patch_shape"], kw["overlap"], kw["trim"], 1000, (1, 99.9), batch=7)
     backend = _EngineSlabBackend(model.engine("bf16"))
     modes = []
-    for gather_env in ("", "nccl"):
+    for gather_env in ("", "ce", "nccl"):
         os.environ["EXA_GATHER"] = gather_env
         job = SlabJob(shape, params, 3, backend)
         for step in range(2):   # twice: the second run overwrites the peers' previous result
             full = job.run(job.upload(vol), gather=True)
             assert np.array_equal(full.cpu().numpy(), single), (gather_env, step, rank)
-        modes.append("fused" if job._fused else "nccl")
+        modes.append(("ce" if gather_env == "ce" else "fused") if job._fused else "nccl")
         z0, z1 = job.own_bounds()
         host = torch.empty((3, z1 - z0) + shape[1:], dtype=torch.float32).pin_memory()
         own = job.run_pipelined(job.upload(vol), host)

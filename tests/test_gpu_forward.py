@@ -92,3 +92,62 @@ def test_module_forward_and_error_paths():
     n0 = model.engine().launch_count
     model(x.cuda())
     assert model.engine().launch_count > n0
+
+
+# --- model variants (unet3d.py:37,56-74,254-258) ------------------------------
+VARIANTS = [(False, 1), (True, 2), (False, 2)]
+
+
+@pytest.mark.parametrize("trilinear,width", VARIANTS)
+def test_variant_forward_matches_oracle(trilinear, width):
+    """trilinear=False (ConvTranspose3d upsampling) and width_multiplier=2 against the oracle, whose
+    variant path equals the reference modules exactly (tests/test_oracle_golden.py)."""
+    from oracle.unet_ref import rescaled_state_dict
+
+    sd = rescaled_state_dict(8, 3, trilinear, width)
+    torch.manual_seed(3)
+    x = torch.rand(2, 1, 32, 48, 32)
+    ref = _oracle(x, sd)
+    y32 = _engine(sd, "fp32").forward(x.cuda()).cpu()
+    assert y32.shape == ref.shape
+    err32 = (y32 - ref).abs().max().item()
+    assert err32 <= FP32_LOGIT_TOL, err32
+    assert (torch.sigmoid(y32) - torch.sigmoid(ref)).abs().max().item() <= 1e-4
+    y16 = _engine(sd, "bf16").forward(x.cuda()).cpu()
+    emu = _oracle(x, sd, emulate=True)
+    err_ref = (torch.sigmoid(y16) - torch.sigmoid(ref)).abs().max().item()
+    err_emu = (y16 - emu).abs().max().item()
+    print("variant", trilinear, width, "fp32 err", err32, "bf16 sigmoid err", err_ref, "vs emulation", err_emu)
+    assert err_ref <= 1e-2, (err_ref, err_emu)
+    assert err_emu <= 3e-2, err_emu
+
+
+@pytest.mark.parametrize("trilinear,width", VARIANTS)
+def test_variant_module_predict_matches_oracle(trilinear, width):
+    """The module constructor with the reference's arguments, strict state_dict loading in both
+    directions' key layout, and predict() end to end (trimmed regions, unfused head)."""
+    from aind_exaspim_neuron_segmentation_b200 import UNet3D, predict
+    from helpers import lightsheet_volume
+    from oracle.predict_ref import predict_ref
+    from oracle.unet_ref import make_forward_fn, rescaled_state_dict
+
+    sd = rescaled_state_dict(9, 3, trilinear, width)
+    model = UNet3D(output_channels=3, trilinear=trilinear, width_multiplier=width)
+    assert set(model.state_dict()) == set(sd)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().eval()
+    vol = lightsheet_volume((48, 56, 40), 10)
+    kw = dict(patch_shape=(32, 32, 32), overlap=(8, 8, 8), trim=4)
+    out = predict(vol, model, verbose=False, **kw)
+    ref = predict_ref(vol, make_forward_fn(sd), **kw)
+    err = float(np.abs(out - ref).max())
+    assert out.shape == ref.shape and err <= 1e-2, err
+    assert np.array_equal(out == 0, ref == 0)
+
+
+def test_unsupported_widths_raise():
+    from aind_exaspim_neuron_segmentation_b200 import UNet3D
+
+    for wm in (0.5, 1.5, 8):
+        with pytest.raises(NotImplementedError):
+            UNet3D(output_channels=3, width_multiplier=wm)

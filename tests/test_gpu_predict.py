@@ -16,7 +16,11 @@ FP32_TOL = 1e-4   # north_star: FP32 validation mode
 def _model(kind, seed, precision="bf16", out_channels=3):
     from aind_exaspim_neuron_segmentation_b200 import UNet3D
 
-    m = UNet3D(output_channels=out_channels, precision=precision)
+    tri, width = True, 1
+    if kind.startswith("rescaled/"):   # "rescaled/<trilinear>/<width_multiplier>" (make_golden.py)
+        tri, width = (int(v) for v in kind.split("/")[1:])
+    m = UNet3D(output_channels=out_channels, trilinear=bool(tri), width_multiplier=width,
+               precision=precision)
     m.load_state_dict(state_dict_for(kind, seed, out_channels), strict=True)
     return m.cuda().eval()
 
@@ -30,7 +34,8 @@ def _kwargs(meta):
 
 
 @pytest.mark.parametrize("name", ["c1_default_96", "c1_rescaled_96", "mixed_160x160x100", "small_p32",
-                                  "small_p48_trim0ish", "multireflect_p32", "p128_single"])
+                                  "small_p48_trim0ish", "multireflect_p32", "p128_single",
+                                  "variant_convT", "variant_w2", "variant_convT_w2"])
 @pytest.mark.parametrize("precision", ["bf16", "fp32"])
 def test_predict_matches_reference_golden(golden_meta, name, precision):
     from aind_exaspim_neuron_segmentation_b200 import predict

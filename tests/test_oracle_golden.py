@@ -20,7 +20,7 @@ def _run_oracle(meta):
 
 
 @pytest.mark.parametrize("name", ["small_p32", "small_p48_trim0ish", "c1_rescaled_96", "multireflect_p32",
-                                  "p128_single"])
+                                  "p128_single", "variant_convT", "variant_w2", "variant_convT_w2"])
 def test_oracle_matches_reference_golden(golden_meta, name):
     out = _run_oracle(golden_meta["cases"][name])
     # same fp32 arithmetic (torch CPU conv) -> only thread-count dependent reduction order differs
@@ -78,3 +78,23 @@ def test_sub_block_extensions_reproduce_the_full_run():
     part = pr.predict_ref(corner, make_forward_fn(sd), norm_range=(mn, mx), only_starts=sel, **kw)
     # voxels covered by the selected windows only: z < 48 + 4 (next z window starts at 48), x < 24 + 4
     assert np.array_equal(part[:, :52, :, :28], full[:, :52, :, :28])
+
+
+def test_variant_state_dict_layout_matches_module():
+    """trilinear=False / width_multiplier variants: the product module, the oracle's weight recipe
+    and (checked when the goldens were made: tests/golden/make_golden.py variants) the reference
+    module agree on keys and shapes."""
+    import pytest
+
+    from aind_exaspim_neuron_segmentation_b200 import UNet3D
+    from oracle.unet_ref import rescaled_state_dict
+
+    for trilinear, width in ((True, 1), (False, 1), (True, 2), (False, 2), (True, 4)):
+        sd = rescaled_state_dict(1, 3, trilinear, width)
+        model = UNet3D(output_channels=3, trilinear=trilinear, width_multiplier=width)
+        own = model.state_dict()
+        assert set(own) == set(sd) and len(sd) == (128 if trilinear else 136)
+        assert all(tuple(own[k].shape) == tuple(sd[k].shape) for k in sd)
+        model.load_state_dict(sd, strict=True)
+    with pytest.raises(NotImplementedError):
+        UNet3D(output_channels=3, width_multiplier=0.5)
