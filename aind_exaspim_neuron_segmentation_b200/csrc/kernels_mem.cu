@@ -593,34 +593,45 @@ upsample2_bf16_kernel(const __nv_bfloat16* __restrict__ in, int in_cstride, int 
 // interpolates it in x and y (4 output pixels) and blends it with the two previous planes'
 // results into two output planes: 9 loads and ~150 packed FMAs per 8 output voxels instead of 27
 // loads and ~230, and the z neighbours never leave registers.
+// NJ = channel pairs per thread: 4 (8 channels, 16-byte accesses) or 2 (4 channels, 8-byte accesses:
+// about half the registers, twice the resident warps).
+template <int NJ>
 struct PlaneXY {
-  f32x2 v[2][2][4];  // [y out][x out][channel pair]
+  f32x2 v[2][2][NJ];  // [y out][x out][channel pair]
 };
+template <int NJ>
 struct PlaneLoads {
-  uint4 q[3][3];
+  uint32_t q[3][3][NJ];
 };
+template <int NJ>
 __device__ __forceinline__ void upsample_load(const __nv_bfloat16* __restrict__ plane_base,
-                                              const int (&off)[3][3], PlaneLoads& l) {
+                                              const int (&off)[3][3], PlaneLoads<NJ>& l) {
 #pragma unroll
   for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-    for (int dx = 0; dx < 3; ++dx)
-      l.q[dy][dx] = *reinterpret_cast<const uint4*>(plane_base + off[dy][dx]);
+    for (int dx = 0; dx < 3; ++dx) {
+      if (NJ == 4) {
+        const uint4 t = *reinterpret_cast<const uint4*>(plane_base + off[dy][dx]);
+        l.q[dy][dx][0] = t.x; l.q[dy][dx][1] = t.y; l.q[dy][dx][NJ - 2] = t.z; l.q[dy][dx][NJ - 1] = t.w;
+      } else {
+        const uint2 t = *reinterpret_cast<const uint2*>(plane_base + off[dy][dx]);
+        l.q[dy][dx][0] = t.x; l.q[dy][dx][1] = t.y;
+      }
+    }
 }
-__device__ __forceinline__ void upsample_plane_xy(const PlaneLoads& l, const AxisTaps& ty,
-                                                  const AxisTaps& tx, PlaneXY& o) {
+template <int NJ>
+__device__ __forceinline__ void upsample_plane_xy(const PlaneLoads<NJ>& l, const AxisTaps& ty,
+                                                  const AxisTaps& tx, PlaneXY<NJ>& o) {
   const f32x2 zero = f2_pack(0.f, 0.f);
   const f32x2 xa0 = f2_pack(tx.a0, tx.a0), xa1 = f2_pack(tx.a1, tx.a1);
   const f32x2 xb0 = f2_pack(tx.b0, tx.b0), xb1 = f2_pack(tx.b1, tx.b1);
-  f32x2 pxa[3][4], pxb[3][4];  // x-interpolated rows: output 2xj / 2xj+1
+  f32x2 pxa[3][NJ], pxb[3][NJ];  // x-interpolated rows: output 2xj / 2xj+1
 #pragma unroll
   for (int dy = 0; dy < 3; ++dy) {
-    const uint32_t w0[4] = {l.q[dy][0].x, l.q[dy][0].y, l.q[dy][0].z, l.q[dy][0].w};
-    const uint32_t w1[4] = {l.q[dy][1].x, l.q[dy][1].y, l.q[dy][1].z, l.q[dy][1].w};
-    const uint32_t w2[4] = {l.q[dy][2].x, l.q[dy][2].y, l.q[dy][2].z, l.q[dy][2].w};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const f32x2 f0 = bf16x2_to_f2(w0[j]), f1 = bf16x2_to_f2(w1[j]), f2 = bf16x2_to_f2(w2[j]);
+    for (int j = 0; j < NJ; ++j) {
+      const f32x2 f0 = bf16x2_to_f2(l.q[dy][0][j]), f1 = bf16x2_to_f2(l.q[dy][1][j]),
+                  f2 = bf16x2_to_f2(l.q[dy][2][j]);
       pxa[dy][j] = f2_fma(xa1, f1, f2_fma(xa0, f0, zero));
       pxb[dy][j] = f2_fma(xb1, f2, f2_fma(xb0, f1, zero));
     }
@@ -628,7 +639,7 @@ __device__ __forceinline__ void upsample_plane_xy(const PlaneLoads& l, const Axi
   const f32x2 ya0 = f2_pack(ty.a0, ty.a0), ya1 = f2_pack(ty.a1, ty.a1);
   const f32x2 yb0 = f2_pack(ty.b0, ty.b0), yb1 = f2_pack(ty.b1, ty.b1);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < NJ; ++j) {
     o.v[0][0][j] = f2_fma(ya1, pxa[1][j], f2_fma(ya0, pxa[0][j], zero));
     o.v[0][1][j] = f2_fma(ya1, pxb[1][j], f2_fma(ya0, pxb[0][j], zero));
     o.v[1][0][j] = f2_fma(yb1, pxa[2][j], f2_fma(yb0, pxa[1][j], zero));
@@ -640,16 +651,18 @@ __device__ __forceinline__ void upsample_plane_xy(const PlaneLoads& l, const Axi
 // a1(j)*p[j], output 2j+1 = b0(j)*p[j] + b1(j)*p[j+1] (indices clamped).  So only TWO
 // x/y-interpolated planes are live: when plane j+1 arrives, outputs 2j+1 and 2j+2 are emitted
 // from (p[j], p[j+1]).  The loads of plane j+2 are issued before that blend, so their latency
-// hides behind ~100 packed FMAs and eight stores.
-__global__ void __launch_bounds__(128)
+// hides behind the packed FMAs and the stores.
+template <int NJ>
+__global__ void __launch_bounds__(128, NJ == 2 ? 5 : 3)
 upsample_march_bf16_kernel(const __nv_bfloat16* __restrict__ in, int in_cstride, int in_coff,
                            __nv_bfloat16* __restrict__ out, int out_cstride, int out_coff, int Di,
                            int Hi, int Wi, int C, const ConvRegion rg, int jz0, int jy0, int jx0,
                            int njz, int njy, int njx) {
-  const unsigned cv = (unsigned)C / 8;
+  constexpr int CPT = 2 * NJ;  // channels per thread
+  const unsigned cv = (unsigned)C / CPT;
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (unsigned)njy * njx * cv) return;
-  const int c8 = (int)(i % cv);
+  const int cg = (int)(i % cv);
   const unsigned v = i / cv;
   const int xj = jx0 + (int)(v % (unsigned)njx);
   const int yj = jy0 + (int)(v / (unsigned)njx);
@@ -676,12 +689,12 @@ upsample_march_bf16_kernel(const __nv_bfloat16* __restrict__ in, int in_cstride,
     }
   const size_t in_plane = (size_t)Hi * Wi * in_cstride;
   const size_t out_plane = (size_t)Ho * Wo * out_cstride;
-  const __nv_bfloat16* ibase = in + in_coff + 8 * c8 + (size_t)b * Di * in_plane;
-  __nv_bfloat16* obase = out + out_coff + 8 * c8 + (size_t)b * Do * out_plane;
+  const __nv_bfloat16* ibase = in + in_coff + CPT * cg + (size_t)b * Di * in_plane;
+  __nv_bfloat16* obase = out + out_coff + CPT * cg + (size_t)b * Do * out_plane;
   const f32x2 zero = f2_pack(0.f, 0.f);
 
   // one output plane zo = w_lo * lo + w_hi * hi, stored for the (up to) four pixels of the column
-  auto emit = [&](int zo, float w_lo, float w_hi, const PlaneXY& lo, const PlaneXY& hi) {
+  auto emit = [&](int zo, float w_lo, float w_hi, const PlaneXY<NJ>& lo, const PlaneXY<NJ>& hi) {
     if (zo < rg.lo[0] || zo >= rg.hi[0]) return;
     const f32x2 wl = f2_pack(w_lo, w_lo), wh = f2_pack(w_hi, w_hi);
     __nv_bfloat16* oplane = obase + (size_t)zo * out_plane;
@@ -690,34 +703,37 @@ upsample_march_bf16_kernel(const __nv_bfloat16* __restrict__ in, int in_cstride,
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         if (!ok[bb][c]) continue;
-        uint32_t o[4];
+        uint32_t o[NJ];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < NJ; ++j) {
           const f32x2 r = f2_fma(wh, hi.v[bb][c][j], f2_fma(wl, lo.v[bb][c][j], zero));
           float a, d;
           f2_unpack(r, a, d);
           o[j] = pack_bf16x2(a, d);
         }
-        *reinterpret_cast<uint4*>(oplane + ooff[bb][c]) = make_uint4(o[0], o[1], o[2], o[3]);
+        if (NJ == 4)
+          *reinterpret_cast<uint4*>(oplane + ooff[bb][c]) = make_uint4(o[0], o[1], o[NJ - 2], o[NJ - 1]);
+        else
+          *reinterpret_cast<uint2*>(oplane + ooff[bb][c]) = make_uint2(o[0], o[1]);
       }
   };
 
-  PlaneLoads ld;
-  PlaneXY pc, pn;  // interpolated planes zj and zj+1
+  PlaneLoads<NJ> ld;
+  PlaneXY<NJ> pc, pn;  // interpolated planes zj and zj+1
   {
     // prologue: output 2*zj_begin blends planes (zj_begin-1, zj_begin)
-    PlaneXY pm;
-    upsample_load(ibase + (size_t)max(zj_begin - 1, 0) * in_plane, off, ld);
-    upsample_plane_xy(ld, ty, tx, pm);
-    upsample_load(ibase + (size_t)zj_begin * in_plane, off, ld);
-    upsample_plane_xy(ld, ty, tx, pc);
+    PlaneXY<NJ> pm;
+    upsample_load<NJ>(ibase + (size_t)max(zj_begin - 1, 0) * in_plane, off, ld);
+    upsample_plane_xy<NJ>(ld, ty, tx, pm);
+    upsample_load<NJ>(ibase + (size_t)zj_begin * in_plane, off, ld);
+    upsample_plane_xy<NJ>(ld, ty, tx, pc);
     const AxisTaps tz = axis_taps(zj_begin, Di);
     emit(2 * zj_begin, tz.a0, tz.a1, pm, pc);
   }
-  upsample_load(ibase + (size_t)min(zj_begin + 1, Di - 1) * in_plane, off, ld);
+  upsample_load<NJ>(ibase + (size_t)min(zj_begin + 1, Di - 1) * in_plane, off, ld);
   for (int zj = zj_begin; zj < zj_end; ++zj) {
-    upsample_plane_xy(ld, ty, tx, pn);  // plane min(zj+1, Di-1) (clamped: window element 2)
-    if (zj + 1 < zj_end) upsample_load(ibase + (size_t)min(zj + 2, Di - 1) * in_plane, off, ld);
+    upsample_plane_xy<NJ>(ld, ty, tx, pn);  // plane min(zj+1, Di-1) (clamped: window element 2)
+    if (zj + 1 < zj_end) upsample_load<NJ>(ibase + (size_t)min(zj + 2, Di - 1) * in_plane, off, ld);
     const AxisTaps tz = axis_taps(zj, Di);
     emit(2 * zj + 1, tz.b0, tz.b1, pc, pn);
     if (zj + 1 < zj_end) {
@@ -755,16 +771,30 @@ Status launch_upsample(const Act& in, const Act& out, const ConvRegion* region, 
     const int jz0 = rg.lo[0] / 2, jy0 = rg.lo[1] / 2, jx0 = rg.lo[2] / 2;
     const int njz = (rg.hi[0] + 1) / 2 - jz0, njy = (rg.hi[1] + 1) / 2 - jy0,
               njx = (rg.hi[2] + 1) / 2 - jx0;
+    // channels per thread: 8 (16-byte accesses).  The 4-channel form (EXA_UP_CPT=4: 93 instead of
+    // 149 registers, 5 instead of 3 resident blocks) was measured SLOWER on a B200, 12.8 vs 10.3 ms
+    // per 512^3: the kernel is bound by its 8-byte accesses then, not by occupancy
+    // (profiles/r02g_ab_upsample_cpt.txt)
+    static const int cpt = []() {
+      const char* e = getenv("EXA_UP_CPT");
+      return e && atoi(e) == 4 ? 4 : 8;
+    }();
     // z is marched inside the kernel; split it only as far as needed to fill the GPU
-    const int threads_per_col = njy * njx * (out.C / 8) * out.B;
+    const int threads_per_col = njy * njx * (out.C / cpt) * out.B;
     int zsplit = 1;
-    while (zsplit < njz && (long long)threads_per_col * zsplit < 148LL * 1536) zsplit *= 2;
+    while (zsplit < njz && (long long)threads_per_col * zsplit < 148LL * 2048) zsplit *= 2;
     const int zchunk = ceil_div(njz, zsplit);
-    const dim3 blocks2((unsigned)ceil_div(njy * njx * (out.C / 8), 128), (unsigned)ceil_div(njz, zchunk),
+    const dim3 blocks2((unsigned)ceil_div(njy * njx * (out.C / cpt), 128), (unsigned)ceil_div(njz, zchunk),
                        (unsigned)out.B);
-    upsample_march_bf16_kernel<<<blocks2, 128, 0, s>>>(
-        (const __nv_bfloat16*)in.ptr, in.cstride, in.coff, (__nv_bfloat16*)out.ptr, out.cstride,
-        out.coff, in.D, in.H, in.W, in.C, rg, jz0, jy0, jx0, zchunk, njy, njx);
+    if (cpt == 8) {
+      upsample_march_bf16_kernel<4><<<blocks2, 128, 0, s>>>(
+          (const __nv_bfloat16*)in.ptr, in.cstride, in.coff, (__nv_bfloat16*)out.ptr, out.cstride,
+          out.coff, in.D, in.H, in.W, in.C, rg, jz0, jy0, jx0, zchunk, njy, njx);
+    } else {
+      upsample_march_bf16_kernel<2><<<blocks2, 128, 0, s>>>(
+          (const __nv_bfloat16*)in.ptr, in.cstride, in.coff, (__nv_bfloat16*)out.ptr, out.cstride,
+          out.coff, in.D, in.H, in.W, in.C, rg, jz0, jy0, jx0, zchunk, njy, njx);
+    }
   }
   EXA_CUDA(cudaGetLastError());
   return Status::OK();

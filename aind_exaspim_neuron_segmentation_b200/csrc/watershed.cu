@@ -110,6 +110,14 @@ struct DevBuf {
     AllocTimer t;
     cudaMemPool_t pool;
     EXA_TRY(ws_pool(&pool));
+    // four size classes per octave above 1 MiB: the sizes of a call depend on its data (faces,
+    // live edges), and odd-sized blocks fragment the pool, which then re-maps memory at the next
+    // large request (0.1-0.4 s at 512^3); class sizes make freed blocks fit later requests
+    if (bytes > (1u << 20)) {
+      size_t step = (size_t)1 << 18;
+      while (step * 8 <= bytes) step <<= 1;   // step = 2^(floor(log2 bytes) - 2)
+      bytes = (bytes + step - 1) / step * step;
+    }
     EXA_CUDA(cudaMallocFromPoolAsync(&p, bytes ? bytes : 1, pool, s));
     return Status::OK();
   }

@@ -386,6 +386,8 @@ _SYMMETRIC_OUTPUTS = {}
 class _EngineSlabBackend:
     """Slab compute on the native engine (device tensors)."""
 
+    stream_ordered = True   # everything is queued on torch's current stream
+
     def __init__(self, engine):
         self.engine = engine
         self.device = engine.device
@@ -540,7 +542,11 @@ class SlabJob:
         if halo is not None:
             ops.append(dist.P2POp(dist.isend, halo, self._peer(self.rank + 1), self.group))
         if ops:
-            self.backend.sync()  # partial sums are produced on the engine's stream
+            # the partial sums are produced on the current stream (the engine launches there); NCCL
+            # orders its streams after it at enqueue and wait() orders the current stream after the
+            # transfer -- no host synchronisation, the launch queue stays full
+            if not getattr(self.backend, "stream_ordered", False):
+                self.backend.sync()
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
         return seed
