@@ -1097,8 +1097,10 @@ Status Engine::set_peer_outputs(float* local_base, int64_t elems, float* const* 
   peer_local_ = n_peers > 0 ? local_base : nullptr;
   peer_elems_ = n_peers > 0 ? elems : 0;
   {
+    // default: copy-engine transfers; EXA_GATHER=store: stores from the stitch kernel (measured
+    // 7 ms slower per 1024^3 step on 8 GPUs: profiles/r02i_*)
     const char* g = getenv("EXA_GATHER");
-    peer_ce_ = g && std::string(g) == "ce";
+    peer_ce_ = !(g && std::string(g) == "store");
   }
   for (int i = 0; i < n_peers; ++i) {
     EXA_CHECK(peer_bases[i] != nullptr, "set_peer_outputs: null peer pointer");

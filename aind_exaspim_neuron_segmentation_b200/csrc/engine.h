@@ -217,9 +217,9 @@ class Engine {
   float* peer_local_ = nullptr;
   int64_t peer_elems_ = 0;
   std::vector<float*> peer_bases_;
-  // EXA_GATHER=ce: finished planes go to the peers' copies by copy-engine transfers on side
-  // streams (no SM time, overlapped with the next waves) instead of stores from the stitch kernel
-  bool peer_ce_ = false;
+  // finished planes go to the peers' copies by copy-engine transfers on side streams (no SM time,
+  // overlapped with the next waves); EXA_GATHER=store: by stores from the stitch kernel instead
+  bool peer_ce_ = true;
   static constexpr int kPeerStreams = 4;
   cudaStream_t peer_stream_[kPeerStreams] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t peer_ready_ = nullptr, peer_done_[kPeerStreams] = {nullptr, nullptr, nullptr, nullptr};

@@ -251,11 +251,12 @@ inline int64_t agglomerate(uint32_t n_nodes, size_t n_edges, const uint32_t* ea,
     nbr[b].for_each([&](uint32_t nb, const Stat& st) {
       if (nb != a) {
         moved.emplace_back(nb, st);
-        nbr[nb].prefetch(b);
+        __builtin_prefetch(&nbr[nb]);   // the table header first, its slots in the next pass
         nbr[a].prefetch(nb);
       }
     });
     nbr[b].clear();
+    for (const auto& kv : moved) nbr[kv.first].prefetch(b);
     for (const auto& kv : moved) {
       const uint32_t nb = kv.first;
       nbr[nb].erase(b);

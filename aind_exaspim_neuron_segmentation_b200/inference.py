@@ -575,9 +575,9 @@ class SlabJob:
 
     def _fused_gather_ready(self):
         """C3 without a gather pass: the output lives in symmetric memory and the stitch kernel
-        stores every finished element to all ranks' copies (exa_set_peer_outputs); with
-        ``EXA_GATHER=ce`` the finished planes travel by copy-engine transfers on side streams
-        instead (no SM time, overlapped with the following waves).  Falls back to the grouped NCCL
+        sends every finished band of planes to all ranks' copies (exa_set_peer_outputs): by
+        copy-engine transfers on side streams (default; no SM time, overlapped with the following
+        waves) or, with ``EXA_GATHER=store``, by stores from the stitch kernel itself.  Falls back to the grouped NCCL
         send/recv gather when the backend has no peer mapping (CPU test backend),
         ``EXA_GATHER=nccl`` is set, or the symmetric-memory rendezvous is not possible here."""
         if self._fused is None:

@@ -359,13 +359,13 @@ def sharded_parity_check(model, dev, rank, world):
     backend = _EngineSlabBackend(model.engine("bf16"))
     same, modes = True, []
     saved = os.environ.get("EXA_GATHER")
-    for gather_env in ("", "ce", "nccl"):
+    for gather_env in ("", "store", "nccl"):
         os.environ["EXA_GATHER"] = gather_env
         job = SlabJob(PARITY_SHAPE, params, 3, backend)
         for _ in range(2):   # the second run overwrites the peers' previous result in place
             full = job.run(job.upload(vol), gather=True)
             same = same and bool(np.array_equal(full.cpu().numpy(), single))
-        modes.append(("copy-engine peer copies" if gather_env == "ce" else "fused peer-store")
+        modes.append(("fused peer-store" if gather_env == "store" else "copy-engine peer copies")
                      if job._fused else "nccl send/recv")
         z0, z1 = job.own_bounds()
         host_own = torch.empty((3, z1 - z0) + PARITY_SHAPE[1:], dtype=torch.float32).pin_memory()

@@ -1,9 +1,9 @@
 """torchrun worker of tests/test_gpu_sharded.py: one process per GPU, NCCL.
 
 Every rank computes the single-GPU result itself (small volume) and checks that the sharded
-forms are bit-identical to it: the fused peer-store gather (symmetric memory + stitch kernel
-stores to all ranks' copies), its copy-engine form (EXA_GATHER=ce), the grouped NCCL send/recv
-gather, and the row-pipelined
+forms are bit-identical to it: the fused gather over symmetric memory in both forms (copy-engine
+transfers of finished bands, the default; stores from the stitch kernel, EXA_GATHER=store), the
+grouped NCCL send/recv gather, and the row-pipelined
 ``run_pipelined`` / ``predict_sharded(gather=False)`` with host buffers.
 """
 
@@ -41,13 +41,13 @@ def main():
     params = _native.make_params(kw["patch_shape"], kw["overlap"], kw["trim"], 1000, (1, 99.9), batch=7)
     backend = _EngineSlabBackend(model.engine("bf16"))
     modes = []
-    for gather_env in ("", "ce", "nccl"):
+    for gather_env in ("", "store", "nccl"):
         os.environ["EXA_GATHER"] = gather_env
         job = SlabJob(shape, params, 3, backend)
         for step in range(2):   # twice: the second run overwrites the peers' previous result
             full = job.run(job.upload(vol), gather=True)
             assert np.array_equal(full.cpu().numpy(), single), (gather_env, step, rank)
-        modes.append(("ce" if gather_env == "ce" else "fused") if job._fused else "nccl")
+        modes.append(("peer-store" if gather_env == "store" else "copy-engine") if job._fused else "nccl")
         z0, z1 = job.own_bounds()
         host = torch.empty((3, z1 - z0) + shape[1:], dtype=torch.float32).pin_memory()
         own = job.run_pipelined(job.upload(vol), host)
