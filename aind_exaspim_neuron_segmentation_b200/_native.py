@@ -149,6 +149,7 @@ _SIGNATURES = {
         ctypes.POINTER(ctypes.c_double), ctypes.c_int, ctypes.c_double, ctypes.c_double,
         ctypes.c_int64, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64),
         ctypes.POINTER(ctypes.c_int64)]),
+    "exa_ws_release_memory": (ctypes.c_int, []),
     "exa_ws_last_profile": (ctypes.c_int, [ctypes.POINTER(ctypes.c_double), ctypes.c_int]),
     "exa_region_agglomerate": (ctypes.c_int, [ctypes.c_int, ctypes.c_uint32, ctypes.c_int64,
                                               ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,

@@ -228,6 +228,11 @@ int exa_affinities_to_segmentation(int device, const float* aff_host, int D, int
   });
 }
 
+int exa_ws_release_memory(void) {
+  exa::ws_release_memory();
+  return EXA_OK;
+}
+
 int exa_ws_last_profile(double* out, int n) {
   if (!out || n < 0) return EXA_ERR_INVALID;
   exa::ws_last_profile(out, n);

@@ -41,6 +41,8 @@
 
 #include <algorithm>
 #include <chrono>
+#include <map>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -67,59 +69,84 @@ struct AllocTimer {
   }
 };
 
-// Stream-ordered allocations from a pool of our own (cudaMemPoolCreate): it never gives memory back
-// to the driver (release threshold = max), so after the first call at a given size the ~30
-// allocations of a call cost microseconds.  (The device's default pool was measured to hand
-// memory back between calls now and then: 250-900 ms of allocator time per call at 256^3-512^3.)
-cudaMemPool_t g_pool[64] = {};
+// Device memory comes from a block cache of our own: cudaMalloc'd blocks in size classes (four per
+// octave above 1 MiB) that go back to a per-device free list instead of to the driver, so after
+// the first call at a given size the ~30 allocations of a call cost microseconds and nothing
+// depends on the driver's pools.  (Measured with stream-ordered pools, default or our own with the
+// release threshold at its maximum: now and then 0.1-0.9 s of allocator time per call at
+// 256^3-512^3 -- the pool re-maps fragmented memory.)  Everything of one call is queued on ONE
+// stream, so a block may be handed out again while work that used it is still queued: the later
+// work runs after it.  Every call ends with that stream synchronised (also on errors), so blocks
+// are idle when another call, possibly on another stream, takes them.  exa_ws_release_memory()
+// gives the cached blocks back to the driver; an allocation that fails does so first and retries.
+struct BlockCache {
+  std::mutex mu;
+  std::multimap<size_t, void*> free_blocks;
+};
+BlockCache g_cache[64];
 
-Status ws_pool(cudaMemPool_t* out) {
-  int dev = 0;
-  EXA_CUDA(cudaGetDevice(&dev));
-  EXA_CHECK(dev >= 0 && dev < 64, "affinities_to_segmentation: device index out of range");
-  if (!g_pool[dev]) {
-    cudaMemPoolProps props = {};
-    props.allocType = cudaMemAllocationTypePinned;
-    props.handleTypes = cudaMemHandleTypeNone;
-    props.location.type = cudaMemLocationTypeDevice;
-    props.location.id = dev;
-    cudaMemPool_t pool;
-    EXA_CUDA(cudaMemPoolCreate(&pool, &props));
-    uint64_t keep = ~0ull;
-    EXA_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-    g_pool[dev] = pool;
-  }
-  *out = g_pool[dev];
-  return Status::OK();
+size_t size_class(size_t bytes) {
+  if (bytes <= ((size_t)1 << 20)) return (bytes + 511) / 512 * 512 + 512;
+  size_t step = (size_t)1 << 18;
+  while (step * 8 <= bytes) step <<= 1;  // step = 2^(floor(log2 bytes) - 2)
+  return (bytes + step - 1) / step * step;
+}
+
+void cache_release_all(int dev) {
+  BlockCache& c = g_cache[dev];
+  std::lock_guard<std::mutex> lock(c.mu);
+  for (auto& kv : c.free_blocks) cudaFree(kv.second);
+  c.free_blocks.clear();
 }
 
 struct DevBuf {
   void* p = nullptr;
-  cudaStream_t s = nullptr;
-  explicit DevBuf(cudaStream_t stream = nullptr) : s(stream) {}
+  size_t bytes = 0;
+  int dev = -1;
+  explicit DevBuf(cudaStream_t = nullptr) {}
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { release(); }
   void release() {
-    AllocTimer t;
-    if (p) cudaFreeAsync(p, s);
+    if (!p) return;
+    BlockCache& c = g_cache[dev];
+    std::lock_guard<std::mutex> lock(c.mu);
+    c.free_blocks.emplace(bytes, p);
     p = nullptr;
   }
-  Status alloc(size_t bytes) {
+  Status alloc(size_t want) {
     release();
     AllocTimer t;
-    cudaMemPool_t pool;
-    EXA_TRY(ws_pool(&pool));
-    // four size classes per octave above 1 MiB: the sizes of a call depend on its data (faces,
-    // live edges), and odd-sized blocks fragment the pool, which then re-maps memory at the next
-    // large request (0.1-0.4 s at 512^3); class sizes make freed blocks fit later requests
-    if (bytes > (1u << 20)) {
-      size_t step = (size_t)1 << 18;
-      while (step * 8 <= bytes) step <<= 1;   // step = 2^(floor(log2 bytes) - 2)
-      bytes = (bytes + step - 1) / step * step;
+    EXA_CUDA(cudaGetDevice(&dev));
+    EXA_CHECK(dev >= 0 && dev < 64, "affinities_to_segmentation: device index out of range");
+    bytes = size_class(want);
+    {
+      BlockCache& c = g_cache[dev];
+      std::lock_guard<std::mutex> lock(c.mu);
+      auto it = c.free_blocks.find(bytes);
+      if (it != c.free_blocks.end()) {
+        p = it->second;
+        c.free_blocks.erase(it);
+        return Status::OK();
+      }
     }
-    EXA_CUDA(cudaMallocFromPoolAsync(&p, bytes ? bytes : 1, pool, s));
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaErrorMemoryAllocation) {
+      cudaGetLastError();
+      cache_release_all(dev);
+      e = cudaMalloc(&p, bytes);
+    }
+    if (e != cudaSuccess) {
+      p = nullptr;
+      return Status::Err(std::string("affinities_to_segmentation: cudaMalloc of ") +
+                         std::to_string(bytes >> 20) + " MiB failed: " + cudaGetErrorString(e));
+    }
     return Status::OK();
+  }
+  void swap(DevBuf& o) {  // the block with its size: it returns to the cache under that size
+    std::swap(p, o.p);
+    std::swap(bytes, o.bytes);
+    std::swap(dev, o.dev);
   }
   template <typename T>
   T* as() const {
@@ -788,11 +815,11 @@ Status agglomerate_rounds(EdgeStore& es, uint32_t m0, uint32_t n_frag, int64_t T
       EXA_TRY(spare.alloc(live));
       agg_compact_kernel<<<gb, 256, 0, s>>>(m, E, off.as<uint32_t>(), spare.view());
       EXA_CUDA(cudaGetLastError());
-      std::swap(es.u.p, spare.u.p);
-      std::swap(es.v.p, spare.v.p);
-      std::swap(es.q.p, spare.q.p);
-      std::swap(es.c.p, spare.c.p);
-      std::swap(es.k.p, spare.k.p);
+      es.u.swap(spare.u);
+      es.v.swap(spare.v);
+      es.q.swap(spare.q);
+      es.c.swap(spare.c);
+      es.k.swap(spare.k);
       m = live;
       return Status::OK();
     };
@@ -817,7 +844,7 @@ Status agglomerate_rounds(EdgeStore& es, uint32_t m0, uint32_t n_frag, int64_t T
       // rename + combine; the table holds at most `live` pairs (one host round trip per round:
       // the counters are read after the whole round was queued)
       uint32_t want = 1024;
-      while (want < 2u * live && want < (1u << 31)) want <<= 1;
+      while ((unsigned long long)want < 2ull * live && want < (1u << 31)) want <<= 1;
       if (want > table_slots) {
         EXA_TRY(tkey.alloc((size_t)want * 8));
         EXA_TRY(towner.alloc((size_t)want * 4));
@@ -934,11 +961,36 @@ Status agglomerate_rounds(EdgeStore& es, uint32_t m0, uint32_t n_frag, int64_t T
 
 }  // namespace
 
+namespace {
+Status segmentation_impl(const float* aff, int D, int H, int W, const double* thresholds,
+                         int n_thresholds, double aff_low, double aff_high, int64_t min_segment_size,
+                         uint64_t* seg, int64_t* n_fragments, int64_t* n_segments, cudaStream_t s);
+}
+
 Status affinities_to_segmentation_device(const float* aff, int D, int H, int W,
                                          const double* thresholds, int n_thresholds, double aff_low,
                                          double aff_high, int64_t min_segment_size, uint64_t* seg,
                                          int64_t* n_fragments, int64_t* n_segments,
                                          cudaStream_t s) {
+  Status st = segmentation_impl(aff, D, H, W, thresholds, n_thresholds, aff_low, aff_high,
+                                min_segment_size, seg, n_fragments, n_segments, s);
+  // also after an error: the blocks of this call are back in the cache and must be idle
+  cudaStreamSynchronize(s);
+  return st;
+}
+
+void ws_release_memory() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) {
+    cudaDeviceSynchronize();
+    cache_release_all(dev);
+  }
+}
+
+namespace {
+Status segmentation_impl(const float* aff, int D, int H, int W, const double* thresholds,
+                         int n_thresholds, double aff_low, double aff_high, int64_t min_segment_size,
+                         uint64_t* seg, int64_t* n_fragments, int64_t* n_segments, cudaStream_t s) {
   EXA_CHECK(aff && seg, "affinities_to_segmentation: null buffer");
   EXA_CHECK(D > 0 && H > 0 && W > 0, "affinities_to_segmentation: dims must be positive");
   EXA_CHECK(thresholds && n_thresholds > 0, "affinities_to_segmentation: no agglomeration threshold");
@@ -1028,7 +1080,7 @@ Status affinities_to_segmentation_device(const float* aff, int D, int H, int W,
                                                   pos.as<uint32_t>(), g, claim, rank.as<uint32_t>(),
                                                   base, next.as<uint32_t>());
       EXA_CUDA(cudaGetLastError());
-      std::swap(front.p, next.p);
+      front.swap(next);
       n_front = n_next;
       ++levels;
     }
@@ -1082,11 +1134,11 @@ Status affinities_to_segmentation_device(const float* aff, int D, int H, int W,
     EXA_CUDA(cudaStreamSynchronize(s));
     const unsigned long long n_faces = last_off + last_cnt;
     sub("count faces");
-    EXA_CHECK(n_faces < (1ull << 31),
-              "affinities_to_segmentation: more than 2^31 faces between fragments; split the volume");
+    EXA_CHECK(n_faces < (1ull << 32),
+              "affinities_to_segmentation: more than 2^32 faces between fragments; split the volume");
     EdgeStore es(s);
     if (n_faces > 0) {
-      const int m = (int)n_faces;
+      const long long m = (long long)n_faces;   // 64-bit item counts in the CUB calls below
       DevBuf keys(s), vals(s), keys2(s), vals2(s), ucnt(s), nruns(s);
       EXA_TRY(keys.alloc((size_t)m * 8));
       EXA_TRY(vals.alloc((size_t)m * 8));
@@ -1112,25 +1164,29 @@ Status affinities_to_segmentation_device(const float* aff, int D, int H, int W,
       sub("sort faces");
       // segmented sum and run lengths; `keys` / `vals` are free again and take the outputs
       EXA_TRY(ucnt.alloc((size_t)m * 4));
-      EXA_TRY(nruns.alloc(8));
+      EXA_TRY(nruns.alloc(16));
       unsigned long long* ukey = keys.as<unsigned long long>();
       unsigned long long* usum = vals.as<unsigned long long>();
+      long long* n_runs = nruns.as<long long>();
       EXA_CUDA(cub::DeviceReduce::ReduceByKey(nullptr, tmp_bytes, keys2.as<unsigned long long>(), ukey,
-                                              vals2.as<unsigned long long>(), usum, nruns.as<int>(),
+                                              vals2.as<unsigned long long>(), usum, n_runs,
                                               cub::Sum(), m, s));
       EXA_TRY(tmp.alloc(tmp_bytes));
       EXA_CUDA(cub::DeviceReduce::ReduceByKey(tmp.p, tmp_bytes, keys2.as<unsigned long long>(), ukey,
-                                              vals2.as<unsigned long long>(), usum, nruns.as<int>(),
+                                              vals2.as<unsigned long long>(), usum, n_runs,
                                               cub::Sum(), m, s));
-      EXA_CUDA(cub::DeviceRunLengthEncode::Encode(nullptr, tmp_bytes, keys2.as<unsigned long long>(),
-                                                  ukey, ucnt.as<uint32_t>(), nruns.as<int>() + 1, m, s));
+      // faces per pair: the same reduction over ones (the run-length primitive takes 32-bit counts)
+      cub::ConstantInputIterator<uint32_t> ones(1u);
+      EXA_CUDA(cub::DeviceReduce::ReduceByKey(nullptr, tmp_bytes, keys2.as<unsigned long long>(), ukey,
+                                              ones, ucnt.as<uint32_t>(), n_runs + 1, cub::Sum(), m, s));
       EXA_TRY(tmp.alloc(tmp_bytes));
-      EXA_CUDA(cub::DeviceRunLengthEncode::Encode(tmp.p, tmp_bytes, keys2.as<unsigned long long>(),
-                                                  ukey, ucnt.as<uint32_t>(), nruns.as<int>() + 1, m, s));
-      int runs[2] = {0, 0};
-      EXA_CUDA(cudaMemcpyAsync(runs, nruns.p, 8, cudaMemcpyDeviceToHost, s));
+      EXA_CUDA(cub::DeviceReduce::ReduceByKey(tmp.p, tmp_bytes, keys2.as<unsigned long long>(), ukey,
+                                              ones, ucnt.as<uint32_t>(), n_runs + 1, cub::Sum(), m, s));
+      long long runs[2] = {0, 0};
+      EXA_CUDA(cudaMemcpyAsync(runs, nruns.p, 16, cudaMemcpyDeviceToHost, s));
       EXA_CUDA(cudaStreamSynchronize(s));
       EXA_CHECK(runs[0] == runs[1], "affinities_to_segmentation: region graph run counts disagree");
+      EXA_CHECK(runs[0] < (1ll << 32) - 1, "affinities_to_segmentation: more than 2^32 region edges");
       n_region_edges = (uint32_t)runs[0];
       keys2.release();
       vals2.release();
@@ -1141,8 +1197,8 @@ Status affinities_to_segmentation_device(const float* aff, int D, int H, int W,
           n_region_edges, ukey, es.u.as<uint32_t>(), es.v.as<uint32_t>(), es.k.as<uint32_t>());
       EXA_CUDA(cudaGetLastError());
       // the sums and counts stay where they are: hand the buffers over
-      std::swap(es.q.p, vals.p);
-      std::swap(es.c.p, ucnt.p);
+      es.q.swap(vals);
+      es.c.swap(ucnt);
     }
     sub("reduce by pair");
     lap("region graph (GPU)", 1);
@@ -1191,6 +1247,8 @@ Status affinities_to_segmentation_device(const float* aff, int D, int H, int W,
   lap("sizes + relabel (GPU)", 4);
   return Status::OK();
 }
+
+}  // namespace
 
 void ws_last_profile(double* out, int n) {
   for (int i = 0; i < n && i < 8; ++i) out[i] = g_last_profile[i];
@@ -1244,11 +1302,15 @@ Status region_agglomerate(int device, uint32_t n_fragments, int64_t n_edges, con
     EXA_CUDA(cudaMemcpyAsync(es.k.p, key.data(), m * 4, cudaMemcpyHostToDevice, s));
     EXA_CUDA(cudaStreamSynchronize(s));
   }
-  EXA_TRY(agglomerate_rounds(es, (uint32_t)m, n_fragments, T, root.as<uint32_t>(), s, false, nullptr,
-                             nullptr));
-  EXA_CUDA(cudaMemcpyAsync(root_out, root.p, ((size_t)n_fragments + 1) * 4, cudaMemcpyDeviceToHost, s));
-  EXA_CUDA(cudaStreamSynchronize(s));
-  return Status::OK();
+  Status st = agglomerate_rounds(es, (uint32_t)m, n_fragments, T, root.as<uint32_t>(), s, false,
+                                 nullptr, nullptr);
+  if (st.ok) {
+    cudaError_t e = cudaMemcpyAsync(root_out, root.p, ((size_t)n_fragments + 1) * 4,
+                                    cudaMemcpyDeviceToHost, s);
+    if (e != cudaSuccess) st = Status::Err(std::string("region_agglomerate: ") + cudaGetErrorString(e));
+  }
+  cudaStreamSynchronize(s);  // also after an error: the cached blocks must be idle
+  return st;
 }
 
 Status affinities_to_segmentation_host(int device, const float* aff, int D, int H, int W,

@@ -25,6 +25,9 @@ Status affinities_to_segmentation_host(int device, const float* aff, int D, int 
 // relabel, then counts: [5] parallel rounds, [6] region-graph edges, [7] edges given to the host queue
 void ws_last_profile(double* out, int n);
 
+// gives the device memory cached by this file's block cache (current device) back to the driver
+void ws_release_memory();
+
 // The agglomeration step alone on a region graph given as host arrays: edges eu[i] < ev[i] (fragment
 // ids 1..n_fragments, every pair at most once, sorted by (eu, ev): the index is the tie-break rank),
 // qsum[i] = sum of the affinities between the two in 32.32 fixed point, count[i] = faces.

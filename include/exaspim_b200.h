@@ -177,6 +177,10 @@ int exa_affinities_to_segmentation_device(const float* aff_dev, int D, int H, in
                                           int64_t min_segment_size, uint64_t* seg_dev,
                                           int64_t* n_fragments, int64_t* n_segments, void* stream);
 
+/* exa_affinities_to_segmentation* keep the device blocks they used in a per-device cache (the next
+ * call of the same size allocates nothing); this gives them back to the driver (current device). */
+int exa_ws_release_memory(void);
+
 /* measurement (no reference analogue): wall milliseconds of the phases of the last
  * exa_affinities_to_segmentation[_device] call of this process -- [0] fragments, [1] region graph,
  * [2] parallel agglomeration rounds, [3] host queue, [4] sizes + relabel -- then counts:

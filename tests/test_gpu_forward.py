@@ -151,3 +151,32 @@ def test_unsupported_widths_raise():
     for wm in (0.5, 1.5, 8):
         with pytest.raises(NotImplementedError):
             UNet3D(output_channels=3, width_multiplier=wm)
+
+
+def test_validation_forward_pass_of_the_trainer():
+    """The eval-mode half of Trainer.forward_pass / validate_step (train.py:159-223): under
+    no_grad and model.eval(), ``hat_y = model(x); loss = BCEWithLogitsLoss()(hat_y, y)`` runs on
+    the drop-in module (logits from the engine, the criterion on them by torch).  Training-mode
+    forward (batch statistics) and backward are not built and raise."""
+    from aind_exaspim_neuron_segmentation_b200 import UNet3D
+    from oracle.unet_ref import rescaled_state_dict
+
+    sd = rescaled_state_dict(11, 3)
+    model = UNet3D(output_channels=3)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda()
+    torch.manual_seed(4)
+    x = torch.rand(2, 1, 32, 32, 32)
+    y = (torch.rand(2, 3, 32, 32, 32) > 0.7).float()
+    criterion = torch.nn.BCEWithLogitsLoss()
+    with torch.no_grad():
+        model.eval()
+        hat_y = model(x.to("cuda", dtype=torch.float))
+        loss = criterion(hat_y, y.to("cuda", dtype=torch.float))
+    ref_logits = _oracle(x, sd)
+    ref_loss = criterion(ref_logits, y)
+    assert abs(float(loss) - float(ref_loss)) <= 2e-3, (float(loss), float(ref_loss))
+    assert ((hat_y.cpu() > 0) == (ref_logits > 0)).float().mean().item() >= 0.995   # compute_stats' binarisation
+    model.train()
+    with pytest.raises(RuntimeError):
+        model(x.cuda())
