@@ -823,12 +823,11 @@ Status agglomerate_rounds(EdgeStore& es, uint32_t m0, uint32_t n_frag, int64_t T
       m = live;
       return Status::OK();
     };
-    uint32_t* h = nullptr;  // pinned: {merges of the round, dead slots in total}
-    EXA_CUDA(cudaMallocHost(&h, 8));
-    struct Unpin {
-      uint32_t* p;
-      ~Unpin() { cudaFreeHost(p); }
-    } unpin{h};
+    // pinned: {merges of the round, dead slots in total}.  Allocated once per process:
+    // cudaMallocHost / cudaFreeHost per call cost up to hundreds of milliseconds now and then
+    // (they synchronise with the whole device)
+    static thread_local uint32_t* h = nullptr;
+    if (!h) EXA_CUDA(cudaMallocHost(&h, 8));
     while (rounds < max_rounds) {
       ++rounds;
       Edges E = es.view();
