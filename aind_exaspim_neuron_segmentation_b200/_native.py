@@ -16,9 +16,9 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_PKG_DIR, "csrc")
 LIB_PATH = os.path.join(_PKG_DIR, "libexaspim_b200.so")
 SOURCES = ["capi.cu", "engine.cu", "kernels_mem.cu", "conv_umma.cu", "conv_zfold.cu", "conv_stem.cu",
-           "watershed.cu"]
+           "watershed.cu", "float_volume.cu"]
 HEADERS = ["common.cuh", "conv_umma.cuh", "conv_zfold.cuh", "conv_zfold2.cuh", "conv_stem.cuh", "engine.h",
-           "kernels.h", "tmap.h", "watershed.h", "ws_agglomerate.h"]
+           "kernels.h", "tmap.h", "watershed.h", "ws_agglomerate.h", "float_volume.h"]
 
 PRECISION_BF16 = 0
 PRECISION_FP32 = 1
@@ -124,6 +124,15 @@ _SIGNATURES = {
     "exa_percentiles_from_hist": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_double,
                                                  ctypes.c_double, ctypes.POINTER(ctypes.c_double),
                                                  ctypes.POINTER(ctypes.c_double)]),
+    "exa_set_normalization_table": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                                   ctypes.c_double, ctypes.c_double]),
+    "exa_compress_float_volume": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64,
+                                                 ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p,
+                                                 ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]),
+    "exa_percentiles_from_hist_values": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                                        ctypes.c_int, ctypes.c_double, ctypes.c_double,
+                                                        ctypes.POINTER(ctypes.c_double),
+                                                        ctypes.POINTER(ctypes.c_double)]),
     "exa_set_normalization": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, ctypes.c_double,
                                              ctypes.c_int]),
     "exa_slab_run": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,

@@ -6,6 +6,7 @@
 
 #include "../../include/exaspim_b200.h"
 #include "engine.h"
+#include "float_volume.h"
 #include "watershed.h"
 
 struct exa_engine {
@@ -168,6 +169,25 @@ int exa_percentiles_from_hist(const uint64_t* hist, int nbins, double q_lo, doub
 
 int exa_set_normalization(exa_engine* e, double mn, double mx, int clip) {
   return guarded(e, [&] { return e->impl.set_normalization(mn, mx, clip); });
+}
+
+int exa_set_normalization_table(exa_engine* e, const double* values, int n, double mn, double mx) {
+  return guarded(e, [&] { return e->impl.set_normalization_table(values, n, mn, mx); });
+}
+
+int exa_compress_float_volume(const void* vol_dev, int is_double, int64_t n, double clip,
+                              uint16_t* idx_dev, double* table_out, int* n_table, void* stream) {
+  return guarded_static([&] {
+    return exa::compress_float_volume(vol_dev, is_double, n, clip, idx_dev, table_out, n_table,
+                                      (cudaStream_t)stream);
+  });
+}
+
+int exa_percentiles_from_hist_values(const uint64_t* hist, const double* values, int nbins, int is_f32,
+                                     double q_lo, double q_hi, double* mn, double* mx) {
+  return guarded_static([&] {
+    return exa::percentiles_from_hist_values(hist, values, nbins, is_f32, q_lo, q_hi, mn, mx);
+  });
 }
 
 int exa_slab_run(exa_engine* e, const uint16_t* slab_dev, int D, int H, int W,

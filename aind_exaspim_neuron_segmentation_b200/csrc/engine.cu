@@ -847,6 +847,30 @@ Status Engine::set_normalization(double mn, double mx, int clip) {
   return Status::OK();
 }
 
+// The same table for a rank-compressed float volume (float_volume.cu): entry v is the normalised
+// value of the v-th distinct clipped intensity, evaluated in float64 like img_util.py:527-531
+Status Engine::set_normalization_table(const double* values, int n, double mn, double mx) {
+  EXA_CUDA(cudaSetDevice(device_));
+  EXA_CHECK(values && n >= 1 && n <= 65536, "set_normalization_table: 1..65536 values");
+  const int clip = n - 1;
+  std::vector<float> lut(n);
+  const double den = mx - mn + 1e-8;
+  for (int v = 0; v < n; ++v) {
+    double t = (values[v] - mn) / den;
+    t = t < 0.0 ? 0.0 : (t > 1.0 ? 1.0 : t);
+    lut[v] = (float)t;
+  }
+  if (lut_clip_ != clip) {
+    free_dev(lut_);
+    lut_ = nullptr;
+    EXA_CUDA(cudaMalloc(&lut_, sizeof(float) * n));
+    lut_clip_ = clip;
+  }
+  EXA_CUDA(cudaMemcpy(lut_, lut.data(), sizeof(float) * n, cudaMemcpyHostToDevice));
+  norm_set_ = true;
+  return Status::OK();
+}
+
 Status Engine::slab_run(const uint16_t* slab_dev, int D, int H, int W, const exa_predict_params& p,
                         int row_begin, int row_end, cudaStream_t s) {
   EXA_CUDA(cudaSetDevice(device_));

@@ -58,6 +58,7 @@ class Engine {
   Status histogram(const uint16_t* vol_dev, int64_t n, int clip, uint64_t* hist_dev,
                    cudaStream_t s);
   Status set_normalization(double mn, double mx, int clip);
+  Status set_normalization_table(const double* values, int n, double mn, double mx);
   Status slab_run(const uint16_t* slab_dev, int D, int H, int W, const exa_predict_params& p,
                   int row_begin, int row_end, cudaStream_t s);
   Status slab_partial(float* halo_dev, cudaStream_t s);

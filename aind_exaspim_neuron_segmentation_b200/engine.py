@@ -171,6 +171,30 @@ class Engine:
         _native.check(self._lib.exa_set_normalization(self._h, float(mn), float(mx), int(clip)),
                       self._h, "exa_set_normalization")
 
+    def set_normalization_table(self, values, mn, mx):
+        """Normalisation for a rank-compressed float volume: ``values`` are its distinct clipped
+        intensities in ascending order (``compress_float_volume``)."""
+        values = np.ascontiguousarray(values, dtype=np.float64)
+        _native.check(self._lib.exa_set_normalization_table(
+            self._h, values.ctypes.data_as(ctypes.c_void_p), int(values.size), float(mn), float(mx)),
+            self._h, "exa_set_normalization_table")
+
+    def compress_float_volume(self, vol_dev, clip):
+        """cuda float32 / float64 (D,H,W) tensor -> (cuda uint16 ranks of min(x, clip), float64 table
+        of the distinct clipped values); raises when there are more than 65536 of them."""
+        if vol_dev.dtype not in (torch.float32, torch.float64) or not vol_dev.is_contiguous():
+            raise TypeError("expected a contiguous float32 / float64 CUDA tensor")
+        idx = torch.empty(vol_dev.shape, dtype=torch.uint16, device=self.device)
+        table = np.zeros(65536, dtype=np.float64)
+        n = ctypes.c_int(0)
+        with torch.cuda.device(self.device):
+            code = self._lib.exa_compress_float_volume(
+                _ptr(vol_dev), 1 if vol_dev.dtype == torch.float64 else 0, vol_dev.numel(), float(clip),
+                _ptr(idx), table.ctypes.data_as(ctypes.c_void_p), ctypes.byref(n),
+                _stream_ptr(self.device))
+        _native.check(code, None, "exa_compress_float_volume")
+        return idx, table[:n.value].copy()
+
     def slab_run(self, slab_dev, shape, params, row_begin, row_end):
         d, h, w = shape
         code = self._lib.exa_slab_run(self._h, _ptr(slab_dev), d, h, w, ctypes.byref(params),
@@ -226,6 +250,18 @@ def plan_slab(shape, params, row_begin, row_end):
                                        ctypes.byref(plan))
     _native.check(code, None, "exa_plan_slab")
     return plan.as_dict()
+
+
+def percentiles_from_hist_values(hist, values, is_f32, q_lo, q_hi):
+    """np.percentile(method="linear") from the histogram of ranks and the table of values."""
+    hist = np.ascontiguousarray(hist, dtype=np.uint64)
+    values = np.ascontiguousarray(values, dtype=np.float64)
+    mn, mx = ctypes.c_double(), ctypes.c_double()
+    code = _native.lib().exa_percentiles_from_hist_values(
+        hist.ctypes.data_as(ctypes.c_void_p), values.ctypes.data_as(ctypes.c_void_p), hist.size,
+        1 if is_f32 else 0, q_lo, q_hi, ctypes.byref(mn), ctypes.byref(mx))
+    _native.check(code, None, "exa_percentiles_from_hist_values")
+    return mn.value, mx.value
 
 
 def percentiles_from_hist(hist, q_lo, q_hi):

@@ -25,7 +25,7 @@ import numpy as np
 import torch
 
 from . import _native
-from .engine import Engine, percentiles_from_hist, plan_slab
+from .engine import Engine, percentiles_from_hist, percentiles_from_hist_values, plan_slab
 from .machine_learning.unet3d import UNet3D, engine_for_module
 
 __all__ = ["predict", "predict_sharded", "predict_streamed", "load_model", "count_patches",
@@ -106,8 +106,8 @@ def _as_volume_u16(img, brightness_clip):
                 "the clipped volume does not fit the uint16 kernels (lower the clip to <= 65535)")
         return np.minimum(arr, min(clip, 65535)).astype(np.uint16)
     raise TypeError(
-        f"unsupported image dtype {arr.dtype}: the B200 path consumes integer (ExaSPIM uint16) "
-        "volumes; there is no CPU fallback for floating-point images"
+        f"unsupported image dtype {arr.dtype}: predict_sharded / predict_streamed consume integer "
+        "(ExaSPIM uint16) volumes; floating-point images go through predict()"
     )
 
 
@@ -148,8 +148,6 @@ def predict(
     a lower bound on the number of patches per wave -- it has no numerical effect
     (eval-mode BatchNorm, no cross-sample op).
     """
-    _check_clip(img, brightness_clip)
-    vol = _as_volume_u16(img, brightness_clip)
     engine = _engine_for(model, precision)
     n_channels = 3 if affinity_mode else 1
     if engine.out_channels != n_channels:
@@ -157,6 +155,12 @@ def predict(
             f"model has {engine.out_channels} output channels but affinity_mode={affinity_mode} "
             f"needs {n_channels}"
         )
+    if np.asarray(img).dtype.kind == "f":
+        res = _predict_float(np.asarray(img), engine, n_channels, batch_size, brightness_clip,
+                             normalization_percentiles, patch_shape, overlap, trim, out)
+        return res if affinity_mode else res[0]
+    _check_clip(img, brightness_clip)
+    vol = _as_volume_u16(img, brightness_clip)
     shape5 = (1, 1) + vol.shape
     n_patches = count_patches(shape5, patch_shape, overlap)
     params = _native.make_params(patch_shape, overlap, trim, brightness_clip,
@@ -182,6 +186,48 @@ def predict(
             engine.set_progress(None)
         pbar.update(n_patches - state["done"])
     return out if affinity_mode else out[0]
+
+
+def _predict_float(arr, engine, n_channels, batch_size, brightness_clip, normalization_percentiles,
+                   patch_shape, overlap, trim, out):
+    """Floating-point images (the reference takes any dtype: inference.py:79-80).  The volume is
+    rank-compressed on the GPU -- uint16 index of min(x, clip) among its distinct values, at most
+    65536 of them, otherwise this raises -- and the normalisation table is evaluated on the exact
+    values in float64, so the uint16 kernels reproduce the reference bit for bit
+    (csrc/float_volume.cu).  float16 is widened to float32 like numpy's percentile/normalise do."""
+    if arr.ndim > 5 or arr.ndim < 3 or any(s != 1 for s in arr.shape[:-3]):
+        raise ValueError("image must have between 3 and 5 dimensions with leading dimensions of 1")
+    if brightness_clip < 0:
+        raise ValueError("brightness_clip must be >= 0")
+    arr = arr.reshape(arr.shape[-3:])
+    if arr.dtype not in (np.float32, np.float64):
+        raise TypeError(f"unsupported floating-point image dtype {arr.dtype}: float32 and float64 "
+                        "images are handled")
+    shape = tuple(int(v) for v in arr.shape)
+    c = n_channels
+    dev = engine.device
+    vol_dev = torch.from_numpy(np.ascontiguousarray(arr)).to(dev)
+    idx, table = engine.compress_float_volume(vol_dev, brightness_clip)
+    del vol_dev
+    clip = int(table.size) - 1
+    params = _native.make_params(patch_shape, overlap, trim, clip, normalization_percentiles,
+                                 batch=max(int(batch_size), 32))
+    hist = engine.histogram(idx, clip)
+    mn, mx = percentiles_from_hist_values(hist.cpu().numpy().astype(np.uint64), table,
+                                          arr.dtype == np.float32, params.pct_lo, params.pct_hi)
+    engine.set_normalization_table(table, mn, mx)
+    res = out if out is not None else np.empty((c,) + shape, dtype=np.float32)
+    if tuple(res.shape) != (c,) + shape or res.dtype != np.float32 or not res.flags["C_CONTIGUOUS"]:
+        raise ValueError(f"out must be a C-contiguous float32 array of shape {(c,) + shape}")
+    nz = plan_slab(shape, params, 0, 0)["nz"]
+    if nz == 0 or count_patches((1, 1) + shape, patch_shape, overlap) == 0:
+        res[...] = 0.0
+        return res
+    own = torch.empty((c,) + shape, dtype=torch.float32, device=dev)
+    engine.slab_predict(idx, shape, params, 0, nz, own, None, None)
+    engine.slab_finish(None, own, None)
+    res[...] = own.cpu().numpy()
+    return res
 
 
 # --- volumes larger than memory: chunks of z patch-rows, one after the other ------------------

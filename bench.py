@@ -559,6 +559,21 @@ def run_segment(args):
             "max_abs_affinity_diff": max(float(np.abs(aff[c] - aff32[c]).max()) for c in range(3)),
             "what": "segmentation of the bf16 affinities vs segmentation of the FP32-validation "
                     "affinities (both by the product), ignoring voxels that are background in the latter"}
+        if not lean:
+            # the default thresholds merge everything on random-init weights (one segment, SURVEY.md
+            # 8c): the same comparison where the segmentation is NOT degenerate -- the watershed
+            # fragments themselves and two lower thresholds
+            del seg32
+            dev16, dev32 = torch.from_numpy(aff).cuda(), torch.from_numpy(aff32).cuda()
+            extra = []
+            for thr, min_size in (([0.0], 0), ([0.2], 0), ([0.35], 0)):
+                a = affinities_to_segmentation(dev16, thr, min_size)
+                b = affinities_to_segmentation(dev32, thr, min_size)
+                extra.append({"thresholds": thr, "min_segment_size": min_size,
+                              "segments_bf16": int(a.max().item()), "segments_fp32": int(b.max().item()),
+                              "agreement": adapted_rand_on_device(a, b)})
+                del a, b
+            line["adapted_rand"]["non_degenerate"] = extra
     emit(line)
 
 # --- B200 arm ------------------------------------------------------------------------------

@@ -121,6 +121,19 @@ int exa_percentiles_from_hist(const uint64_t* hist, int nbins, double q_lo, doub
                               double* mn, double* mx);
 /* normalisation scalars (img_util.py:526-531) for the following slab calls */
 int exa_set_normalization(exa_engine* e, double mn, double mx, int clip);
+/* Floating-point images (inference.py:79-80 accepts any dtype).  exa_compress_float_volume turns n
+ * float32 (is_double = 0) / float64 values on the device into uint16 ranks of min(x, clip) among its
+ * distinct values, which it returns in ascending order in table_out (65536 doubles, host); more than
+ * 65536 distinct clipped values, or NaN, is an error.  exa_percentiles_from_hist_values is
+ * np.percentile(method="linear") from the histogram of the ranks (exa_histogram) and that table
+ * (is_f32: the image was float32 -- numpy takes the neighbour difference in the array's dtype);
+ * exa_set_normalization_table installs the lookup table of the normalised values
+ * (img_util.py:527-531 in float64) for the following slab calls, whose brightness_clip is n - 1. */
+int exa_compress_float_volume(const void* vol_dev, int is_double, int64_t n, double clip,
+                              uint16_t* idx_dev, double* table_out, int* n_table, void* stream);
+int exa_percentiles_from_hist_values(const uint64_t* hist, const double* values, int nbins, int is_f32,
+                                     double q_lo, double q_hi, double* mn, double* mx);
+int exa_set_normalization_table(exa_engine* e, const double* values, int n, double mn, double mx);
 /* run all patches of rows [row_begin,row_end); slab_dev holds planes [in_z0,in_z1) */
 int exa_slab_run(exa_engine* e, const uint16_t* slab_dev, int D, int H, int W,
                  const exa_predict_params* p, int row_begin, int row_end, void* stream);

@@ -71,7 +71,29 @@ CASES = {
                    dict(patch_shape=(32, 32, 32), overlap=(8, 8, 8), trim=4)),
     "variant_convT_w2": ((48, 56, 40), 8, ("rescaled/0/2", 6),
                          dict(patch_shape=(32, 32, 32), overlap=(8, 8, 8), trim=4)),
+    # round 2: floating-point images (inference.py:79-80 takes any dtype); optional 5th entry =
+    # float_image() kind applied to the uint16 volume
+    "float32_integers": ((48, 56, 40), 9, ("rescaled", 7),
+                         dict(patch_shape=(32, 32, 32), overlap=(8, 8, 8), trim=4), "f32"),
+    "float32_quarters": ((40, 40, 72), 10, ("rescaled", 7),
+                         dict(patch_shape=(32, 32, 32), overlap=(8, 8, 8), trim=4, brightness_clip=300.1,
+                              normalization_percentiles=(2, 99.5)), "f32_quarter"),
+    "float64_thirds": ((40, 64, 40), 11, ("rescaled", 7),
+                       dict(patch_shape=(32, 32, 32), overlap=(8, 8, 8), trim=4, brightness_clip=500),
+                       "f64_third"),
 }
+
+
+def float_image(vol, kind):
+    """Floating-point images for the float-input cases: integer data stored as float32, quarter
+    steps in float32, thirds in float64 (few thousand distinct values, not all exact in binary)."""
+    if kind == "f32":
+        return vol.astype(np.float32)
+    if kind == "f32_quarter":
+        return (vol.astype(np.float32) * np.float32(0.25)).astype(np.float32)
+    if kind == "f64_third":
+        return vol.astype(np.float64) / 3.0
+    raise ValueError(kind)
 
 
 def make_volume(shape, seed):
@@ -109,10 +131,13 @@ def main():
         with open(meta_path) as f:
             old = json.load(f)
         meta = old["cases"]
-    for name, (shape, vseed, (wkind, wseed), kwargs) in CASES.items():
+    for name, case in CASES.items():
+        shape, vseed, (wkind, wseed), kwargs = case[:4]
         if only is not None and name not in only:
             continue
         vol = make_volume(shape, vseed)
+        if len(case) > 4:
+            vol = float_image(vol, case[4])
         if wkind == "default":
             torch.manual_seed(wseed)
             model = UNet3D(output_channels=3).eval()
@@ -131,6 +156,8 @@ def main():
         np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **red)
         meta[name] = dict(shape=shape, vol_seed=vseed, weights=[wkind, wseed], kwargs=kwargs,
                           min=float(out.min()), max=float(out.max()))
+        if len(case) > 4:
+            meta[name]["float_image"] = case[4]
         print(name, out.shape, float(out.min()), float(out.max()), red["bbox"].tolist())
     if only is not None:
         old["cases"] = meta

@@ -9,6 +9,18 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+def float_image(vol, kind):
+    """Floating-point images for the float-input cases: integer data stored as float32, quarter
+    steps in float32, thirds in float64 (few thousand distinct values, not all exact in binary)."""
+    if kind == "f32":
+        return vol.astype(np.float32)
+    if kind == "f32_quarter":
+        return (vol.astype(np.float32) * np.float32(0.25)).astype(np.float32)
+    if kind == "f64_third":
+        return vol.astype(np.float64) / 3.0
+    raise ValueError(kind)
+
+
 def make_volume(shape, seed):
     rng = np.random.default_rng(seed)
     return rng.integers(0, 2000, tuple(shape), dtype=np.uint16)

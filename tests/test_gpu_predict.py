@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import (compare_with_golden, lightsheet_volume, load_golden, make_volume,
+from helpers import (compare_with_golden, float_image, lightsheet_volume, load_golden, make_volume,
                      state_dict_for)
 
 pytestmark = pytest.mark.gpu
@@ -35,7 +35,8 @@ def _kwargs(meta):
 
 @pytest.mark.parametrize("name", ["c1_default_96", "c1_rescaled_96", "mixed_160x160x100", "small_p32",
                                   "small_p48_trim0ish", "multireflect_p32", "p128_single",
-                                  "variant_convT", "variant_w2", "variant_convT_w2"])
+                                  "variant_convT", "variant_w2", "variant_convT_w2",
+                                  "float32_integers", "float32_quarters", "float64_thirds"])
 @pytest.mark.parametrize("precision", ["bf16", "fp32"])
 def test_predict_matches_reference_golden(golden_meta, name, precision):
     from aind_exaspim_neuron_segmentation_b200 import predict
@@ -44,6 +45,8 @@ def test_predict_matches_reference_golden(golden_meta, name, precision):
     if precision == "fp32" and name == "mixed_160x160x100":
         pytest.skip("fp32 validation mode is the slow SIMT path; covered by the other cases")
     vol = make_volume(meta["shape"], meta["vol_seed"])
+    if "float_image" in meta:
+        vol = float_image(vol, meta["float_image"])
     model = _model(*meta["weights"], precision=precision)
     before = vol.copy()
     out = predict(vol, model, verbose=False, **_kwargs(meta))
@@ -271,3 +274,24 @@ def test_config2_512_matches_oracle_on_sampled_blocks():
         want_sum = json.load(f)["n1_512"]
     print("bench checksum", checksum, "recorded", want_sum["value"])
     assert abs(checksum - want_sum["value"]) <= want_sum["tol"]
+
+
+def test_float_images_too_many_values_or_nan_raise():
+    """predict() takes float images whose clipped values form a table of at most 65536 entries
+    (goldens float32_integers / float32_quarters / float64_thirds above); anything else is refused,
+    never approximated."""
+    from aind_exaspim_neuron_segmentation_b200 import predict
+
+    model = _model("rescaled", 7)
+    rng = np.random.default_rng(5)
+    noisy = (rng.random((48, 48, 48)) * 900).astype(np.float32)      # ~110 000 distinct values
+    with pytest.raises(RuntimeError, match="65536"):
+        predict(noisy, model, verbose=False, patch_shape=(32, 32, 32), overlap=(8, 8, 8), trim=4)
+    bad = make_volume((48, 48, 48), 1).astype(np.float32)
+    bad[3, 4, 5] = np.nan
+    with pytest.raises(RuntimeError, match="NaN"):
+        predict(bad, model, verbose=False, patch_shape=(32, 32, 32), overlap=(8, 8, 8), trim=4)
+    # a clip below every noisy value leaves ONE distinct value: allowed (and all-constant input)
+    flat = predict(noisy + 1000, model, verbose=False, brightness_clip=500, patch_shape=(32, 32, 32),
+                   overlap=(8, 8, 8), trim=4)
+    assert flat.shape == (3, 48, 48, 48) and np.isfinite(flat).all()

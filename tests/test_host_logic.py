@@ -218,3 +218,23 @@ def test_sharded_rejects_triple_z_overlap(monkeypatch):
     with pytest.raises(ValueError, match="three or more z rows"):
         inference.predict_sharded(vol, None, patch_shape=(32, 32, 32), overlap=(24, 8, 8), trim=0,
                                   backend=object())
+
+
+def test_percentiles_from_histogram_and_value_table_are_bit_exact():
+    """Float images: np.percentile from the histogram of ranks + the table of distinct values
+    (exa_percentiles_from_hist_values), float32 (numpy takes the neighbour difference in float32)
+    and float64."""
+    from aind_exaspim_neuron_segmentation_b200.engine import percentiles_from_hist_values
+
+    rng = np.random.default_rng(3)
+    for dt in (np.float32, np.float64):
+        for _ in range(12):
+            n = int(rng.integers(5, 4000))
+            pool = np.unique((rng.random(int(rng.integers(2, 300))) * 1000 / 3).astype(dt))
+            a = rng.choice(pool, n).astype(dt)
+            table = np.unique(a)
+            hist = np.array([(a == t).sum() for t in table], np.uint64)
+            for pct in ((1, 99.9), (5, 99), (0, 100), (50, 50.5), (33.3, 66.6)):
+                ref = np.percentile(a, pct)
+                got = percentiles_from_hist_values(hist, table.astype(np.float64), dt == np.float32, *pct)
+                assert (float(ref[0]), float(ref[1])) == got, (dt, pct)

@@ -6,11 +6,13 @@ import pytest
 from oracle import predict_ref as pr
 from oracle.unet_ref import make_forward_fn
 
-from helpers import compare_with_golden, load_golden, make_volume, state_dict_for
+from helpers import compare_with_golden, float_image, load_golden, make_volume, state_dict_for
 
 
 def _run_oracle(meta):
     vol = make_volume(meta["shape"], meta["vol_seed"])
+    if "float_image" in meta:
+        vol = float_image(vol, meta["float_image"])
     sd = state_dict_for(*meta["weights"])
     kw = dict(meta["kwargs"])
     for key in ("patch_shape", "overlap", "normalization_percentiles"):
@@ -20,7 +22,8 @@ def _run_oracle(meta):
 
 
 @pytest.mark.parametrize("name", ["small_p32", "small_p48_trim0ish", "c1_rescaled_96", "multireflect_p32",
-                                  "p128_single", "variant_convT", "variant_w2", "variant_convT_w2"])
+                                  "p128_single", "variant_convT", "variant_w2", "variant_convT_w2",
+                                  "float32_integers", "float32_quarters", "float64_thirds"])
 def test_oracle_matches_reference_golden(golden_meta, name):
     out = _run_oracle(golden_meta["cases"][name])
     # same fp32 arithmetic (torch CPU conv) -> only thread-count dependent reduction order differs
