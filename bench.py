@@ -566,7 +566,7 @@ def run_segment(args):
             del seg32
             dev16, dev32 = torch.from_numpy(aff).cuda(), torch.from_numpy(aff32).cuda()
             extra = []
-            for thr, min_size in (([0.0], 0), ([0.2], 0), ([0.35], 0)):
+            for thr, min_size in (([0.0], 0), ([0.45], 0), ([0.5], 0), ([0.55], 0)):
                 a = affinities_to_segmentation(dev16, thr, min_size)
                 b = affinities_to_segmentation(dev32, thr, min_size)
                 extra.append({"thresholds": thr, "min_segment_size": min_size,
