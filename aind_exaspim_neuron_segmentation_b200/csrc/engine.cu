@@ -1073,6 +1073,8 @@ Status Engine::stitch_planes(const float* seed_dev, float* out_dev, size_t out_c
 Status Engine::copy_planes_to_peers(const float* out_dev, size_t out_cstride, int nz, int y0, int y1,
                                     cudaStream_t s) {
   if (!peer_ready_) {
+    const char* ns = getenv("EXA_PEER_STREAMS");
+    if (ns && atoi(ns) >= 1 && atoi(ns) <= kPeerStreams) n_peer_streams_ = atoi(ns);
     EXA_CUDA(cudaEventCreateWithFlags(&peer_ready_, cudaEventDisableTiming));
     for (int i = 0; i < kPeerStreams; ++i) {
       EXA_CUDA(cudaStreamCreateWithFlags(&peer_stream_[i], cudaStreamNonBlocking));
@@ -1083,9 +1085,9 @@ Status Engine::copy_planes_to_peers(const float* out_dev, size_t out_cstride, in
   const ptrdiff_t off = out_dev - peer_local_;
   const bool band = y1 > y0 && !(y0 == 0 && (size_t)y1 * plan_.W == plane);
   EXA_CUDA(cudaEventRecord(peer_ready_, s));
-  for (int i = 0; i < kPeerStreams; ++i) EXA_CUDA(cudaStreamWaitEvent(peer_stream_[i], peer_ready_, 0));
+  for (int i = 0; i < n_peer_streams_; ++i) EXA_CUDA(cudaStreamWaitEvent(peer_stream_[i], peer_ready_, 0));
   for (size_t i = 0; i < peer_bases_.size(); ++i) {
-    cudaStream_t ps = peer_stream_[i % kPeerStreams];
+    cudaStream_t ps = peer_stream_[i % n_peer_streams_];
     for (int c = 0; c < out_channels_; ++c) {
       const float* src = out_dev + c * out_cstride;
       float* dst = peer_bases_[i] + off + c * out_cstride;
@@ -1105,7 +1107,7 @@ Status Engine::copy_planes_to_peers(const float* out_dev, size_t out_cstride, in
 
 Status Engine::join_peer_copies(cudaStream_t s) {
   if (!peer_pending_) return Status::OK();
-  for (int i = 0; i < kPeerStreams; ++i) {
+  for (int i = 0; i < n_peer_streams_; ++i) {
     EXA_CUDA(cudaEventRecord(peer_done_[i], peer_stream_[i]));
     EXA_CUDA(cudaStreamWaitEvent(s, peer_done_[i], 0));
   }

@@ -221,9 +221,10 @@ class Engine {
   // finished planes go to the peers' copies by copy-engine transfers on side streams (no SM time,
   // overlapped with the next waves); EXA_GATHER=store: by stores from the stitch kernel instead
   bool peer_ce_ = true;
-  static constexpr int kPeerStreams = 4;
-  cudaStream_t peer_stream_[kPeerStreams] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t peer_ready_ = nullptr, peer_done_[kPeerStreams] = {nullptr, nullptr, nullptr, nullptr};
+  static constexpr int kPeerStreams = 8;   // created; n_peer_streams_ of them are used
+  int n_peer_streams_ = 4;                 // EXA_PEER_STREAMS (1..8)
+  cudaStream_t peer_stream_[kPeerStreams] = {};
+  cudaEvent_t peer_ready_ = nullptr, peer_done_[kPeerStreams] = {};
   bool peer_pending_ = false;
   Status copy_planes_to_peers(const float* out_dev, size_t out_cstride, int nz, int y0, int y1,
                               cudaStream_t s);
