@@ -222,7 +222,7 @@ class Engine {
   // overlapped with the next waves); EXA_GATHER=store: by stores from the stitch kernel instead
   bool peer_ce_ = true;
   static constexpr int kPeerStreams = 8;   // created; n_peer_streams_ of them are used
-  int n_peer_streams_ = 4;                 // EXA_PEER_STREAMS (1..8)
+  int n_peer_streams_ = 7;                 // EXA_PEER_STREAMS (1..8); 7 = one per peer at 8 GPUs
   cudaStream_t peer_stream_[kPeerStreams] = {};
   cudaEvent_t peer_ready_ = nullptr, peer_done_[kPeerStreams] = {};
   bool peer_pending_ = false;
