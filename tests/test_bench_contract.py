@@ -47,3 +47,22 @@ def test_reference_arm_prints_one_contract_line():
     base = line["cpu_baseline"]
     assert base["kind"] == "port" and base["cores"] >= 1 and base["value"] == line["value"]
     assert "sample" in base and line["config"]["workload"].startswith("predict() on a synthetic 512x512x512")
+
+
+def test_adapted_rand_on_device_equals_the_oracle_form():
+    """bench.py --workload segment scores 1024^3 label volumes with a torch implementation of the
+    oracle's adapted-Rand agreement; both must agree (here on CPU tensors)."""
+    import numpy as np
+    import torch
+
+    import bench
+    from oracle.watershed_ref import adapted_rand_agreement
+
+    rng = np.random.default_rng(0)
+    for _ in range(5):
+        a = rng.integers(0, 9, (12, 14, 10))
+        b = rng.integers(0, 6, (12, 14, 10))
+        got = bench.adapted_rand_on_device(torch.from_numpy(a), torch.from_numpy(b))
+        assert abs(got - adapted_rand_agreement(a, b)) < 1e-12
+    z = np.zeros((4, 4, 4), np.int64)
+    assert bench.adapted_rand_on_device(torch.from_numpy(z + 3), torch.from_numpy(z)) == 1.0
