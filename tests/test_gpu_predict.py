@@ -192,6 +192,17 @@ def test_predict_streamed_equals_predict(tmp_path):
     assert np.array_equal(out1, predict(vol, fg, affinity_mode=False, verbose=False, **kw))
     with pytest.raises(ValueError):
         predict_streamed(vol[None], model, np.empty((3,) + shape, np.float32), **kw)
+    # file-backed source and sink (utils/img_util.py): a directory of .npy z-chunks read through
+    # img_util.read(), one .npy file per finished plane range written by NpySink
+    from aind_exaspim_neuron_segmentation_b200.utils import img_util
+
+    chunks = tmp_path / "chunks"
+    chunks.mkdir()
+    for i, (a, b) in enumerate(((0, 40), (40, 41), (41, 120), (120, 150))):
+        np.save(chunks / f"z{i:03d}.npy", vol[a:b])
+    sink = img_util.NpySink(str(tmp_path / "aff_chunks"))
+    predict_streamed(img_util.read(str(chunks)), model, sink, rows_per_chunk=2, **kw)
+    assert np.array_equal(img_util.NpySink.open(str(tmp_path / "aff_chunks")), ref)
 
 
 def test_config2_512_matches_oracle_on_sampled_blocks():

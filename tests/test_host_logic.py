@@ -238,3 +238,31 @@ def test_percentiles_from_histogram_and_value_table_are_bit_exact():
                 ref = np.percentile(a, pct)
                 got = percentiles_from_hist_values(hist, table.astype(np.float64), dt == np.float32, *pct)
                 assert (float(ref[0]), float(ref[1])) == got, (dt, pct)
+
+
+def test_npy_stack_and_sink_round_trip(tmp_path):
+    """utils/img_util.py: a directory of .npy z-chunks as a sliceable source, one file per assigned
+    plane range as a sink (what predict_streamed reads from / writes to), read() dispatch."""
+    from aind_exaspim_neuron_segmentation_b200.utils import img_util
+
+    rng = np.random.default_rng(0)
+    vol = rng.integers(0, 2000, (37, 6, 5), dtype=np.uint16)
+    src = tmp_path / "vol"
+    src.mkdir()
+    for i, (a, b) in enumerate(((0, 10), (10, 11), (11, 30), (30, 37))):
+        np.save(src / f"chunk{i}.npy", vol[a:b])
+    stack = img_util.read(str(src))
+    assert isinstance(stack, img_util.NpyStack) and stack.shape == vol.shape and stack.dtype == vol.dtype
+    for z0, z1 in ((0, 37), (3, 9), (9, 12), (10, 11), (29, 37), (12, 12)):
+        assert np.array_equal(stack[z0:z1], vol[z0:z1])
+    assert np.array_equal(stack[5], vol[5]) and np.array_equal(stack[-1], vol[-1])
+    assert np.array_equal(stack[4:20, 1:3], vol[4:20, 1:3]) and np.array_equal(np.asarray(stack), vol)
+    np.save(tmp_path / "single.npy", vol)
+    assert np.array_equal(img_util.read(str(tmp_path / "single.npy")), vol)
+    with pytest.raises(ValueError):
+        img_util.read(str(tmp_path / "volume.xyz"))
+    sink = img_util.NpySink(str(tmp_path / "out"), channels=3)
+    res = rng.random((3, 37, 6, 5)).astype(np.float32)
+    for z0, z1 in ((0, 16), (16, 17), (17, 37)):
+        sink[:, z0:z1] = res[:, z0:z1]
+    assert np.array_equal(img_util.NpySink.open(str(tmp_path / "out")), res)
