@@ -108,3 +108,39 @@ def test_anisotropic_patch_shapes_match_oracle(patch, overlap, trim, shape):
     print(patch, "max abs err", err)
     assert err <= BF16_TOL, err
     assert np.array_equal(out == 0, ref == 0)
+
+
+VARIANT_SCRIPT = """
+import sys
+import numpy as np
+sys.path.insert(0, {root!r}); sys.path.insert(0, {tests!r})
+from helpers import lightsheet_volume, state_dict_for
+from aind_exaspim_neuron_segmentation_b200 import UNet3D, predict
+from oracle.predict_ref import predict_ref
+from oracle.unet_ref import make_forward_fn
+sd = state_dict_for("rescaled", 61)
+model = UNet3D(output_channels=3); model.load_state_dict(sd, strict=True); model = model.cuda().eval()
+vol = lightsheet_volume((96, 112, 128), 62)
+out = predict(vol, model, verbose=False)
+ref = predict_ref(vol, make_forward_fn(sd))
+print("MAXERR", float(np.abs(out - ref).max()), bool(np.array_equal(out == 0, ref == 0)))
+"""
+
+
+@pytest.mark.parametrize("env", [{"EXA_NO_PAIR": "1"}, {"EXA_NO_ZFOLD": "1"}, {"EXA_NO_TC_STEM": "1"},
+                                 {"EXA_NO_MT2": "1"}, {"EXA_UP_CPT": "4"}, {"EXA_STITCH_OVERLAP": "1"}])
+def test_alternative_kernel_variants_match_oracle(env):
+    """The kernel variants behind the A/B knobs (one CTA per MMA, per-tap conv everywhere, SIMT
+    stem, single M tile, 4-channel upsample threads, stitch on a second stream) stay correct: a
+    96^3-patch predict() under each knob, in a fresh process, against the oracle."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = VARIANT_SCRIPT.format(root=root, tests=os.path.join(root, "tests"))
+    res = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=600,
+                         env={**os.environ, **env})
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = [ln for ln in res.stdout.splitlines() if ln.startswith("MAXERR")][-1].split()
+    assert float(line[1]) <= BF16_TOL and line[2] == "True", (env, line)
