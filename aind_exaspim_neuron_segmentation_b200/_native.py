@@ -16,9 +16,10 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_PKG_DIR, "csrc")
 LIB_PATH = os.path.join(_PKG_DIR, "libexaspim_b200.so")
 SOURCES = ["capi.cu", "engine.cu", "kernels_mem.cu", "conv_umma.cu", "conv_zfold.cu", "conv_stem.cu",
-           "watershed.cu", "float_volume.cu"]
+           "watershed.cu", "float_volume.cu", "train_kernels.cu", "trainer.cu"]
 HEADERS = ["common.cuh", "conv_umma.cuh", "conv_zfold.cuh", "conv_zfold2.cuh", "conv_stem.cuh", "engine.h",
-           "kernels.h", "tmap.h", "watershed.h", "ws_agglomerate.h", "float_volume.h"]
+           "kernels.h", "tmap.h", "watershed.h", "ws_agglomerate.h", "float_volume.h", "train_kernels.h",
+           "trainer.h"]
 
 PRECISION_BF16 = 0
 PRECISION_FP32 = 1
@@ -182,6 +183,27 @@ _SIGNATURES = {
                                           ctypes.POINTER(ctypes.c_int64),
                                           ctypes.POINTER(ctypes.c_int32), ctypes.c_int]),
     "exa_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),
+    # training step
+    "exa_train_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
+    "exa_train_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "exa_train_last_error": (ctypes.c_char_p, [ctypes.c_void_p]),
+    "exa_train_bind": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p,
+                                      ctypes.POINTER(ctypes.c_int64), ctypes.c_int]),
+    "exa_train_grad_elems": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)]),
+    "exa_train_grad_slot": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p,
+                                           ctypes.POINTER(ctypes.c_int64),
+                                           ctypes.POINTER(ctypes.c_int64)]),
+    "exa_train_out_channels": (ctypes.c_int, [ctypes.c_void_p]),
+    "exa_train_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                         ctypes.POINTER(ctypes.c_int32), ctypes.c_void_p,
+                                         ctypes.c_void_p]),
+    "exa_train_backward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                          ctypes.c_void_p, ctypes.c_void_p]),
+    "exa_train_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),
+    "exa_train_workspace_bytes": (ctypes.c_int64, [ctypes.c_void_p]),
+    "exa_bce_with_logits": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                           ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p,
+                                           ctypes.c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -7,7 +7,13 @@
 #include "../../include/exaspim_b200.h"
 #include "engine.h"
 #include "float_volume.h"
+#include "trainer.h"
 #include "watershed.h"
+
+struct exa_trainer {
+  exa::Trainer impl;
+  exa_trainer(int device, int precision) : impl(device, precision) {}
+};
 
 struct exa_engine {
   exa::Engine impl;
@@ -56,6 +62,23 @@ int guarded_static(F&& f) {
     return EXA_ERR_INVALID;
   } catch (...) {
     g_create_error = "unknown exception";
+    return EXA_ERR_INVALID;
+  }
+}
+
+template <typename F>
+int guarded_train(exa_trainer* t, F&& f) {
+  if (!t) return EXA_ERR_INVALID;
+  try {
+    exa::Status s = f();
+    if (s.ok) return EXA_OK;
+    t->impl.last_error = s.msg;
+    return code_for(s.msg);
+  } catch (const std::exception& ex) {
+    t->impl.last_error = std::string("exception: ") + ex.what();
+    return EXA_ERR_INVALID;
+  } catch (...) {
+    t->impl.last_error = "unknown exception";
     return EXA_ERR_INVALID;
   }
 }
@@ -323,5 +346,80 @@ int exa_profile_layers(exa_engine* e, double* ms, int64_t* launches, int32_t* ki
 }
 
 int64_t exa_launch_count(const exa_engine* e) { return e ? e->impl.launches : -1; }
+
+// ---- training step (trainer.h) --------------------------------------------------------------
+int exa_train_create(int device, int precision, exa_trainer** out) {
+  if (!out) return EXA_ERR_INVALID;
+  *out = nullptr;
+  return guarded_static([&] {
+    exa_trainer* t = new (std::nothrow) exa_trainer(device, precision);
+    if (!t) return exa::Status::Err("out of host memory");
+    exa::Status s = t->impl.init();
+    if (!s.ok) {
+      delete t;
+      return s;
+    }
+    *out = t;
+    return exa::Status::OK();
+  });
+}
+
+int exa_train_destroy(exa_trainer* t) {
+  if (!t) return EXA_ERR_INVALID;
+  delete t;
+  return EXA_OK;
+}
+
+const char* exa_train_last_error(const exa_trainer* t) {
+  return t ? t->impl.last_error.c_str() : g_create_error.c_str();
+}
+
+int exa_train_bind(exa_trainer* t, const char* name, float* dev_ptr, const int64_t* shape,
+                   int ndim) {
+  return guarded_train(t, [&] { return t->impl.bind(name, dev_ptr, shape, ndim); });
+}
+
+int exa_train_grad_elems(exa_trainer* t, int64_t* n) {
+  return guarded_train(t, [&] { return t->impl.grad_elems(n); });
+}
+
+int exa_train_grad_slot(exa_trainer* t, const char* name, int64_t* offset, int64_t* numel) {
+  return guarded_train(t, [&] { return t->impl.grad_slot(name, offset, numel); });
+}
+
+int exa_train_out_channels(exa_trainer* t) {
+  if (!t) return EXA_ERR_INVALID;
+  int64_t n = 0;
+  const int code = guarded_train(t, [&] { return t->impl.grad_elems(&n); });  // resolves
+  return code < 0 ? code : t->impl.out_channels();
+}
+
+int exa_train_forward(exa_trainer* t, const float* x_dev, int batch, const int32_t patch[3],
+                      float* logits_dev, void* stream) {
+  return guarded_train(t, [&] {
+    if (!patch) return exa::Status::Err("train_forward: null patch");
+    return t->impl.forward(x_dev, batch, patch, logits_dev, (cudaStream_t)stream);
+  });
+}
+
+int exa_train_backward(exa_trainer* t, const float* x_dev, const float* grad_logits_dev,
+                       float* grads_dev, void* stream) {
+  return guarded_train(
+      t, [&] { return t->impl.backward(x_dev, grad_logits_dev, grads_dev, (cudaStream_t)stream); });
+}
+
+int64_t exa_train_launch_count(const exa_trainer* t) { return t ? t->impl.launches : -1; }
+int64_t exa_train_workspace_bytes(const exa_trainer* t) {
+  return t ? (int64_t)t->impl.workspace_bytes() : -1;
+}
+
+int exa_bce_with_logits(const float* logits_dev, const float* target_dev, int64_t n,
+                        float grad_scale, double* loss_sum_dev, float* grad_dev, void* stream) {
+  return guarded_static([&] {
+    if (n <= 0) return exa::Status::Err("bce_with_logits: n must be positive");
+    return exa::launch_bce_with_logits(logits_dev, target_dev, (size_t)n, grad_scale, loss_sum_dev,
+                                       grad_dev, (cudaStream_t)stream);
+  });
+}
 
 }  // extern "C"

@@ -8,7 +8,10 @@ SURVEY.md 8a-1), so checkpoints written by the reference's Trainer load with
 ``width_multiplier`` 1..4 are supported by the engine as well.  The
 arithmetic is not done by these torch modules -- ``forward`` hands the input to
 ``Engine.forward`` (C ABI ``exa_forward``), which folds the eval-mode BatchNorm
-into the convolutions and runs the CUDA kernels.  On a CPU tensor ``forward``
+into the convolutions and runs the CUDA kernels.  In ``train()`` mode ``forward`` goes through
+the native trainer instead (``training.train_forward``: batch-statistics BatchNorm, logits with
+a ``grad_fn`` whose backward yields every parameter gradient), so the reference's
+``Trainer`` (train.py:123-157) runs on this module unchanged.  On a CPU tensor ``forward``
 raises: there is no fallback path.
 """
 
@@ -138,6 +141,12 @@ class UNet3D(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("UNet3D (B200 engine) needs CUDA tensors; there is no CPU fallback")
         if self.training:
-            raise RuntimeError("training-mode forward is outside this engine's scope")
+            # train.py:200-223 (Trainer.forward_pass): batch statistics, autograd-visible
+            if not self.trilinear or self.channels[0] != 32:
+                raise NotImplementedError("the native trainer covers the configuration the "
+                                          "reference Trainer builds (train.py:77): "
+                                          "trilinear=True, width_multiplier=1")
+            from .training import train_forward
+            return train_forward(self, x, self.precision)
         with torch.no_grad():
             return self.engine().forward(x)

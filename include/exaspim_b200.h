@@ -236,6 +236,44 @@ int exa_profile_layers(exa_engine* e, double* ms, int64_t* launches, int32_t* ki
 /* number of kernel launches issued by this engine since creation (bench bookkeeping) */
 int64_t exa_launch_count(const exa_engine* e);
 
+/* ---- training step (reference machine_learning/train.py:123-157, 200-223) ----
+ * What `model.train(); hat_y = model(x); loss = criterion(hat_y, y); loss.backward()` does for
+ * the U-Net of unet3d.py:16-105 (trilinear=True, width_multiplier=1, what Trainer builds at
+ * train.py:77): the forward pass with BatchNorm3d in TRAINING mode (batch statistics; running
+ * statistics updated in place, momentum 0.1, unet3d.py:144,147) and the backward pass to every
+ * parameter gradient.  The reference has no FFI; its boundary is nn.Module.__call__ plus
+ * autograd, which INTEGRATION.md maps onto these calls through a torch.autograd.Function.
+ *
+ * Parameters stay where the optimiser keeps them: exa_train_bind() takes the DEVICE pointer of
+ * every float32 state_dict entry (the 128 entries of SURVEY.md 8a-1 minus the 18 int64
+ * num_batches_tracked counters, which the caller increments).  Every forward reads the current
+ * values.  The gradients of one backward are written (not accumulated) into one flat float32
+ * device buffer of exa_train_grad_elems() elements; exa_train_grad_slot() gives the slot of a
+ * parameter.  A backward differentiates the most recent forward of the same trainer. */
+typedef struct exa_trainer exa_trainer;
+int exa_train_create(int device, int precision, exa_trainer** out);
+int exa_train_destroy(exa_trainer* t);
+const char* exa_train_last_error(const exa_trainer* t); /* t may be NULL: last create error */
+int exa_train_bind(exa_trainer* t, const char* name, float* dev_ptr, const int64_t* shape,
+                   int ndim);
+int exa_train_grad_elems(exa_trainer* t, int64_t* n);
+int exa_train_grad_slot(exa_trainer* t, const char* name, int64_t* offset, int64_t* numel);
+int exa_train_out_channels(exa_trainer* t);
+/* x: (B,1,D,H,W) float32 on the device, patch = (D,H,W) multiples of 16;
+ * logits: (B,C,D,H,W) float32 on the device (unet3d.py:77-105 in train() mode) */
+int exa_train_forward(exa_trainer* t, const float* x_dev, int batch, const int32_t patch[3],
+                      float* logits_dev, void* stream);
+/* x: the input of that forward; grad_logits: dLoss/dlogits, (B,C,D,H,W) float32 */
+int exa_train_backward(exa_trainer* t, const float* x_dev, const float* grad_logits_dev,
+                       float* grads_dev, void* stream);
+int64_t exa_train_launch_count(const exa_trainer* t);
+int64_t exa_train_workspace_bytes(const exa_trainer* t);
+/* nn.BCEWithLogitsLoss() (train.py:76,222), mean reduction: *loss_sum_dev (double, zeroed by the
+ * caller) += sum of the element losses; when grad_dev is not NULL it receives
+ * grad_scale * (sigmoid(logit) - target) / n  (grad_scale = the GradScaler factor, train.py:140) */
+int exa_bce_with_logits(const float* logits_dev, const float* target_dev, int64_t n,
+                        float grad_scale, double* loss_sum_dev, float* grad_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
