@@ -199,8 +199,17 @@ _SIGNATURES = {
                                          ctypes.c_void_p]),
     "exa_train_backward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                           ctypes.c_void_p, ctypes.c_void_p]),
+    "exa_train_profile_begin": (ctypes.c_int, [ctypes.c_void_p]),
+    "exa_train_profile_end": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double),
+                                             ctypes.POINTER(ctypes.c_int64), ctypes.c_int]),
     "exa_train_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),
     "exa_train_workspace_bytes": (ctypes.c_int64, [ctypes.c_void_p]),
+    "exa_conv3d_weight_grad": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                              ctypes.c_void_p] + [ctypes.c_int] * 6 +
+                               [ctypes.c_void_p, ctypes.c_void_p]),
+    "exa_conv3d_data_grad": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                            ctypes.c_void_p] + [ctypes.c_int] * 6 +
+                             [ctypes.c_void_p, ctypes.c_void_p]),
     "exa_bce_with_logits": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
                                            ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p,
                                            ctypes.c_void_p]),

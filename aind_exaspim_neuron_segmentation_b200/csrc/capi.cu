@@ -408,9 +408,35 @@ int exa_train_backward(exa_trainer* t, const float* x_dev, const float* grad_log
       t, [&] { return t->impl.backward(x_dev, grad_logits_dev, grads_dev, (cudaStream_t)stream); });
 }
 
+int exa_train_profile_begin(exa_trainer* t) {
+  return guarded_train(t, [&] { return t->impl.profile_begin(); });
+}
+
+int exa_train_profile_end(exa_trainer* t, double* ms_by_category, int64_t* launches_by_category,
+                          int n) {
+  return guarded_train(
+      t, [&] { return t->impl.profile_end(ms_by_category, launches_by_category, n); });
+}
+
 int64_t exa_train_launch_count(const exa_trainer* t) { return t ? t->impl.launches : -1; }
 int64_t exa_train_workspace_bytes(const exa_trainer* t) {
   return t ? (int64_t)t->impl.workspace_bytes() : -1;
+}
+
+int exa_conv3d_weight_grad(int device, int precision, const void* x_dev, const void* dz_dev, int B,
+                           int D, int H, int W, int cin, int cout, float* dw_dev, void* stream) {
+  return guarded_static([&] {
+    return exa::conv3d_weight_grad(device, precision, x_dev, dz_dev, B, D, H, W, cin, cout, dw_dev,
+                                   (cudaStream_t)stream);
+  });
+}
+
+int exa_conv3d_data_grad(int device, int precision, const void* dz_dev, const float* w_dev, int B,
+                         int D, int H, int W, int cin, int cout, void* dx_dev, void* stream) {
+  return guarded_static([&] {
+    return exa::conv3d_data_grad(device, precision, dz_dev, w_dev, B, D, H, W, cin, cout, dx_dev,
+                                 (cudaStream_t)stream);
+  });
 }
 
 int exa_bce_with_logits(const float* logits_dev, const float* target_dev, int64_t n,

@@ -478,6 +478,38 @@ Status launch_double_to_float(const double* in, float* out, int n, cudaStream_t 
   return Status::OK();
 }
 
+template <typename T>
+__global__ void __launch_bounds__(256)
+decode_kernel(const T* __restrict__ in, int i_cstride, int i_coff, bool enc, T* __restrict__ out,
+              int o_cstride, int o_coff, int C, size_t voxels) {
+  const int cv = C / 8;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= voxels * cv) return;
+  const int c8 = (int)(i % cv);
+  const size_t v = i / cv;
+  float f[8];
+  load8_dec<T>(in + v * i_cstride + i_coff + 8 * c8, enc, f);
+  store8<T>(out + v * o_cstride + o_coff + 8 * c8, f);
+}
+
+Status launch_decode(const TView& in, const Act& out, cudaStream_t s) {
+  EXA_CHECK(vec_ok(in.a) && vec_ok(out) && in.a.C == out.C && same_grid(in.a, out) &&
+                in.a.fp32 == out.fp32,
+            "decode: shape mismatch");
+  const size_t vox = out.voxels();
+  const unsigned blocks = (unsigned)ceil_div64((int64_t)(vox * (out.C / 8)), 256);
+  if (out.fp32)
+    decode_kernel<float><<<blocks, 256, 0, s>>>((const float*)in.a.ptr, in.a.cstride, in.a.coff,
+                                                 in.enc, (float*)out.ptr, out.cstride, out.coff,
+                                                 out.C, vox);
+  else
+    decode_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(
+        (const __nv_bfloat16*)in.a.ptr, in.a.cstride, in.a.coff, in.enc, (__nv_bfloat16*)out.ptr,
+        out.cstride, out.coff, out.C, vox);
+  EXA_CUDA(cudaGetLastError());
+  return Status::OK();
+}
+
 // ---------------------------------------------------------------------------
 // T3: max-pool backward (+ skip gradient), upsample adjoint, head backward
 // ---------------------------------------------------------------------------
@@ -1149,13 +1181,11 @@ bce_with_logits_kernel(const float* __restrict__ x, const float* __restrict__ y,
   __shared__ float sh[256];
   float local = 0.f;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  int cnt = 0;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float xv = x[i], yv = y[i];
     // max(x, 0) - x y + log(1 + exp(-|x|)): the stable form ATen uses
     local += fmaxf(xv, 0.f) - xv * yv + log1pf(expf(-fabsf(xv)));
     if (grad) grad[i] = gscale * (1.f / (1.f + expf(-xv)) - yv);
-    ++cnt;
   }
   sh[threadIdx.x] = local;
   __syncthreads();

@@ -57,6 +57,8 @@ Status launch_bn_bwd_apply(const TView& grad_a, const Act& a, const TView& z, co
                            const float* rstd, const float* coef, const Act& dz, double* bias_sums,
                            cudaStream_t s);
 Status launch_double_to_float(const double* in, float* out, int n, cudaStream_t s);
+// out = plain values of an (encoded) tensor
+Status launch_decode(const TView& in, const Act& out, cudaStream_t s);
 
 // ---- MaxPool3d(2) backward merged with the skip connection's gradient --------------------------
 // out[v] = skip[v] + (v is the first maximum of its 2x2x2 window of `a` ? pooled[window] : 0)

@@ -45,14 +45,65 @@ Act channel_slice(const Act& a, int c0, int n) {
 
 }  // namespace
 
-#define EXA_LAUNCH(expr) \
-  do {                   \
-    EXA_TRY(expr);       \
-    ++launches;          \
+#define EXA_LAUNCH(cat, expr)   \
+  do {                         \
+    Scope _sc(this, (cat), s); \
+    EXA_TRY(expr);             \
   } while (0)
+
+Trainer::Scope::Scope(Trainer* tr, int cat, cudaStream_t st) : t(tr), s(st) {
+  ++t->launches;
+  if (!t->prof_on_) return;
+  ProfRec r;
+  r.cat = cat;
+  if (cudaEventCreate(&r.start) != cudaSuccess || cudaEventCreate(&r.stop) != cudaSuccess) return;
+  cudaEventRecord(r.start, s);
+  stop = r.stop;
+  t->prof_.push_back(r);
+}
+Trainer::Scope::~Scope() {
+  if (stop) cudaEventRecord(stop, s);
+}
+
+Status Trainer::profile_begin() {
+  EXA_CUDA(cudaSetDevice(device_));
+  for (auto& r : prof_) {
+    cudaEventDestroy(r.start);
+    cudaEventDestroy(r.stop);
+  }
+  prof_.clear();
+  prof_on_ = true;
+  return Status::OK();
+}
+
+Status Trainer::profile_end(double* ms_by_cat, int64_t* launches_by_cat, int n) {
+  EXA_CHECK(ms_by_cat && launches_by_cat && n >= CAT_COUNT, "train_profile_end: need >= 8 slots");
+  EXA_CUDA(cudaSetDevice(device_));
+  prof_on_ = false;
+  for (int i = 0; i < n; ++i) {
+    ms_by_cat[i] = 0.0;
+    launches_by_cat[i] = 0;
+  }
+  EXA_CUDA(cudaDeviceSynchronize());
+  for (auto& r : prof_) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.start, r.stop) == cudaSuccess) {
+      ms_by_cat[r.cat] += ms;
+      ++launches_by_cat[r.cat];
+    }
+    cudaEventDestroy(r.start);
+    cudaEventDestroy(r.stop);
+  }
+  prof_.clear();
+  return Status::OK();
+}
 
 Trainer::~Trainer() {
   cudaSetDevice(device_);
+  for (auto& r : prof_) {
+    cudaEventDestroy(r.start);
+    cudaEventDestroy(r.stop);
+  }
   free_dev(ws_);
   free_dev(small_);
 }
@@ -368,7 +419,8 @@ Status Trainer::conv_any(const Act& in, const Act& out, const void* w_plain, con
                          const float* bias, cudaStream_t s) {
   if (precision_ == EXA_PRECISION_FP32)
     return launch_conv_fp32(in, out, (const float*)w_plain, bias, s);
-  if (w_zf && conv_zfold_supported(in, out.C, true))
+  static const bool no_zf = getenv("EXA_TRAIN_NO_ZFOLD") != nullptr;  // A/B: generic kernel only
+  if (!no_zf && w_zf && conv_zfold_supported(in, out.C, true))
     return launch_conv_zfold(in, out, (const __nv_bfloat16*)w_zf, bias, nullptr, nullptr, nullptr,
                              num_sms_, true, s);
   return launch_conv_umma(in, out, (const __nv_bfloat16*)w_plain, bias, nullptr, num_sms_, s);
@@ -379,40 +431,40 @@ Status Trainer::layer_forward(int l, const float* x, cudaStream_t s) {
   const bool f32 = precision_ == EXA_PRECISION_FP32;
   if (l == 0) {
     if (f32) {
-      EXA_LAUNCH(launch_pack_stem_fp32(L.w, (float*)L.w_fwd, L.cout, s));
-      EXA_LAUNCH(launch_expand_input16(x, (float*)stem_in_, L.z.voxels(), s));
+      EXA_LAUNCH(CAT_PACK, launch_pack_stem_fp32(L.w, (float*)L.w_fwd, L.cout, s));
+      EXA_LAUNCH(CAT_PACK, launch_expand_input16(x, (float*)stem_in_, L.z.voxels(), s));
       Act in = L.z;
       in.ptr = stem_in_;
       in.C = in.cstride = 16;
-      EXA_LAUNCH(launch_conv_fp32(in, L.z, (const float*)L.w_fwd, L.b, s));
+      EXA_LAUNCH(CAT_FPROP, launch_conv_fp32(in, L.z, (const float*)L.w_fwd, L.b, s));
     } else {
       const int groups = L.cout / 32;
-      EXA_LAUNCH(launch_pack_stem_band(L.w, (__nv_bfloat16*)L.w_fwd, groups, s));
+      EXA_LAUNCH(CAT_PACK, launch_pack_stem_band(L.w, (__nv_bfloat16*)L.w_fwd, groups, s));
       PatchSource src;
       src.x = x;
-      EXA_LAUNCH(launch_stem_split(src, L.z.B, L.z.D, L.z.H, L.z.W, (__nv_bfloat16*)stem_in_, s));
+      EXA_LAUNCH(CAT_FPROP, launch_stem_split(src, L.z.B, L.z.D, L.z.H, L.z.W, (__nv_bfloat16*)stem_in_, s));
       for (int g = 0; g < groups; ++g)
-        EXA_LAUNCH(launch_stem_tc((const __nv_bfloat16*)stem_in_,
+        EXA_LAUNCH(CAT_FPROP, launch_stem_tc((const __nv_bfloat16*)stem_in_,
                                   (const __nv_bfloat16*)L.w_fwd + (size_t)g * 9 * 128 * 16,
                                   L.b + g * 32, channel_slice(L.z, g * 32, 32), num_sms_, s));
     }
   } else {
     // forward operand [tap][Cout][Cin] (bf16; fp32: [tap][Cin][Cout]); the data gradient is the
     // same convolution with the taps flipped and the channel roles swapped
-    EXA_LAUNCH(launch_pack_conv_weights(L.w, L.w_fwd, L.cout, L.cin, !f32, false, false, f32, s));
-    EXA_LAUNCH(launch_pack_conv_weights(L.w, L.w_bwd, L.cout, L.cin, f32, true, false, f32, s));
+    EXA_LAUNCH(CAT_PACK, launch_pack_conv_weights(L.w, L.w_fwd, L.cout, L.cin, !f32, false, false, f32, s));
+    EXA_LAUNCH(CAT_PACK, launch_pack_conv_weights(L.w, L.w_bwd, L.cout, L.cin, f32, true, false, f32, s));
     if (L.w_fwd_zf)
-      EXA_LAUNCH(launch_pack_conv_weights(L.w, L.w_fwd_zf, L.cout, L.cin, true, false, true, false, s));
+      EXA_LAUNCH(CAT_PACK, launch_pack_conv_weights(L.w, L.w_fwd_zf, L.cout, L.cin, true, false, true, false, s));
     if (L.w_bwd_zf)
-      EXA_LAUNCH(launch_pack_conv_weights(L.w, L.w_bwd_zf, L.cout, L.cin, false, true, true, false, s));
-    EXA_LAUNCH(conv_any(L.x, L.z, L.w_fwd, L.w_fwd_zf, L.b, s));
+      EXA_LAUNCH(CAT_PACK, launch_pack_conv_weights(L.w, L.w_bwd_zf, L.cout, L.cin, false, true, true, false, s));
+    EXA_LAUNCH(CAT_FPROP, conv_any(L.x, L.z, L.w_fwd, L.w_fwd_zf, L.b, s));
   }
   const double count = (double)L.z.voxels();
   EXA_CUDA(cudaMemsetAsync(L.sums, 0, sizeof(double) * 2 * L.cout, s));
-  EXA_LAUNCH(launch_bn_stats(encoded(L.z), L.sums, s));
-  EXA_LAUNCH(launch_bn_finalize(L.sums, L.cout, count, L.gamma, L.beta, L.rmean, L.rvar, L.mean,
+  EXA_LAUNCH(CAT_BN_FWD, launch_bn_stats(encoded(L.z), L.sums, s));
+  EXA_LAUNCH(CAT_BN_FWD, launch_bn_finalize(L.sums, L.cout, count, L.gamma, L.beta, L.rmean, L.rvar, L.mean,
                                 L.rstd, L.scale, L.shift, s));
-  EXA_LAUNCH(launch_bn_apply(encoded(L.z), L.scale, L.shift, L.a, s));
+  EXA_LAUNCH(CAT_BN_FWD, launch_bn_apply(encoded(L.z), L.scale, L.shift, L.a, s));
   return Status::OK();
 }
 
@@ -431,28 +483,28 @@ Status Trainer::forward(const float* x, int batch, const int32_t patch[3], float
 
   EXA_TRY(layer_forward(0, x, s));
   EXA_TRY(layer_forward(1, x, s));
-  EXA_LAUNCH(launch_maxpool(x1_, p1_, s));
+  EXA_LAUNCH(CAT_MISC_FWD, launch_maxpool(x1_, p1_, s));
   EXA_TRY(layer_forward(2, x, s));
   EXA_TRY(layer_forward(3, x, s));
-  EXA_LAUNCH(launch_maxpool(x2_, p2_, s));
+  EXA_LAUNCH(CAT_MISC_FWD, launch_maxpool(x2_, p2_, s));
   EXA_TRY(layer_forward(4, x, s));
   EXA_TRY(layer_forward(5, x, s));
-  EXA_LAUNCH(launch_maxpool(x3_, p3_, s));
+  EXA_LAUNCH(CAT_MISC_FWD, launch_maxpool(x3_, p3_, s));
   EXA_TRY(layer_forward(6, x, s));
   EXA_TRY(layer_forward(7, x, s));
-  EXA_LAUNCH(launch_maxpool(x4_, p4_, s));
+  EXA_LAUNCH(CAT_MISC_FWD, launch_maxpool(x4_, p4_, s));
   EXA_TRY(layer_forward(8, x, s));
   EXA_TRY(layer_forward(9, x, s));
-  EXA_LAUNCH(launch_upsample(x5_, up1_slot_, nullptr, s));  // cat([x4, up(x5)]), unet3d.py:288
+  EXA_LAUNCH(CAT_MISC_FWD, launch_upsample(x5_, up1_slot_, nullptr, s));  // cat([x4, up(x5)]), unet3d.py:288
   EXA_TRY(layer_forward(10, x, s));
   EXA_TRY(layer_forward(11, x, s));
-  EXA_LAUNCH(launch_upsample(u1_, up2_slot_, nullptr, s));
+  EXA_LAUNCH(CAT_MISC_FWD, launch_upsample(u1_, up2_slot_, nullptr, s));
   EXA_TRY(layer_forward(12, x, s));
   EXA_TRY(layer_forward(13, x, s));
-  EXA_LAUNCH(launch_upsample(u2_, up3_slot_, nullptr, s));
+  EXA_LAUNCH(CAT_MISC_FWD, launch_upsample(u2_, up3_slot_, nullptr, s));
   EXA_TRY(layer_forward(14, x, s));
   EXA_TRY(layer_forward(15, x, s));
-  EXA_LAUNCH(launch_upsample(u3_, up4_slot_, nullptr, s));
+  EXA_LAUNCH(CAT_MISC_FWD, launch_upsample(u3_, up4_slot_, nullptr, s));
   EXA_TRY(layer_forward(16, x, s));
   EXA_TRY(layer_forward(17, x, s));
   HeadParams head;
@@ -462,7 +514,7 @@ Status Trainer::forward(const float* x, int batch, const int32_t patch[3], float
   head.C = out_channels_;
   head.trim = 0;
   head.apply_sigmoid = 0;
-  EXA_LAUNCH(launch_head(u4_, head, s));  // outc, unet3d.py:318
+  EXA_LAUNCH(CAT_MISC_FWD, launch_head(u4_, head, s));  // outc, unet3d.py:318
   forward_valid_ = true;
   return Status::OK();
 }
@@ -476,22 +528,22 @@ Status Trainer::layer_backward(int l, const TView& grad_a, const float* x, float
   dz.D = L.z.D; dz.H = L.z.H; dz.W = L.z.W;
   dz.C = dz.cstride = L.cout;
   EXA_CUDA(cudaMemsetAsync(L.sums, 0, sizeof(double) * 2 * L.cout, s));
-  EXA_LAUNCH(launch_bn_bwd_reduce(grad_a, L.a, encoded(L.z), L.mean, L.rstd, L.sums, s));
-  EXA_LAUNCH(launch_bn_bwd_finalize(L.sums, L.cout, count, L.gamma, L.rstd, grads + L.ggamma,
+  EXA_LAUNCH(CAT_BN_BWD, launch_bn_bwd_reduce(grad_a, L.a, encoded(L.z), L.mean, L.rstd, L.sums, s));
+  EXA_LAUNCH(CAT_BN_BWD, launch_bn_bwd_finalize(L.sums, L.cout, count, L.gamma, L.rstd, grads + L.ggamma,
                                     grads + L.gbeta, L.coef, s));
   EXA_CUDA(cudaMemsetAsync(L.sums, 0, sizeof(double) * 2 * L.cout, s));
-  EXA_LAUNCH(launch_bn_bwd_apply(grad_a, L.a, encoded(L.z), L.mean, L.rstd, L.coef, dz, L.sums, s));
-  EXA_LAUNCH(launch_double_to_float(L.sums, grads + L.gb, L.cout, s));
+  EXA_LAUNCH(CAT_BN_BWD, launch_bn_bwd_apply(grad_a, L.a, encoded(L.z), L.mean, L.rstd, L.coef, dz, L.sums, s));
+  EXA_LAUNCH(CAT_BN_BWD, launch_double_to_float(L.sums, grads + L.gb, L.cout, s));
   if (l == 0) {
-    EXA_LAUNCH(launch_wgrad_stem(x, dz, partial_, num_sms_, s));
-    EXA_LAUNCH(launch_wgrad_reduce(partial_, wgrad_stem_splits(dz, num_sms_), (size_t)L.cout * 27,
+    EXA_LAUNCH(CAT_WGRAD, launch_wgrad_stem(x, dz, partial_, num_sms_, s));
+    EXA_LAUNCH(CAT_WGRAD, launch_wgrad_reduce(partial_, wgrad_stem_splits(dz, num_sms_), (size_t)L.cout * 27,
                                    grads + L.gw, s));
     return Status::OK();
   }
-  EXA_LAUNCH(launch_wgrad(L.x, dz, partial_, num_sms_, s));
-  EXA_LAUNCH(launch_wgrad_reduce(partial_, wgrad_splits(L.x, L.cout, num_sms_),
+  EXA_LAUNCH(CAT_WGRAD, launch_wgrad(L.x, dz, partial_, num_sms_, s));
+  EXA_LAUNCH(CAT_WGRAD, launch_wgrad_reduce(partial_, wgrad_splits(L.x, L.cout, num_sms_),
                                  (size_t)L.cout * L.cin * 27, grads + L.gw, s));
-  EXA_LAUNCH(conv_any(dz, L.gx, L.w_bwd, L.w_bwd_zf, zero_bias_, s));
+  EXA_LAUNCH(CAT_DGRAD, conv_any(dz, L.gx, L.w_bwd, L.w_bwd_zf, zero_bias_, s));
   return Status::OK();
 }
 
@@ -505,42 +557,135 @@ Status Trainer::backward(const float* x, const float* dlogits, float* grads, cud
   // head (unet3d.py:318)
   const int nh = C * c[0] + C;
   EXA_CUDA(cudaMemsetAsync(head_sums_, 0, sizeof(double) * nh, s));
-  EXA_LAUNCH(launch_head_bwd_dw(dlogits, u4_, C, head_sums_, s));
-  EXA_LAUNCH(launch_double_to_float(head_sums_, grads + g_head_w_, C * c[0], s));
-  EXA_LAUNCH(launch_double_to_float(head_sums_ + C * c[0], grads + g_head_b_, C, s));
-  EXA_LAUNCH(launch_head_bwd_dx(dlogits, head_w_, C, g_u4_, s));
+  EXA_LAUNCH(CAT_MISC_BWD, launch_head_bwd_dw(dlogits, u4_, C, head_sums_, s));
+  EXA_LAUNCH(CAT_MISC_BWD, launch_double_to_float(head_sums_, grads + g_head_w_, C * c[0], s));
+  EXA_LAUNCH(CAT_MISC_BWD, launch_double_to_float(head_sums_ + C * c[0], grads + g_head_b_, C, s));
+  EXA_LAUNCH(CAT_MISC_BWD, launch_head_bwd_dx(dlogits, head_w_, C, g_u4_, s));
   // decoder
   EXA_TRY(layer_backward(17, plain(g_u4_), x, grads, s));
   EXA_TRY(layer_backward(16, encoded(g_u4a_), x, grads, s));
-  EXA_LAUNCH(launch_upsample_bwd(encoded(channel_slice(g_cat4_, c[0], c[0])), g_u3_, s));
+  EXA_LAUNCH(CAT_MISC_BWD, launch_upsample_bwd(encoded(channel_slice(g_cat4_, c[0], c[0])), g_u3_, s));
   EXA_TRY(layer_backward(15, plain(g_u3_), x, grads, s));
   EXA_TRY(layer_backward(14, encoded(g_u3a_), x, grads, s));
-  EXA_LAUNCH(launch_upsample_bwd(encoded(channel_slice(g_cat3_, c[1], c[1])), g_u2_, s));
+  EXA_LAUNCH(CAT_MISC_BWD, launch_upsample_bwd(encoded(channel_slice(g_cat3_, c[1], c[1])), g_u2_, s));
   EXA_TRY(layer_backward(13, plain(g_u2_), x, grads, s));
   EXA_TRY(layer_backward(12, encoded(g_u2a_), x, grads, s));
-  EXA_LAUNCH(launch_upsample_bwd(encoded(channel_slice(g_cat2_, c[2], c[2])), g_u1_, s));
+  EXA_LAUNCH(CAT_MISC_BWD, launch_upsample_bwd(encoded(channel_slice(g_cat2_, c[2], c[2])), g_u1_, s));
   EXA_TRY(layer_backward(11, plain(g_u1_), x, grads, s));
   EXA_TRY(layer_backward(10, encoded(g_u1a_), x, grads, s));
-  EXA_LAUNCH(launch_upsample_bwd(encoded(channel_slice(g_cat1_, c[3], c[3])), g_x5_, s));
+  EXA_LAUNCH(CAT_MISC_BWD, launch_upsample_bwd(encoded(channel_slice(g_cat1_, c[3], c[3])), g_x5_, s));
   // encoder: every skip tensor collects its concat half and the max-pool's gradient
   EXA_TRY(layer_backward(9, plain(g_x5_), x, grads, s));
   EXA_TRY(layer_backward(8, encoded(g_d4a_), x, grads, s));
-  EXA_LAUNCH(launch_pool_bwd_merge(encoded(channel_slice(g_cat1_, 0, c[3])), encoded(g_p4_), x4_,
+  EXA_LAUNCH(CAT_MISC_BWD, launch_pool_bwd_merge(encoded(channel_slice(g_cat1_, 0, c[3])), encoded(g_p4_), x4_,
                                    g_x4_, s));
   EXA_TRY(layer_backward(7, plain(g_x4_), x, grads, s));
   EXA_TRY(layer_backward(6, encoded(g_d3a_), x, grads, s));
-  EXA_LAUNCH(launch_pool_bwd_merge(encoded(channel_slice(g_cat2_, 0, c[2])), encoded(g_p3_), x3_,
+  EXA_LAUNCH(CAT_MISC_BWD, launch_pool_bwd_merge(encoded(channel_slice(g_cat2_, 0, c[2])), encoded(g_p3_), x3_,
                                    g_x3_, s));
   EXA_TRY(layer_backward(5, plain(g_x3_), x, grads, s));
   EXA_TRY(layer_backward(4, encoded(g_d2a_), x, grads, s));
-  EXA_LAUNCH(launch_pool_bwd_merge(encoded(channel_slice(g_cat3_, 0, c[1])), encoded(g_p2_), x2_,
+  EXA_LAUNCH(CAT_MISC_BWD, launch_pool_bwd_merge(encoded(channel_slice(g_cat3_, 0, c[1])), encoded(g_p2_), x2_,
                                    g_x2_, s));
   EXA_TRY(layer_backward(3, plain(g_x2_), x, grads, s));
   EXA_TRY(layer_backward(2, encoded(g_d1a_), x, grads, s));
-  EXA_LAUNCH(launch_pool_bwd_merge(encoded(channel_slice(g_cat4_, 0, c[0])), encoded(g_p1_), x1_,
+  EXA_LAUNCH(CAT_MISC_BWD, launch_pool_bwd_merge(encoded(channel_slice(g_cat4_, 0, c[0])), encoded(g_p1_), x1_,
                                    g_x1_, s));
   EXA_TRY(layer_backward(1, plain(g_x1_), x, grads, s));
   EXA_TRY(layer_backward(0, encoded(g_a0_), x, grads, s));
+  return Status::OK();
+}
+
+// ---------------------------------------------------------------------------
+// operator-level entry points (tests)
+// ---------------------------------------------------------------------------
+namespace {
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() { free_dev(p); }
+  Status alloc(size_t bytes) {
+    EXA_CUDA(cudaMalloc(&p, bytes ? bytes : 16));
+    return Status::OK();
+  }
+};
+Status device_sms(int device, int* sms) {
+  int count = 0;
+  EXA_CHECK(cudaGetDeviceCount(&count) == cudaSuccess && device >= 0 && device < count,
+            "no such CUDA device (this library has no CPU fallback)");
+  EXA_CUDA(cudaSetDevice(device));
+  EXA_CUDA(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, device));
+  return Status::OK();
+}
+Act dense_act(const void* p, int B, int D, int H, int W, int C, bool f32) {
+  Act a;
+  a.ptr = const_cast<void*>(p);
+  a.B = B; a.D = D; a.H = H; a.W = W;
+  a.C = a.cstride = C;
+  a.coff = 0;
+  a.fp32 = f32;
+  return a;
+}
+}  // namespace
+
+Status conv3d_weight_grad(int device, int precision, const void* x, const void* dz, int B, int D,
+                          int H, int W, int cin, int cout, float* dw, cudaStream_t s) {
+  EXA_CHECK(x && dz && dw && B > 0 && D > 0 && H > 0 && W > 0, "conv3d_weight_grad: bad arguments");
+  EXA_CHECK(precision == EXA_PRECISION_BF16 || precision == EXA_PRECISION_FP32, "unknown precision");
+  int sms = 0;
+  EXA_TRY(device_sms(device, &sms));
+  const bool f32 = precision == EXA_PRECISION_FP32;
+  const Act dza = dense_act(dz, B, D, H, W, cout, f32);
+  DevBuf partial;
+  if (cin == 1) {  // stem: x is the raw float32 (B,1,D,H,W) input
+    const int splits = wgrad_stem_splits(dza, sms);
+    EXA_TRY(partial.alloc((size_t)splits * cout * 27 * 4));
+    EXA_TRY(launch_wgrad_stem((const float*)x, dza, (float*)partial.p, sms, s));
+    EXA_TRY(launch_wgrad_reduce((const float*)partial.p, splits, (size_t)cout * 27, dw, s));
+  } else {
+    const Act xa = dense_act(x, B, D, H, W, cin, f32);
+    EXA_TRY(partial.alloc(wgrad_partial_elems(xa, cout, sms) * 4));
+    EXA_TRY(launch_wgrad(xa, dza, (float*)partial.p, sms, s));
+    EXA_TRY(launch_wgrad_reduce((const float*)partial.p, wgrad_splits(xa, cout, sms),
+                                (size_t)cout * cin * 27, dw, s));
+  }
+  EXA_CUDA(cudaStreamSynchronize(s));
+  return Status::OK();
+}
+
+Status conv3d_data_grad(int device, int precision, const void* dz, const float* w, int B, int D,
+                        int H, int W, int cin, int cout, void* dx, cudaStream_t s) {
+  EXA_CHECK(dz && w && dx && B > 0 && D > 0 && H > 0 && W > 0, "conv3d_data_grad: bad arguments");
+  EXA_CHECK(precision == EXA_PRECISION_BF16 || precision == EXA_PRECISION_FP32, "unknown precision");
+  EXA_CHECK(cin % 32 == 0 && cout % 32 == 0, "conv3d_data_grad: channels must be multiples of 32");
+  int sms = 0;
+  EXA_TRY(device_sms(device, &sms));
+  const bool f32 = precision == EXA_PRECISION_FP32;
+  const size_t esz = f32 ? 4 : 2, n = (size_t)27 * cin * cout;
+  const Act dza = dense_act(dz, B, D, H, W, cout, f32);
+  DevBuf wp, wz, zero, raw;
+  EXA_TRY(wp.alloc(n * esz));
+  EXA_TRY(zero.alloc(4 * (size_t)cin));
+  EXA_TRY(raw.alloc(dza.voxels() * cin * esz));
+  EXA_CUDA(cudaMemsetAsync(zero.p, 0, 4 * (size_t)cin, s));
+  EXA_TRY(launch_pack_conv_weights(w, wp.p, cout, cin, f32, true, false, f32, s));
+  const Act rawa = dense_act(raw.p, B, D, H, W, cin, f32);
+  static const bool no_zf = getenv("EXA_TRAIN_NO_ZFOLD") != nullptr;
+  if (f32) {
+    EXA_TRY(launch_conv_fp32(dza, rawa, (const float*)wp.p, (const float*)zero.p, s));
+  } else if (!no_zf && conv_zfold_supported(dza, cin, true)) {
+    EXA_TRY(wz.alloc(n * esz));
+    EXA_TRY(launch_pack_conv_weights(w, wz.p, cout, cin, false, true, true, false, s));
+    EXA_TRY(launch_conv_zfold(dza, rawa, (const __nv_bfloat16*)wz.p, (const float*)zero.p, nullptr,
+                              nullptr, nullptr, sms, true, s));
+  } else {
+    EXA_TRY(launch_conv_umma(dza, rawa, (const __nv_bfloat16*)wp.p, (const float*)zero.p, nullptr,
+                             sms, s));
+  }
+  TView enc;
+  enc.a = rawa;
+  enc.enc = true;
+  EXA_TRY(launch_decode(enc, dense_act(dx, B, D, H, W, cin, f32), s));
+  EXA_CUDA(cudaStreamSynchronize(s));
   return Status::OK();
 }
 

@@ -32,6 +32,11 @@ class Trainer {
   // x: the tensor of the matching forward; dlogits: (B,C,D,H,W); grads: grad_elems() floats
   Status backward(const float* x, const float* dlogits, float* grads, cudaStream_t s);
   size_t workspace_bytes() const { return ws_bytes_; }
+  // per-category kernel timing with CUDA events on the launching stream (bench / roofline)
+  enum Category { CAT_PACK = 0, CAT_FPROP, CAT_BN_FWD, CAT_MISC_FWD, CAT_BN_BWD, CAT_WGRAD,
+                  CAT_DGRAD, CAT_MISC_BWD, CAT_COUNT };
+  Status profile_begin();
+  Status profile_end(double* ms_by_cat, int64_t* launches_by_cat, int n);
 
   std::string last_error;
   int64_t launches = 0;
@@ -58,6 +63,20 @@ class Trainer {
   Status layer_backward(int l, const TView& grad_a, const float* x, float* grads, cudaStream_t s);
   Status conv_any(const Act& in, const Act& out, const void* w_plain, const void* w_zf,
                   const float* bias, cudaStream_t s);
+
+  struct ProfRec {
+    int cat;
+    cudaEvent_t start, stop;
+  };
+  struct Scope {  // counts the launch and, when profiling, brackets it with two events
+    Trainer* t;
+    cudaStream_t s;
+    cudaEvent_t stop = nullptr;
+    Scope(Trainer* tr, int cat, cudaStream_t st);
+    ~Scope();
+  };
+  bool prof_on_ = false;
+  std::vector<ProfRec> prof_;
 
   int device_, precision_;
   int num_sms_ = 148;
@@ -89,5 +108,14 @@ class Trainer {
   float* partial_ = nullptr;
   bool forward_valid_ = false;
 };
+
+// Operator-level entry points of the two tensor-core pieces of the backward pass, for parity
+// tests against torch.nn.grad.conv3d_weight / conv3d_input on identical operands.  Tensors are
+// NDHWC device arrays of the precision's element type (bf16 or fp32); w and dw are float32 in
+// the reference's (Cout, Cin, 3, 3, 3) layout.  Temporary buffers are allocated per call.
+Status conv3d_weight_grad(int device, int precision, const void* x, const void* dz, int B, int D,
+                          int H, int W, int cin, int cout, float* dw, cudaStream_t s);
+Status conv3d_data_grad(int device, int precision, const void* dz, const float* w, int B, int D,
+                        int H, int W, int cin, int cout, void* dx, cudaStream_t s);
 
 }  // namespace exa

@@ -128,6 +128,20 @@ class TrainEngine:
                                                  _stream_ptr(x.device)), "exa_train_backward")
         return [flat[off:off + numel].view(shape) for _, off, numel, shape in self._slots]
 
+    PROFILE_CATEGORIES = ("pack", "fprop", "bn_fwd", "misc_fwd", "bn_bwd", "wgrad", "dgrad",
+                          "misc_bwd")
+
+    def profile_begin(self):
+        self._check(self._lib.exa_train_profile_begin(self._h), "exa_train_profile_begin")
+
+    def profile_end(self):
+        """{category: (device ms, launches)} since profile_begin (synchronises)."""
+        n = len(self.PROFILE_CATEGORIES)
+        ms = (ctypes.c_double * n)()
+        cnt = (ctypes.c_int64 * n)()
+        self._check(self._lib.exa_train_profile_end(self._h, ms, cnt, n), "exa_train_profile_end")
+        return {name: (ms[i], cnt[i]) for i, name in enumerate(self.PROFILE_CATEGORIES)}
+
     @property
     def launch_count(self):
         return int(self._lib.exa_train_launch_count(self._h))

@@ -576,6 +576,180 @@ def run_segment(args):
             line["adapted_rand"]["non_degenerate"] = extra
     emit(line)
 
+
+# --- training step -------------------------------------------------------------
+def train_flops(batch, p=96):
+    """Executed FLOPs of one step: forward convs (all 18, full patches -- nothing is trimmed in
+    training), data gradients (17: the stem's input needs none) and weight gradients (18)."""
+    fwd = sum(layer_flops(i, p) for i in range(18))
+    return {"fprop": batch * fwd, "dgrad": batch * (fwd - layer_flops(0, p)), "wgrad": batch * fwd}
+
+
+def run_train(args):
+    """`--workload train`: one training step of reference train.py:136-140 (forward_pass + backward)
+    on one GPU, B = 16 patches of 96^3 (Trainer / dataset defaults, train.py:39, data_handling.py:33).
+    `value`: patch voxels/s with x and y resident in HBM; `e2e`: host x, y in -> loss on the host,
+    every parameter's .grad on the device, through model(x) / criterion / loss.backward();
+    `cpu_baseline`: the oracle's torch-autograd step (oracle/train_ref.py) on the host cores, B = 2."""
+    import torch
+
+    from aind_exaspim_neuron_segmentation_b200 import UNet3D
+    from aind_exaspim_neuron_segmentation_b200.machine_learning.training import trainer_for_module
+    from oracle.train_ref import train_inputs_structured  # seeded inputs only
+    from oracle.unet_ref import rescaled_state_dict      # weights recipe only
+
+    torch.cuda.set_device(0)
+    B, P = args.train_batch, args.patch
+    model = UNet3D(output_channels=3)
+    model.load_state_dict(rescaled_state_dict(0), strict=True)
+    model = model.cuda().train()
+    crit = torch.nn.BCEWithLogitsLoss()
+    x_host, y_host = train_inputs_structured(1, B, (P, P, P))
+    x_host, y_host = x_host.pin_memory(), y_host.pin_memory()
+    x_dev, y_dev = x_host.cuda(), y_host.cuda()
+    voxels = float(B) * P ** 3
+
+    def step(x, y):
+        model.zero_grad(set_to_none=True)
+        hat_y = model(x)
+        loss = crit(hat_y, y)
+        loss.backward()
+        return loss
+
+    def step_e2e():
+        x = x_host.cuda(non_blocking=True)
+        y = y_host.cuda(non_blocking=True)
+        return float(step(x, y).detach().cpu())
+
+    for _ in range(max(args.warmup, 1)):
+        loss0 = step(x_dev, y_dev)
+    torch.cuda.synchronize()
+    eng = trainer_for_module(model, model.precision)
+    launches0 = eng.launch_count
+    sampler = ClockSampler(0)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(x_dev, y_dev)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    clocks = sampler.stop()
+    launches = (eng.launch_count - launches0) // args.steps
+    # per-category pass, separately (events around every launch)
+    eng.profile_begin()
+    step(x_dev, y_dev)
+    prof = eng.profile_end()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        loss_e2e = step_e2e()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) / args.steps * 1e3
+    fl = train_flops(B, P)
+    peaks = measured_peaks()
+    cat_ms = {k: v[0] for k, v in prof.items()}
+    tflops = {k: fl[k] / (cat_ms[k] * 1e-3) / 1e12 for k in ("fprop", "dgrad", "wgrad") if cat_ms[k] > 0}
+    line = {
+        "metric": "training patch voxels/sec", "value": voxels / (ms * 1e-3), "unit": "voxels/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": f"one training step (forward with batch-statistics BatchNorm, "
+                               f"BCEWithLogitsLoss, backward to all 74 parameter gradients) on "
+                               f"{B} patches of {P}^3, UNet3D(output_channels=3)",
+                   "batch": B, "patch": [P, P, P],
+                   "l2": f"activations of one step ({eng.workspace_bytes / 2**30:.1f} GiB workspace) "
+                         "are far larger than the L2",
+                   "workspace_gib": eng.workspace_bytes / 2 ** 30},
+        "e2e": {"value": voxels / (e2e_ms * 1e-3), "unit": "voxels/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(voxels) * 4 * 4, "d2h_bytes_per_step": 4,
+                "note": "pinned float32 x (B,1,P,P,P) and y (B,3,P,P,P) in -> float loss out; "
+                        "gradients stay on the device for the optimizer, as in train.py:139-147"},
+        "gpu_launches": int(launches),
+        "loss": float(loss0.detach()), "loss_e2e": loss_e2e,
+        "per_category_ms": cat_ms, "per_category_launches": {k: v[1] for k, v in prof.items()},
+        "tflops": tflops,
+        "roofline": {"bound": "tensor", "achieved": tflops.get("wgrad"), "peak": peaks["bf16_tflops"],
+                     "unit": "TFLOP/s",
+                     "frac": (tflops.get("wgrad") or 0) / peaks["bf16_tflops"], "traffic": None,
+                     "kernel": "wgrad_mma_kernel (weight gradients, mma.sync m16n8k16): executed "
+                               "FLOPs = batch x 370.145 GFLOP / summed event time of the category "
+                               "(includes the split-K reduction)", "peak_source": peaks["source"]},
+        "clocks": clocks,
+    }
+    if not args.no_cpu:
+        from oracle.train_ref import train_step_ref
+
+        torch.set_num_threads(os.cpu_count())
+        xs, ys = x_host[:2].clone(), y_host[:2].clone()
+        sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        t0 = time.perf_counter()
+        train_step_ref(xs, ys, sd)
+        cpu_s = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": 2 * P ** 3 / cpu_s, "unit": "voxels/s", "cores": os.cpu_count(),
+                                "kind": "port",
+                                "sample": f"oracle/train_ref.py (torch autograd, fp32) on 2 patches of "
+                                          f"{P}^3, {cpu_s:.2f} s"}
+    emit(line)
+
+
+def run_train_library(args):
+    """The reference's own GPU path for the same step: torch autograd over cuDNN with fp16
+    autocast and GradScaler-style loss scaling (train.py:79-84,140), on the oracle's functional
+    restatement of the model.  Not part of the bench contract; "impl": "library"."""
+    import contextlib
+
+    import torch
+
+    from oracle.train_ref import is_parameter, train_inputs_structured, unet_forward_train
+    from oracle.unet_ref import rescaled_state_dict
+
+    dev = torch.device("cuda", 0)
+    B, P = args.train_batch, args.patch
+    p = {}
+    for k, v in rescaled_state_dict(0).items():
+        if v.dtype == torch.int64:
+            continue
+        t = v.to(dev)
+        if is_parameter(k):
+            t.requires_grad_(True)
+        p[k] = t
+    x, y = train_inputs_structured(1, B, (P, P, P))
+    x, y = x.to(dev), y.to(dev)
+    torch.backends.cudnn.benchmark = True
+    out = {}
+    for name, dtype in (("fp16_autocast", torch.float16), ("bf16_autocast", torch.bfloat16),
+                        ("tf32", None)):
+        def step():
+            for t in p.values():
+                t.grad = None
+            ctx = torch.autocast("cuda", dtype=dtype) if dtype else contextlib.nullcontext()
+            with ctx:
+                logits = unet_forward_train(x, p, {})
+                loss = torch.nn.functional.binary_cross_entropy_with_logits(logits.float(), y)
+            (loss * 1024.0).backward()
+            return loss
+        try:
+            for _ in range(2):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.steps):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / args.steps
+            out[name] = {"ms_per_step": ms, "voxels_per_s": B * P ** 3 / (ms * 1e-3),
+                         "peak_mem_gib": torch.cuda.max_memory_allocated() / 2 ** 30}
+        except Exception as exc:  # noqa: BLE001
+            out[name] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
+        torch.cuda.empty_cache()
+    emit({"impl": "library", "what": f"PyTorch/cuDNN training step (forward, BCE, backward) of the "
+          f"same UNet3D, B={B} x {P}^3", "torch": torch.__version__,
+          "cudnn": torch.backends.cudnn.version(), "settings": out})
+
 # --- B200 arm ------------------------------------------------------------------------------
 def run_b200(args):
     import torch
@@ -861,7 +1035,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--volume", type=int, default=0, choices=[0, 256, 512, 1024],
                     help="fix the volume at N^3 for every --gpus (strong scaling); 0 = N x 512^3 (weak)")
-    ap.add_argument("--workload", default="predict", choices=["predict", "segment"],
+    ap.add_argument("--train-batch", type=int, default=16,
+                    help="--workload train: patches per step (Trainer default 16, train.py:39)")
+    ap.add_argument("--workload", default="predict", choices=["predict", "segment", "train"],
                     help="predict = the headline hot path; segment = BASELINE config 5 (predict, then "
                          "affinities_to_segmentation timed; one GPU)")
     ap.add_argument("--patch", type=int, default=96, choices=[96, 128],
@@ -879,6 +1055,8 @@ def main():
     capture_stdout()
     if args.workload == "segment":
         run_segment(args)
+    elif args.workload == "train":
+        run_train_library(args) if args.impl == "library" else run_train(args)
     elif args.impl == "reference":
         run_reference(args)
     elif args.impl == "library":

@@ -267,7 +267,24 @@ int exa_train_forward(exa_trainer* t, const float* x_dev, int batch, const int32
 int exa_train_backward(exa_trainer* t, const float* x_dev, const float* grad_logits_dev,
                        float* grads_dev, void* stream);
 int64_t exa_train_launch_count(const exa_trainer* t);
+/* like exa_profile_begin / exa_profile_end: summed device milliseconds and launches per category:
+ * 0 weight packing, 1 forward convolutions (tcgen05), 2 BatchNorm forward (statistics + apply),
+ * 3 max-pool / upsample / head forward, 4 BatchNorm + LeakyReLU backward, 5 weight gradients,
+ * 6 data gradients (tcgen05), 7 max-pool / upsample / head backward.  n >= 8. */
+enum { EXA_TRAIN_PROFILE_CATEGORIES = 8 };
+int exa_train_profile_begin(exa_trainer* t);
+int exa_train_profile_end(exa_trainer* t, double* ms_by_category, int64_t* launches_by_category,
+                          int n);
 int64_t exa_train_workspace_bytes(const exa_trainer* t);
+/* Operator-level entry points of the backward pass's two tensor-core pieces, for parity tests:
+ * what torch.nn.grad.conv3d_weight / conv3d_input compute for the Conv3d(k=3, padding=1) of
+ * unet3d.py:143,146.  x / dz / dx: NDHWC device arrays of the precision's element type (bf16
+ * or float32; for cin == 1, x is the raw float32 (B,1,D,H,W) input); w / dw: float32 device
+ * arrays in the reference's (Cout, Cin, 3, 3, 3) layout.  Synchronous. */
+int exa_conv3d_weight_grad(int device, int precision, const void* x_dev, const void* dz_dev, int B,
+                           int D, int H, int W, int cin, int cout, float* dw_dev, void* stream);
+int exa_conv3d_data_grad(int device, int precision, const void* dz_dev, const float* w_dev, int B,
+                         int D, int H, int W, int cin, int cout, void* dx_dev, void* stream);
 /* nn.BCEWithLogitsLoss() (train.py:76,222), mean reduction: *loss_sum_dev (double, zeroed by the
  * caller) += sum of the element losses; when grad_dev is not NULL it receives
  * grad_scale * (sigmoid(logit) - target) / n  (grad_scale = the GradScaler factor, train.py:140) */
