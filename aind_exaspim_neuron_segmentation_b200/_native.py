@@ -16,7 +16,7 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_PKG_DIR, "csrc")
 LIB_PATH = os.path.join(_PKG_DIR, "libexaspim_b200.so")
 SOURCES = ["capi.cu", "engine.cu", "kernels_mem.cu", "conv_umma.cu", "conv_zfold.cu", "conv_stem.cu",
-           "watershed.cu", "float_volume.cu", "train_kernels.cu", "trainer.cu"]
+           "watershed.cu", "float_volume.cu", "train_kernels.cu", "train_wgrad.cu", "trainer.cu"]
 HEADERS = ["common.cuh", "conv_umma.cuh", "conv_zfold.cuh", "conv_zfold2.cuh", "conv_stem.cuh", "engine.h",
            "kernels.h", "tmap.h", "watershed.h", "ws_agglomerate.h", "float_volume.h", "train_kernels.h",
            "trainer.h"]

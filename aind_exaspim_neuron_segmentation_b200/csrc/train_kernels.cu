@@ -1024,6 +1024,7 @@ static int wgrad_units(const Act& x) {  // tiles (bf16) or 128-voxel chunks (fp3
 }
 
 int wgrad_splits(const Act& x, int cout, int num_sms) {
+  if (!x.fp32 && wgrad_tc_enabled()) return wgrad_tc_splits(x, cout, num_sms);
   const int blocks = (x.fp32 ? x.C / 16 : x.C / 32) * (cout / 32);
   int s = (2 * num_sms + blocks - 1) / blocks;
   const int units = wgrad_units(x);
@@ -1050,6 +1051,7 @@ Status launch_wgrad(const Act& x, const Act& dz, float* partial, int num_sms, cu
     return Status::OK();
   }
   EXA_CHECK(x.C % 32 == 0 && x.cstride % 8 == 0 && x.coff % 8 == 0, "wgrad: Cin % 32 (bf16)");
+  if (wgrad_tc_enabled()) return launch_wgrad_tc(x, dz, partial, num_sms, s);
   static bool configured = false;
   if (!configured) {
     EXA_CUDA(cudaFuncSetAttribute(wgrad_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

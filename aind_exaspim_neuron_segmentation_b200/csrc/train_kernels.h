@@ -79,7 +79,11 @@ Status launch_head_bwd_dw(const float* dlogits, const Act& u, int C, double* sum
 // partial sums [splits][cout][cin][27] that launch_wgrad_reduce adds up (deterministic).
 int wgrad_splits(const Act& x, int cout, int num_sms);
 size_t wgrad_partial_elems(const Act& x, int cout, int num_sms);
-// bf16: warp-level tensor-core MMA (m16n8k16), fp32 accumulation; fp32: SIMT
+// bf16: tcgen05 kernel of train_wgrad.cu (EXA_WGRAD=mma: the warp-level m16n8k16 kernel of
+// train_kernels.cu instead), fp32 accumulation; fp32: SIMT
+bool wgrad_tc_enabled();
+int wgrad_tc_splits(const Act& x, int cout, int num_sms);
+Status launch_wgrad_tc(const Act& x, const Act& dz, float* partial, int num_sms, cudaStream_t s);
 Status launch_wgrad(const Act& x, const Act& dz, float* partial, int num_sms, cudaStream_t s);
 // stem (Cin = 1): x is the raw (B,1,D,H,W) float32 input
 Status launch_wgrad_stem(const float* x, const Act& dz, float* partial, int num_sms,

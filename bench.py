@@ -581,8 +581,9 @@ def run_segment(args):
 def train_flops(batch, p=96):
     """Executed FLOPs of one step: forward convs (all 18, full patches -- nothing is trimmed in
     training), data gradients (17: the stem's input needs none) and weight gradients (18)."""
-    fwd = sum(layer_flops(i, p) for i in range(18))
-    return {"fprop": batch * fwd, "dgrad": batch * (fwd - layer_flops(0, p)), "wgrad": batch * fwd}
+    stem = 2 * p ** 3 * 32 * 27
+    convs = sum(2 * (p >> lvl) ** 3 * cout * 27 * cin for lvl, cin, cout in LAYER_SHAPES.values())
+    return {"fprop": batch * (convs + stem), "dgrad": batch * convs, "wgrad": batch * (convs + stem)}
 
 
 def run_train(args):
