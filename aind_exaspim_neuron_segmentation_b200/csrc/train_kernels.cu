@@ -317,46 +317,96 @@ Status launch_bn_apply(const TView& z, const float* scale, const float* shift, c
   return Status::OK();
 }
 
+// Raw 8-channel vectors: the loads of several voxels are issued before any is converted, so
+// that enough bytes are in flight per thread (these kernels hold ~70 per-channel constants in
+// registers, which limits occupancy).
+template <typename T>
+struct Raw8;
+template <>
+struct Raw8<__nv_bfloat16> {
+  uint4 v;
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) { v = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void get(float (&f)[8]) const {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 t = __bfloat1622float2(h[i]);
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
+  }
+};
+template <>
+struct Raw8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) {
+    a = *reinterpret_cast<const float4*>(p);
+    b = *reinterpret_cast<const float4*>(p + 4);
+  }
+  __device__ __forceinline__ void get(float (&f)[8]) const {
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+    f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  }
+};
+constexpr int BWD_UNROLL = 4;
+
 template <typename T>
 __global__ void __launch_bounds__(RED_THREADS)
 bn_bwd_reduce_kernel(const T* __restrict__ g, int g_cstride, int g_coff, bool g_enc,
-                     const T* __restrict__ a, int a_cstride, int a_coff, const T* __restrict__ z,
-                     int z_cstride, int z_coff, bool z_enc, const float* __restrict__ mean,
-                     const float* __restrict__ rstd, int C, size_t voxels,
-                     double* __restrict__ sums) {
+                     const float* __restrict__ scale, const float* __restrict__ shift,
+                     const T* __restrict__ z, int z_cstride, int z_coff, bool z_enc,
+                     const float* __restrict__ mean, const float* __restrict__ rstd, int C,
+                     size_t voxels, double* __restrict__ sums) {
   const int cv = C / 8, lanes = RED_THREADS / cv;
   const int c8 = threadIdx.x % cv, lane = threadIdx.x / cv;
-  float m[8], r[8], s[8], q[8];
+  float m[8], r[8], sc[8], sh[8], s[8], q[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     m[j] = __ldg(mean + 8 * c8 + j);
     r[j] = __ldg(rstd + 8 * c8 + j);
+    sc[j] = __ldg(scale + 8 * c8 + j);
+    sh[j] = __ldg(shift + 8 * c8 + j);
     s[j] = q[j] = 0.f;
   }
   const size_t v0 = (size_t)blockIdx.x * lanes * RED_ITER;
-  for (int k = 0; k < RED_ITER; ++k) {
-    const size_t v = v0 + (size_t)k * lanes + lane;
-    if (v >= voxels) break;
-    float fg[8], fa[8], fz[8];
-    load8_dec<T>(g + v * g_cstride + g_coff + 8 * c8, g_enc, fg);
-    load8<T>(a + v * a_cstride + a_coff + 8 * c8, fa);
-    load8_dec<T>(z + v * z_cstride + z_coff + 8 * c8, z_enc, fz);
+  for (int k = 0; k < RED_ITER; k += BWD_UNROLL) {
+    Raw8<T> rg[BWD_UNROLL], rz[BWD_UNROLL];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float gg = fa[j] > 0.f ? fg[j] : 0.01f * fg[j];
-      const float xh = (fz[j] - m[j]) * r[j];
-      s[j] += gg;
-      q[j] = fmaf(gg, xh, q[j]);
+    for (int u = 0; u < BWD_UNROLL; ++u) {
+      const size_t v = v0 + (size_t)(k + u) * lanes + lane;
+      if (v < voxels) {
+        rg[u].load(g + v * g_cstride + g_coff + 8 * c8);
+        rz[u].load(z + v * z_cstride + z_coff + 8 * c8);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < BWD_UNROLL; ++u) {
+      const size_t v = v0 + (size_t)(k + u) * lanes + lane;
+      if (v < voxels) {
+        float fg[8], fz[8];
+        rg[u].get(fg);
+        rz[u].get(fz);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float gv = dec(fg[j], g_enc), zv = dec(fz[j], z_enc);
+          // LeakyReLU mask from the pre-activation, recomputed exactly as bn_apply computed it
+          const float pre = fmaf(zv, sc[j], sh[j]);
+          const float gg = pre > 0.f ? gv : 0.01f * gv;
+          const float xh = (zv - m[j]) * r[j];
+          s[j] += gg;
+          q[j] = fmaf(gg, xh, q[j]);
+        }
+      }
     }
   }
   block_channel_reduce(s, q, cv, C, sums);
 }
 
-Status launch_bn_bwd_reduce(const TView& grad_a, const Act& a, const TView& z, const float* mean,
-                            const float* rstd, double* sums, cudaStream_t s) {
+Status launch_bn_bwd_reduce(const TView& grad_a, const float* scale, const float* shift,
+                            const TView& z, const float* mean, const float* rstd, double* sums,
+                            cudaStream_t s) {
   EXA_TRY(check_reduce_shape(z.a, "bn_bwd_reduce"));
-  EXA_CHECK(vec_ok(grad_a.a) && vec_ok(a) && grad_a.a.C == z.a.C && a.C == z.a.C &&
-                same_grid(grad_a.a, z.a) && same_grid(a, z.a) && a.fp32 == z.a.fp32 &&
+  EXA_CHECK(vec_ok(grad_a.a) && grad_a.a.C == z.a.C && same_grid(grad_a.a, z.a) &&
                 grad_a.a.fp32 == z.a.fp32,
             "bn_bwd_reduce: shape mismatch");
   const size_t vox = z.a.voxels();
@@ -364,14 +414,13 @@ Status launch_bn_bwd_reduce(const TView& grad_a, const Act& a, const TView& z, c
   const unsigned blocks = (unsigned)ceil_div64((int64_t)vox, (int64_t)lanes * RED_ITER);
   if (z.a.fp32)
     bn_bwd_reduce_kernel<float><<<blocks, RED_THREADS, 0, s>>>(
-        (const float*)grad_a.a.ptr, grad_a.a.cstride, grad_a.a.coff, grad_a.enc,
-        (const float*)a.ptr, a.cstride, a.coff, (const float*)z.a.ptr, z.a.cstride, z.a.coff, z.enc,
-        mean, rstd, z.a.C, vox, sums);
+        (const float*)grad_a.a.ptr, grad_a.a.cstride, grad_a.a.coff, grad_a.enc, scale, shift,
+        (const float*)z.a.ptr, z.a.cstride, z.a.coff, z.enc, mean, rstd, z.a.C, vox, sums);
   else
     bn_bwd_reduce_kernel<__nv_bfloat16><<<blocks, RED_THREADS, 0, s>>>(
-        (const __nv_bfloat16*)grad_a.a.ptr, grad_a.a.cstride, grad_a.a.coff, grad_a.enc,
-        (const __nv_bfloat16*)a.ptr, a.cstride, a.coff, (const __nv_bfloat16*)z.a.ptr, z.a.cstride,
-        z.a.coff, z.enc, mean, rstd, z.a.C, vox, sums);
+        (const __nv_bfloat16*)grad_a.a.ptr, grad_a.a.cstride, grad_a.a.coff, grad_a.enc, scale,
+        shift, (const __nv_bfloat16*)z.a.ptr, z.a.cstride, z.a.coff, z.enc, mean, rstd, z.a.C, vox,
+        sums);
   EXA_CUDA(cudaGetLastError());
   return Status::OK();
 }
@@ -402,66 +451,82 @@ Status launch_bn_bwd_finalize(const double* sums, int C, double count, const flo
 template <typename T>
 __global__ void __launch_bounds__(RED_THREADS)
 bn_bwd_apply_kernel(const T* __restrict__ g, int g_cstride, int g_coff, bool g_enc,
-                    const T* __restrict__ a, int a_cstride, int a_coff, const T* __restrict__ z,
-                    int z_cstride, int z_coff, bool z_enc, const float* __restrict__ mean,
-                    const float* __restrict__ rstd, const float* __restrict__ coef,
-                    T* __restrict__ dz, int C, size_t voxels, double* __restrict__ bias_sums) {
+                    const float* __restrict__ scale, const float* __restrict__ shift,
+                    const T* __restrict__ z, int z_cstride, int z_coff, bool z_enc,
+                    const float* __restrict__ mean, const float* __restrict__ rstd,
+                    const float* __restrict__ coef, T* __restrict__ dz, int C, size_t voxels,
+                    double* __restrict__ bias_sums) {
   const int cv = C / 8, lanes = RED_THREADS / cv;
   const int c8 = threadIdx.x % cv, lane = threadIdx.x / cv;
-  float m[8], r[8], k0[8], c1[8], c2[8], s[8], unused[8];
+  // dz = k0 (g - c1 - xhat c2) with xhat = (z - m) r  ==  k0 g - z (k0 c2 r) - k0 (c1 - m r c2)
+  float sc[8], sh[8], k0[8], kz[8], kc[8], s[8], unused[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    m[j] = __ldg(mean + 8 * c8 + j);
-    r[j] = __ldg(rstd + 8 * c8 + j);
+    const float m = __ldg(mean + 8 * c8 + j), r = __ldg(rstd + 8 * c8 + j);
+    const float c1 = __ldg(coef + C + 8 * c8 + j), c2 = __ldg(coef + 2 * C + 8 * c8 + j);
+    sc[j] = __ldg(scale + 8 * c8 + j);
+    sh[j] = __ldg(shift + 8 * c8 + j);
     k0[j] = __ldg(coef + 8 * c8 + j);
-    c1[j] = __ldg(coef + C + 8 * c8 + j);
-    c2[j] = __ldg(coef + 2 * C + 8 * c8 + j);
+    kz[j] = k0[j] * c2 * r;
+    kc[j] = k0[j] * (c1 - m * r * c2);
     s[j] = 0.f;
     unused[j] = 0.f;
   }
   const size_t v0 = (size_t)blockIdx.x * lanes * RED_ITER;
-  for (int k = 0; k < RED_ITER; ++k) {
-    const size_t v = v0 + (size_t)k * lanes + lane;
-    if (v >= voxels) break;
-    float fg[8], fa[8], fz[8], o[8];
-    load8_dec<T>(g + v * g_cstride + g_coff + 8 * c8, g_enc, fg);
-    load8<T>(a + v * a_cstride + a_coff + 8 * c8, fa);
-    load8_dec<T>(z + v * z_cstride + z_coff + 8 * c8, z_enc, fz);
+  for (int k = 0; k < RED_ITER; k += BWD_UNROLL) {
+    Raw8<T> rg[BWD_UNROLL], rz[BWD_UNROLL];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float gg = fa[j] > 0.f ? fg[j] : 0.01f * fg[j];
-      const float xh = (fz[j] - m[j]) * r[j];
-      o[j] = k0[j] * (gg - c1[j] - xh * c2[j]);
-      s[j] += o[j];
+    for (int u = 0; u < BWD_UNROLL; ++u) {
+      const size_t v = v0 + (size_t)(k + u) * lanes + lane;
+      if (v < voxels) {
+        rg[u].load(g + v * g_cstride + g_coff + 8 * c8);
+        rz[u].load(z + v * z_cstride + z_coff + 8 * c8);
+      }
     }
-    store8<T>(dz + v * C + 8 * c8, o);
+#pragma unroll
+    for (int u = 0; u < BWD_UNROLL; ++u) {
+      const size_t v = v0 + (size_t)(k + u) * lanes + lane;
+      if (v < voxels) {
+        float fg[8], fz[8], o[8];
+        rg[u].get(fg);
+        rz[u].get(fz);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float gv = dec(fg[j], g_enc), zv = dec(fz[j], z_enc);
+          const float pre = fmaf(zv, sc[j], sh[j]);
+          const float gg = pre > 0.f ? gv : 0.01f * gv;
+          o[j] = fmaf(k0[j], gg, -fmaf(zv, kz[j], kc[j]));
+          s[j] += o[j];
+        }
+        store8<T>(dz + v * C + 8 * c8, o);
+      }
+    }
   }
   // sums[0..C) take the bias gradient; the second half of the reduction is unused (zeros)
   block_channel_reduce(s, unused, cv, C, bias_sums);
 }
 
-Status launch_bn_bwd_apply(const TView& grad_a, const Act& a, const TView& z, const float* mean,
-                           const float* rstd, const float* coef, const Act& dz, double* bias_sums,
-                           cudaStream_t s) {
+Status launch_bn_bwd_apply(const TView& grad_a, const float* scale, const float* shift,
+                           const TView& z, const float* mean, const float* rstd, const float* coef,
+                           const Act& dz, double* bias_sums, cudaStream_t s) {
   EXA_TRY(check_reduce_shape(z.a, "bn_bwd_apply"));
-  EXA_CHECK(vec_ok(grad_a.a) && vec_ok(a) && grad_a.a.C == z.a.C && a.C == z.a.C &&
-                same_grid(grad_a.a, z.a) && same_grid(a, z.a) && same_grid(dz, z.a) &&
-                dz.C == z.a.C && dz.cstride == dz.C && dz.coff == 0 && dz.fp32 == z.a.fp32 &&
-                a.fp32 == z.a.fp32 && grad_a.a.fp32 == z.a.fp32,
+  EXA_CHECK(vec_ok(grad_a.a) && grad_a.a.C == z.a.C && same_grid(grad_a.a, z.a) &&
+                same_grid(dz, z.a) && dz.C == z.a.C && dz.cstride == dz.C && dz.coff == 0 &&
+                dz.fp32 == z.a.fp32 && grad_a.a.fp32 == z.a.fp32,
             "bn_bwd_apply: shape mismatch (dz must be dense)");
   const size_t vox = z.a.voxels();
   const int lanes = RED_THREADS / (z.a.C / 8);
   const unsigned blocks = (unsigned)ceil_div64((int64_t)vox, (int64_t)lanes * RED_ITER);
   if (z.a.fp32)
     bn_bwd_apply_kernel<float><<<blocks, RED_THREADS, 0, s>>>(
-        (const float*)grad_a.a.ptr, grad_a.a.cstride, grad_a.a.coff, grad_a.enc,
-        (const float*)a.ptr, a.cstride, a.coff, (const float*)z.a.ptr, z.a.cstride, z.a.coff, z.enc,
-        mean, rstd, coef, (float*)dz.ptr, z.a.C, vox, bias_sums);
+        (const float*)grad_a.a.ptr, grad_a.a.cstride, grad_a.a.coff, grad_a.enc, scale, shift,
+        (const float*)z.a.ptr, z.a.cstride, z.a.coff, z.enc, mean, rstd, coef, (float*)dz.ptr,
+        z.a.C, vox, bias_sums);
   else
     bn_bwd_apply_kernel<__nv_bfloat16><<<blocks, RED_THREADS, 0, s>>>(
-        (const __nv_bfloat16*)grad_a.a.ptr, grad_a.a.cstride, grad_a.a.coff, grad_a.enc,
-        (const __nv_bfloat16*)a.ptr, a.cstride, a.coff, (const __nv_bfloat16*)z.a.ptr, z.a.cstride,
-        z.a.coff, z.enc, mean, rstd, coef, (__nv_bfloat16*)dz.ptr, z.a.C, vox, bias_sums);
+        (const __nv_bfloat16*)grad_a.a.ptr, grad_a.a.cstride, grad_a.a.coff, grad_a.enc, scale,
+        shift, (const __nv_bfloat16*)z.a.ptr, z.a.cstride, z.a.coff, z.enc, mean, rstd, coef,
+        (__nv_bfloat16*)dz.ptr, z.a.C, vox, bias_sums);
   EXA_CUDA(cudaGetLastError());
   return Status::OK();
 }

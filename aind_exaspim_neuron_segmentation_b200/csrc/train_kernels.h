@@ -44,18 +44,21 @@ Status launch_bn_finalize(const double* sums, int C, double count, const float* 
 // a = LeakyReLU(scale * z + shift)
 Status launch_bn_apply(const TView& z, const float* scale, const float* shift, const Act& a,
                        cudaStream_t s);
-// backward of BatchNorm + LeakyReLU: g = dA * (a > 0 ? 1 : 0.01);
+// backward of BatchNorm + LeakyReLU: g = dA * (scale z + shift > 0 ? 1 : 0.01) -- the mask is
+// recomputed from the raw conv output exactly as bn_apply computed the pre-activation, which
+// saves reading the activation again;
 // sums[0..C) += sum g, sums[C..2C) += sum g * xhat      (xhat = (z - mean) * rstd)
-Status launch_bn_bwd_reduce(const TView& grad_a, const Act& a, const TView& z, const float* mean,
-                            const float* rstd, double* sums, cudaStream_t s);
+Status launch_bn_bwd_reduce(const TView& grad_a, const float* scale, const float* shift,
+                            const TView& z, const float* mean, const float* rstd, double* sums,
+                            cudaStream_t s);
 // dgamma, dbeta -> gradient slots; coef[0..C) = gamma*rstd, [C..2C) = sum g / n, [2C..3C) = sum g xhat / n
 Status launch_bn_bwd_finalize(const double* sums, int C, double count, const float* gamma,
                               const float* rstd, float* dgamma, float* dbeta, float* coef,
                               cudaStream_t s);
 // dz = k (g - c1 - xhat c2), dense, plain; bias_sums[0..C) += sum dz (double; the conv bias gradient)
-Status launch_bn_bwd_apply(const TView& grad_a, const Act& a, const TView& z, const float* mean,
-                           const float* rstd, const float* coef, const Act& dz, double* bias_sums,
-                           cudaStream_t s);
+Status launch_bn_bwd_apply(const TView& grad_a, const float* scale, const float* shift,
+                           const TView& z, const float* mean, const float* rstd, const float* coef,
+                           const Act& dz, double* bias_sums, cudaStream_t s);
 Status launch_double_to_float(const double* in, float* out, int n, cudaStream_t s);
 // out = plain values of an (encoded) tensor
 Status launch_decode(const TView& in, const Act& out, cudaStream_t s);

@@ -18,7 +18,8 @@
 // and are written out once (split-K partial sums, reduced by launch_wgrad_reduce).
 //
 // A CTA marches columns (batch, 8 rows, 16 voxels of x) along z: per step one new x plane
-// [8][20][32] and one dz plane [10][16][32] arrive by TMA (20 KB for 24 instructions).
+// [8][20][32] and one dz plane [10][16][32] arrive by TMA (20 KB for 24 instructions), four
+// steps ahead of their use.
 // Warp 0: TMA producer, warp 1: MMA issuer, all four warps: final TMEM read-out.
 #include <stdlib.h>
 
@@ -31,8 +32,8 @@ namespace {
 
 constexpr int WT_RY = 8;    // x rows per tile (dz rows: WT_RY + 2)
 constexpr int WT_XW = 20;   // staged voxels per x row: 16 + one halo voxel each side + 2 pad
-constexpr int WT_XS = 4;    // x plane slots (three live + one in flight)
-constexpr int WT_DS = 2;    // dz plane slots
+constexpr int WT_XS = 7;    // x plane slots: three live + four in flight (TMA latency is 2-3 steps)
+constexpr int WT_DS = 5;    // dz plane slots: one live + four in flight
 constexpr int WT_X_BYTES = WT_RY * WT_XW * 64;      // 10240
 constexpr int WT_D_BYTES = (WT_RY + 2) * 16 * 64;   // 10240
 constexpr int WT_BAR_OFF = WT_XS * WT_X_BYTES + WT_DS * WT_D_BYTES;
@@ -67,13 +68,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   uint8_t* xs = smem;
   uint8_t* ds = smem + WT_XS * WT_X_BYTES;
   uint64_t* bars = (uint64_t*)(smem + WT_BAR_OFF);
-  uint64_t* full_x = bars;        // [WT_XS]  TMA -> MMA
-  uint64_t* empty_x = bars + 4;   // [WT_XS]  MMA -> TMA
-  uint64_t* full_d = bars + 8;    // [WT_DS]
-  uint64_t* empty_d = bars + 10;  // [WT_DS]
-  uint64_t* done_bar = bars + 12;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 13);
-  uint32_t* issued = (uint32_t*)(bars + 14);  // [3] accumulator kz has received an MMA
+  uint64_t* full_x = bars;                      // [WT_XS]  TMA -> MMA
+  uint64_t* empty_x = bars + WT_XS;             // [WT_XS]  MMA -> TMA
+  uint64_t* full_d = bars + 2 * WT_XS;          // [WT_DS]
+  uint64_t* empty_d = bars + 2 * WT_XS + WT_DS;  // [WT_DS]
+  uint64_t* done_bar = bars + 2 * WT_XS + 2 * WT_DS;
+  uint32_t* tmem_slot = (uint32_t*)(done_bar + 1);
+  uint32_t* issued = (uint32_t*)(done_bar + 2);  // [3] accumulator kz has received an MMA
+  static_assert((2 * WT_XS + 2 * WT_DS + 4) * 8 <= 256, "barrier block");
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;

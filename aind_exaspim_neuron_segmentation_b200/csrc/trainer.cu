@@ -77,7 +77,7 @@ Status Trainer::profile_begin() {
 }
 
 Status Trainer::profile_end(double* ms_by_cat, int64_t* launches_by_cat, int n) {
-  EXA_CHECK(ms_by_cat && launches_by_cat && n >= CAT_COUNT, "train_profile_end: need >= 8 slots");
+  EXA_CHECK(ms_by_cat && launches_by_cat && n >= CAT_COUNT, "train_profile_end: need >= 12 slots");
   EXA_CUDA(cudaSetDevice(device_));
   prof_on_ = false;
   for (int i = 0; i < n; ++i) {
@@ -528,20 +528,20 @@ Status Trainer::layer_backward(int l, const TView& grad_a, const float* x, float
   dz.D = L.z.D; dz.H = L.z.H; dz.W = L.z.W;
   dz.C = dz.cstride = L.cout;
   EXA_CUDA(cudaMemsetAsync(L.sums, 0, sizeof(double) * 2 * L.cout, s));
-  EXA_LAUNCH(CAT_BN_BWD, launch_bn_bwd_reduce(grad_a, L.a, encoded(L.z), L.mean, L.rstd, L.sums, s));
+  EXA_LAUNCH(CAT_BN_BWD, launch_bn_bwd_reduce(grad_a, L.scale, L.shift, encoded(L.z), L.mean, L.rstd, L.sums, s));
   EXA_LAUNCH(CAT_BN_BWD, launch_bn_bwd_finalize(L.sums, L.cout, count, L.gamma, L.rstd, grads + L.ggamma,
                                     grads + L.gbeta, L.coef, s));
   EXA_CUDA(cudaMemsetAsync(L.sums, 0, sizeof(double) * 2 * L.cout, s));
-  EXA_LAUNCH(CAT_BN_BWD, launch_bn_bwd_apply(grad_a, L.a, encoded(L.z), L.mean, L.rstd, L.coef, dz, L.sums, s));
+  EXA_LAUNCH(CAT_BN_BWD, launch_bn_bwd_apply(grad_a, L.scale, L.shift, encoded(L.z), L.mean, L.rstd, L.coef, dz, L.sums, s));
   EXA_LAUNCH(CAT_BN_BWD, launch_double_to_float(L.sums, grads + L.gb, L.cout, s));
   if (l == 0) {
-    EXA_LAUNCH(CAT_WGRAD, launch_wgrad_stem(x, dz, partial_, num_sms_, s));
-    EXA_LAUNCH(CAT_WGRAD, launch_wgrad_reduce(partial_, wgrad_stem_splits(dz, num_sms_), (size_t)L.cout * 27,
+    EXA_LAUNCH(CAT_WGRAD_STEM, launch_wgrad_stem(x, dz, partial_, num_sms_, s));
+    EXA_LAUNCH(CAT_WGRAD_REDUCE, launch_wgrad_reduce(partial_, wgrad_stem_splits(dz, num_sms_), (size_t)L.cout * 27,
                                    grads + L.gw, s));
     return Status::OK();
   }
   EXA_LAUNCH(CAT_WGRAD, launch_wgrad(L.x, dz, partial_, num_sms_, s));
-  EXA_LAUNCH(CAT_WGRAD, launch_wgrad_reduce(partial_, wgrad_splits(L.x, L.cout, num_sms_),
+  EXA_LAUNCH(CAT_WGRAD_REDUCE, launch_wgrad_reduce(partial_, wgrad_splits(L.x, L.cout, num_sms_),
                                  (size_t)L.cout * L.cin * 27, grads + L.gw, s));
   EXA_LAUNCH(CAT_DGRAD, conv_any(dz, L.gx, L.w_bwd, L.w_bwd_zf, zero_bias_, s));
   return Status::OK();
@@ -557,39 +557,39 @@ Status Trainer::backward(const float* x, const float* dlogits, float* grads, cud
   // head (unet3d.py:318)
   const int nh = C * c[0] + C;
   EXA_CUDA(cudaMemsetAsync(head_sums_, 0, sizeof(double) * nh, s));
-  EXA_LAUNCH(CAT_MISC_BWD, launch_head_bwd_dw(dlogits, u4_, C, head_sums_, s));
-  EXA_LAUNCH(CAT_MISC_BWD, launch_double_to_float(head_sums_, grads + g_head_w_, C * c[0], s));
-  EXA_LAUNCH(CAT_MISC_BWD, launch_double_to_float(head_sums_ + C * c[0], grads + g_head_b_, C, s));
-  EXA_LAUNCH(CAT_MISC_BWD, launch_head_bwd_dx(dlogits, head_w_, C, g_u4_, s));
+  EXA_LAUNCH(CAT_HEAD_BWD, launch_head_bwd_dw(dlogits, u4_, C, head_sums_, s));
+  EXA_LAUNCH(CAT_HEAD_BWD, launch_double_to_float(head_sums_, grads + g_head_w_, C * c[0], s));
+  EXA_LAUNCH(CAT_HEAD_BWD, launch_double_to_float(head_sums_ + C * c[0], grads + g_head_b_, C, s));
+  EXA_LAUNCH(CAT_HEAD_BWD, launch_head_bwd_dx(dlogits, head_w_, C, g_u4_, s));
   // decoder
   EXA_TRY(layer_backward(17, plain(g_u4_), x, grads, s));
   EXA_TRY(layer_backward(16, encoded(g_u4a_), x, grads, s));
-  EXA_LAUNCH(CAT_MISC_BWD, launch_upsample_bwd(encoded(channel_slice(g_cat4_, c[0], c[0])), g_u3_, s));
+  EXA_LAUNCH(CAT_UPSAMPLE_BWD, launch_upsample_bwd(encoded(channel_slice(g_cat4_, c[0], c[0])), g_u3_, s));
   EXA_TRY(layer_backward(15, plain(g_u3_), x, grads, s));
   EXA_TRY(layer_backward(14, encoded(g_u3a_), x, grads, s));
-  EXA_LAUNCH(CAT_MISC_BWD, launch_upsample_bwd(encoded(channel_slice(g_cat3_, c[1], c[1])), g_u2_, s));
+  EXA_LAUNCH(CAT_UPSAMPLE_BWD, launch_upsample_bwd(encoded(channel_slice(g_cat3_, c[1], c[1])), g_u2_, s));
   EXA_TRY(layer_backward(13, plain(g_u2_), x, grads, s));
   EXA_TRY(layer_backward(12, encoded(g_u2a_), x, grads, s));
-  EXA_LAUNCH(CAT_MISC_BWD, launch_upsample_bwd(encoded(channel_slice(g_cat2_, c[2], c[2])), g_u1_, s));
+  EXA_LAUNCH(CAT_UPSAMPLE_BWD, launch_upsample_bwd(encoded(channel_slice(g_cat2_, c[2], c[2])), g_u1_, s));
   EXA_TRY(layer_backward(11, plain(g_u1_), x, grads, s));
   EXA_TRY(layer_backward(10, encoded(g_u1a_), x, grads, s));
-  EXA_LAUNCH(CAT_MISC_BWD, launch_upsample_bwd(encoded(channel_slice(g_cat1_, c[3], c[3])), g_x5_, s));
+  EXA_LAUNCH(CAT_UPSAMPLE_BWD, launch_upsample_bwd(encoded(channel_slice(g_cat1_, c[3], c[3])), g_x5_, s));
   // encoder: every skip tensor collects its concat half and the max-pool's gradient
   EXA_TRY(layer_backward(9, plain(g_x5_), x, grads, s));
   EXA_TRY(layer_backward(8, encoded(g_d4a_), x, grads, s));
-  EXA_LAUNCH(CAT_MISC_BWD, launch_pool_bwd_merge(encoded(channel_slice(g_cat1_, 0, c[3])), encoded(g_p4_), x4_,
+  EXA_LAUNCH(CAT_POOL_BWD, launch_pool_bwd_merge(encoded(channel_slice(g_cat1_, 0, c[3])), encoded(g_p4_), x4_,
                                    g_x4_, s));
   EXA_TRY(layer_backward(7, plain(g_x4_), x, grads, s));
   EXA_TRY(layer_backward(6, encoded(g_d3a_), x, grads, s));
-  EXA_LAUNCH(CAT_MISC_BWD, launch_pool_bwd_merge(encoded(channel_slice(g_cat2_, 0, c[2])), encoded(g_p3_), x3_,
+  EXA_LAUNCH(CAT_POOL_BWD, launch_pool_bwd_merge(encoded(channel_slice(g_cat2_, 0, c[2])), encoded(g_p3_), x3_,
                                    g_x3_, s));
   EXA_TRY(layer_backward(5, plain(g_x3_), x, grads, s));
   EXA_TRY(layer_backward(4, encoded(g_d2a_), x, grads, s));
-  EXA_LAUNCH(CAT_MISC_BWD, launch_pool_bwd_merge(encoded(channel_slice(g_cat3_, 0, c[1])), encoded(g_p2_), x2_,
+  EXA_LAUNCH(CAT_POOL_BWD, launch_pool_bwd_merge(encoded(channel_slice(g_cat3_, 0, c[1])), encoded(g_p2_), x2_,
                                    g_x2_, s));
   EXA_TRY(layer_backward(3, plain(g_x2_), x, grads, s));
   EXA_TRY(layer_backward(2, encoded(g_d1a_), x, grads, s));
-  EXA_LAUNCH(CAT_MISC_BWD, launch_pool_bwd_merge(encoded(channel_slice(g_cat4_, 0, c[0])), encoded(g_p1_), x1_,
+  EXA_LAUNCH(CAT_POOL_BWD, launch_pool_bwd_merge(encoded(channel_slice(g_cat4_, 0, c[0])), encoded(g_p1_), x1_,
                                    g_x1_, s));
   EXA_TRY(layer_backward(1, plain(g_x1_), x, grads, s));
   EXA_TRY(layer_backward(0, encoded(g_a0_), x, grads, s));

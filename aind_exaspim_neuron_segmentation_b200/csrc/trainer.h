@@ -34,7 +34,8 @@ class Trainer {
   size_t workspace_bytes() const { return ws_bytes_; }
   // per-category kernel timing with CUDA events on the launching stream (bench / roofline)
   enum Category { CAT_PACK = 0, CAT_FPROP, CAT_BN_FWD, CAT_MISC_FWD, CAT_BN_BWD, CAT_WGRAD,
-                  CAT_DGRAD, CAT_MISC_BWD, CAT_COUNT };
+                  CAT_DGRAD, CAT_HEAD_BWD, CAT_WGRAD_STEM, CAT_WGRAD_REDUCE, CAT_UPSAMPLE_BWD,
+                  CAT_POOL_BWD, CAT_COUNT };
   Status profile_begin();
   Status profile_end(double* ms_by_cat, int64_t* launches_by_cat, int n);
 

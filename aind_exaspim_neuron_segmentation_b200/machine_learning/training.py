@@ -129,7 +129,7 @@ class TrainEngine:
         return [flat[off:off + numel].view(shape) for _, off, numel, shape in self._slots]
 
     PROFILE_CATEGORIES = ("pack", "fprop", "bn_fwd", "misc_fwd", "bn_bwd", "wgrad", "dgrad",
-                          "misc_bwd")
+                          "head_bwd", "wgrad_stem", "wgrad_reduce", "upsample_bwd", "pool_bwd")
 
     def profile_begin(self):
         self._check(self._lib.exa_train_profile_begin(self._h), "exa_train_profile_begin")

@@ -269,9 +269,11 @@ int exa_train_backward(exa_trainer* t, const float* x_dev, const float* grad_log
 int64_t exa_train_launch_count(const exa_trainer* t);
 /* like exa_profile_begin / exa_profile_end: summed device milliseconds and launches per category:
  * 0 weight packing, 1 forward convolutions (tcgen05), 2 BatchNorm forward (statistics + apply),
- * 3 max-pool / upsample / head forward, 4 BatchNorm + LeakyReLU backward, 5 weight gradients,
- * 6 data gradients (tcgen05), 7 max-pool / upsample / head backward.  n >= 8. */
-enum { EXA_TRAIN_PROFILE_CATEGORIES = 8 };
+ * 3 max-pool / upsample / head forward, 4 BatchNorm + LeakyReLU backward, 5 weight gradients
+ * (tcgen05), 6 data gradients (tcgen05), 7 head backward, 8 weight gradient of the Cin = 1 stem,
+ * 9 split-K reductions of the weight gradients, 10 upsample backward, 11 max-pool backward.
+ * n >= 12. */
+enum { EXA_TRAIN_PROFILE_CATEGORIES = 12 };
 int exa_train_profile_begin(exa_trainer* t);
 int exa_train_profile_end(exa_trainer* t, double* ms_by_category, int64_t* launches_by_category,
                           int n);
