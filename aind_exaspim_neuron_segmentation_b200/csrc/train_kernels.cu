@@ -73,6 +73,39 @@ constexpr int RED_ITER = 32;  // voxels per thread and block: fp32 partial sums 
 
 }  // namespace
 
+// Raw 8-channel vectors: the loads of several voxels are issued before any is converted, so
+// that enough bytes are in flight per thread (these kernels hold ~70 per-channel constants in
+// registers, which limits occupancy).
+template <typename T>
+struct Raw8;
+template <>
+struct Raw8<__nv_bfloat16> {
+  uint4 v;
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) { v = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void get(float (&f)[8]) const {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 t = __bfloat1622float2(h[i]);
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
+  }
+};
+template <>
+struct Raw8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) {
+    a = *reinterpret_cast<const float4*>(p);
+    b = *reinterpret_cast<const float4*>(p + 4);
+  }
+  __device__ __forceinline__ void get(float (&f)[8]) const {
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+    f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  }
+};
+constexpr int BWD_UNROLL = 4;
+
 // ---------------------------------------------------------------------------
 // T1: weight packing
 // ---------------------------------------------------------------------------
@@ -316,39 +349,6 @@ Status launch_bn_apply(const TView& z, const float* scale, const float* shift, c
   EXA_CUDA(cudaGetLastError());
   return Status::OK();
 }
-
-// Raw 8-channel vectors: the loads of several voxels are issued before any is converted, so
-// that enough bytes are in flight per thread (these kernels hold ~70 per-channel constants in
-// registers, which limits occupancy).
-template <typename T>
-struct Raw8;
-template <>
-struct Raw8<__nv_bfloat16> {
-  uint4 v;
-  __device__ __forceinline__ void load(const __nv_bfloat16* p) { v = *reinterpret_cast<const uint4*>(p); }
-  __device__ __forceinline__ void get(float (&f)[8]) const {
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 t = __bfloat1622float2(h[i]);
-      f[2 * i] = t.x;
-      f[2 * i + 1] = t.y;
-    }
-  }
-};
-template <>
-struct Raw8<float> {
-  float4 a, b;
-  __device__ __forceinline__ void load(const float* p) {
-    a = *reinterpret_cast<const float4*>(p);
-    b = *reinterpret_cast<const float4*>(p + 4);
-  }
-  __device__ __forceinline__ void get(float (&f)[8]) const {
-    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
-    f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
-  }
-};
-constexpr int BWD_UNROLL = 4;
 
 template <typename T>
 __global__ void __launch_bounds__(RED_THREADS)
@@ -782,8 +782,9 @@ Status launch_head_bwd_dx(const float* dlogits, const float* hw, int C, const Ac
   return Status::OK();
 }
 
-// dW[k][c] = sum_v dl[b][k][sp] u[v][c], db[k] = sum_v dl[b][k][sp]; thread = (lane, 8 channels)
-template <typename T>
+// dW[k][c] = sum_v dl[b][k][sp] u[v][c], db[k] = sum_v dl[b][k][sp]; thread = (lane, 8 channels);
+// CT = number of head outputs (compile time: 1 foreground, 3 affinities, 8 generic upper bound)
+template <typename T, int CT>
 __global__ void __launch_bounds__(RED_THREADS)
 head_bwd_dw_kernel(const float* __restrict__ dl, const T* __restrict__ u, int u_cstride,
                    int u_coff, int C, int cin, int B, size_t vb, double* __restrict__ sums) {
@@ -791,48 +792,63 @@ head_bwd_dw_kernel(const float* __restrict__ dl, const T* __restrict__ u, int u_
   const int cv = cin / 8, lanes = RED_THREADS / cv;
   const int c8 = threadIdx.x % cv, lane = threadIdx.x / cv;
   const size_t voxels = (size_t)B * vb;
-  float acc[8][8];
-  float db[8];
+  float acc[CT][8];
+  float db[CT];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
+  for (int k = 0; k < CT; ++k) {
     db[k] = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[k][j] = 0.f;
   }
   const size_t v0 = (size_t)blockIdx.x * lanes * RED_ITER;
-  for (int it = 0; it < RED_ITER; ++it) {
-    const size_t v = v0 + (size_t)it * lanes + lane;
-    if (v >= voxels) break;
-    const size_t b = v / vb, sp = v % vb;
-    float f[8];
-    load8<T>(u + v * u_cstride + u_coff + 8 * c8, f);
+  for (int it = 0; it < RED_ITER; it += BWD_UNROLL) {
+    Raw8<T> ru[BWD_UNROLL];
+    float d[BWD_UNROLL][CT];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      if (k < C) {
-        const float d = __ldg(dl + (b * C + k) * vb + sp);
-        db[k] += d;
+    for (int q = 0; q < BWD_UNROLL; ++q) {
+      const size_t v = v0 + (size_t)(it + q) * lanes + lane;
+      if (v < voxels) {
+        const size_t b = v / vb, sp = v % vb;
+        ru[q].load(u + v * u_cstride + u_coff + 8 * c8);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[k][j] = fmaf(d, f[j], acc[k][j]);
+        for (int k = 0; k < CT; ++k) d[q][k] = k < C ? __ldg(dl + (b * C + k) * vb + sp) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < BWD_UNROLL; ++q) {
+      const size_t v = v0 + (size_t)(it + q) * lanes + lane;
+      if (v < voxels) {
+        float f[8];
+        ru[q].get(f);
+#pragma unroll
+        for (int k = 0; k < CT; ++k) {
+          db[k] += d[q][k];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[k][j] = fmaf(d[q][k], f[j], acc[k][j]);
+        }
       }
     }
   }
   // per output channel k: reduce the lanes through shared memory, one double atomic per entry
-  for (int k = 0; k < C; ++k) {
-    __syncthreads();
 #pragma unroll
-    for (int j = 0; j < 8; ++j) sh[threadIdx.x * 8 + j] = acc[k][j];
-    __syncthreads();
-    for (int ch = threadIdx.x; ch < cin; ch += RED_THREADS) {
-      const int cc = ch / 8, j = ch % 8;
-      double a0 = 0.0;
-      for (int l = 0; l < lanes; ++l) a0 += (double)sh[(l * cv + cc) * 8 + j];
-      atomicAdd(sums + (size_t)k * cin + ch, a0);
+  for (int k = 0; k < CT; ++k) {
+    if (k < C) {
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sh[threadIdx.x * 8 + j] = acc[k][j];
+      __syncthreads();
+      for (int ch = threadIdx.x; ch < cin; ch += RED_THREADS) {
+        const int cc = ch / 8, j = ch % 8;
+        double a0 = 0.0;
+        for (int l = 0; l < lanes; ++l) a0 += (double)sh[(l * cv + cc) * 8 + j];
+        atomicAdd(sums + (size_t)k * cin + ch, a0);
+      }
     }
   }
   __syncthreads();
   if (c8 == 0) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) sh[lane * 8 + k] = db[k];
+    for (int k = 0; k < CT; ++k) sh[lane * 8 + k] = db[k];
   }
   __syncthreads();
   if (threadIdx.x < C) {
@@ -842,6 +858,21 @@ head_bwd_dw_kernel(const float* __restrict__ dl, const T* __restrict__ u, int u_
   }
 }
 
+template <typename T>
+static void head_bwd_dw_dispatch(const float* dlogits, const Act& u, int C, double* sums,
+                                 unsigned blocks, size_t vb, cudaStream_t s) {
+  const T* up = (const T*)u.ptr;
+  if (C == 1)
+    head_bwd_dw_kernel<T, 1><<<blocks, RED_THREADS, 0, s>>>(dlogits, up, u.cstride, u.coff, C, u.C,
+                                                             u.B, vb, sums);
+  else if (C <= 3)
+    head_bwd_dw_kernel<T, 3><<<blocks, RED_THREADS, 0, s>>>(dlogits, up, u.cstride, u.coff, C, u.C,
+                                                             u.B, vb, sums);
+  else
+    head_bwd_dw_kernel<T, 8><<<blocks, RED_THREADS, 0, s>>>(dlogits, up, u.cstride, u.coff, C, u.C,
+                                                             u.B, vb, sums);
+}
+
 Status launch_head_bwd_dw(const float* dlogits, const Act& u, int C, double* sums, cudaStream_t s) {
   EXA_TRY(check_reduce_shape(u, "head_bwd_dw"));
   EXA_CHECK(C >= 1 && C <= 8, "head_bwd_dw: at most 8 output channels");
@@ -849,12 +880,9 @@ Status launch_head_bwd_dw(const float* dlogits, const Act& u, int C, double* sum
   const int lanes = RED_THREADS / (u.C / 8);
   const unsigned blocks = (unsigned)ceil_div64((int64_t)u.voxels(), (int64_t)lanes * RED_ITER);
   if (u.fp32)
-    head_bwd_dw_kernel<float><<<blocks, RED_THREADS, 0, s>>>(dlogits, (const float*)u.ptr,
-                                                              u.cstride, u.coff, C, u.C, u.B, vb,
-                                                              sums);
+    head_bwd_dw_dispatch<float>(dlogits, u, C, sums, blocks, vb, s);
   else
-    head_bwd_dw_kernel<__nv_bfloat16><<<blocks, RED_THREADS, 0, s>>>(
-        dlogits, (const __nv_bfloat16*)u.ptr, u.cstride, u.coff, C, u.C, u.B, vb, sums);
+    head_bwd_dw_dispatch<__nv_bfloat16>(dlogits, u, C, sums, blocks, vb, s);
   EXA_CUDA(cudaGetLastError());
   return Status::OK();
 }
@@ -1136,37 +1164,42 @@ Status launch_wgrad(const Act& x, const Act& dz, float* partial, int num_sms, cu
   return Status::OK();
 }
 
-// Stem (Cin = 1): thread = (co of 32, group of 4 taps); a block walks rows (b, z, y) of W voxels.
+// Stem (Cin = 1): thread = (co of 32, kz): nine accumulators (ky, kx); a block walks rows
+// (b, z, y) of W voxels staged in shared memory (dz row as floats, the 3x3 input rows around it).
+// Four voxels per iteration: 4 dz loads + 3 x (float4 + float2) input loads feed 36 FMAs.
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(96)
 wgrad_stem_kernel(const float* __restrict__ x, const T* __restrict__ dz, float* __restrict__ partial,
                   int B, int D, int H, int W, int cout, int rows_total) {
-  extern __shared__ float st_smem[];
-  float* Dsh = st_smem;            // [W][32]
-  float* Xsh = st_smem + W * 32;   // [9][W + 2]
-  const int t = threadIdx.x, co = t & 31, tg = t >> 5;
+  extern __shared__ __align__(16) float st_smem[];
+  const int Wp = (W + 3) & ~3, XS = Wp + 4;
+  float* Dsh = st_smem;            // [Wp][32], zero beyond W
+  float* Xsh = st_smem + Wp * 32;  // [9][XS]: column c <-> x = c - 1, zero outside the volume
+  const int t = threadIdx.x, co = t & 31, kz = t >> 5;
   const int cob = blockIdx.y;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  int kzy[4], kxs[4];
+  float acc[3][3];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int tap = tg * 4 + j;
-    kzy[j] = tap < 27 ? tap / 3 : 0;
-    kxs[j] = tap % 3;
-  }
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) acc[i][j] = 0.f;
   for (int row = blockIdx.x; row < rows_total; row += gridDim.x) {
     const int y = row % H, z = (row / H) % D, b = row / (H * D);
     __syncthreads();
-    for (int i = t; i < W * 4; i += 256) {  // 8 channels per item
+    for (int i = t; i < Wp * 4; i += 96) {  // 8 channels per item
       const int xv = i >> 2, c8 = i & 3;
-      const size_t gv = (((size_t)b * D + z) * H + y) * W + xv;
       float f[8];
-      load8<T>(dz + gv * cout + cob * 32 + c8 * 8, f);
+      if (xv < W) {
+        const size_t gv = (((size_t)b * D + z) * H + y) * W + xv;
+        load8<T>(dz + gv * cout + cob * 32 + c8 * 8, f);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = 0.f;
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) Dsh[xv * 32 + c8 * 8 + j] = f[j];
     }
-    for (int i = t; i < 9 * (W + 2); i += 256) {
-      const int xx = i % (W + 2) - 1, r9 = i / (W + 2);
+    for (int i = t; i < 9 * XS; i += 96) {
+      const int xx = i % XS - 1, r9 = i / XS;
       const int gz = z + r9 / 3 - 1, gy = y + r9 % 3 - 1;
       float v = 0.f;
       if (gz >= 0 && gz < D && gy >= 0 && gy < H && xx >= 0 && xx < W)
@@ -1174,23 +1207,33 @@ wgrad_stem_kernel(const float* __restrict__ x, const T* __restrict__ dz, float* 
       Xsh[i] = v;
     }
     __syncthreads();
-    for (int xv = 0; xv < W; ++xv) {
-      const float d = Dsh[xv * 32 + co];
+    for (int xv = 0; xv < Wp; xv += 4) {
+      float d[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[j] = fmaf(d, Xsh[kzy[j] * (W + 2) + xv + kxs[j]], acc[j]);
+      for (int i = 0; i < 4; ++i) d[i] = Dsh[(xv + i) * 32 + co];
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const float* rowp = Xsh + (kz * 3 + ky) * XS + xv;
+        const float4 p = *reinterpret_cast<const float4*>(rowp);
+        const float2 q = *reinterpret_cast<const float2*>(rowp + 4);
+        const float v[6] = {p.x, p.y, p.z, p.w, q.x, q.y};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) acc[ky][kx] = fmaf(d[i], v[i + kx], acc[ky][kx]);
+      }
     }
   }
-  float* dst = partial + (size_t)blockIdx.x * cout * 27;
+  float* dst = partial + (size_t)blockIdx.x * cout * 27 + (size_t)(cob * 32 + co) * 27 + kz * 9;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int tap = tg * 4 + j;
-    if (tap < 27) dst[(size_t)(cob * 32 + co) * 27 + tap] = acc[j];
-  }
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) dst[ky * 3 + kx] = acc[ky][kx];
 }
 
 int wgrad_stem_splits(const Act& dz, int num_sms) {
   const int rows = dz.B * dz.D * dz.H;
-  int s = 4 * num_sms / (dz.C / 32);
+  int s = 12 * num_sms / (dz.C / 32);  // 96-thread blocks, ~16 KB of shared memory each
   if (s > rows) s = rows;
   return s < 1 ? 1 : s;
 }
@@ -1201,19 +1244,20 @@ Status launch_wgrad_stem(const float* x, const Act& dz, float* partial, int num_
             "wgrad_stem: dz must be dense with a multiple of 32 channels");
   const int rows = dz.B * dz.D * dz.H;
   const int splits = wgrad_stem_splits(dz, num_sms);
-  const size_t smem = (size_t)(dz.W * 32 + 9 * (dz.W + 2)) * 4;
+  const int wp = (dz.W + 3) & ~3;
+  const size_t smem = (size_t)(wp * 32 + 9 * (wp + 4)) * 4;
   dim3 grid((unsigned)splits, (unsigned)(dz.C / 32));
   if (dz.fp32) {
     if (smem > 48 * 1024)
       EXA_CUDA(cudaFuncSetAttribute(wgrad_stem_kernel<float>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    wgrad_stem_kernel<float><<<grid, 256, smem, s>>>(x, (const float*)dz.ptr, partial, dz.B, dz.D,
+    wgrad_stem_kernel<float><<<grid, 96, smem, s>>>(x, (const float*)dz.ptr, partial, dz.B, dz.D,
                                                       dz.H, dz.W, dz.C, rows);
   } else {
     if (smem > 48 * 1024)
       EXA_CUDA(cudaFuncSetAttribute(wgrad_stem_kernel<__nv_bfloat16>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    wgrad_stem_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>(x, (const __nv_bfloat16*)dz.ptr,
+    wgrad_stem_kernel<__nv_bfloat16><<<grid, 96, smem, s>>>(x, (const __nv_bfloat16*)dz.ptr,
                                                               partial, dz.B, dz.D, dz.H, dz.W, dz.C,
                                                               rows);
   }
