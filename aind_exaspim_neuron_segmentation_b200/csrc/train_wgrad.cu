@@ -141,20 +141,34 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       constexpr uint32_t idesc = umma_idesc_bf16(128, 96) | (1u << 15) | (1u << 16);  // A, B MN-major
       uint32_t xbase = 0, dbase = 0;  // global index of this column's plane 0
       uint32_t first[3] = {1u, 1u, 1u};
+      bool peek_x = false, peek_d = false;
       for (int col = blockIdx.x; col < a.cols_total; col += gridDim.x) {
         const int yt = (col / a.ntx) % a.nty;
         const int rows = min(WT_RY, a.H - yt * WT_RY);  // x rows inside the volume
         for (int z = 0; z < D; ++z) {
+          // A barrier probe whose result is consumed at once stalls the issue stream for ~150
+          // cycles (tools/umma_probe.cu); the planes of step z were probed during step z-1
+          // (they arrive four steps ahead), so the blocking wait only runs when the probe failed.
           if (z == 0) {
             const uint32_t g = xbase;
             mbar_wait(smem_u32(&full_x[g % WT_XS]), (g / WT_XS) & 1u);
+            peek_x = peek_d = false;
           }
-          if (z + 1 < D) {
+          if (z + 1 < D && !peek_x) {
             const uint32_t g = xbase + (uint32_t)z + 1u;
             mbar_wait(smem_u32(&full_x[g % WT_XS]), (g / WT_XS) & 1u);
           }
           const uint32_t gd = dbase + (uint32_t)z;
-          mbar_wait(smem_u32(&full_d[gd % WT_DS]), (gd / WT_DS) & 1u);
+          if (!peek_d) mbar_wait(smem_u32(&full_d[gd % WT_DS]), (gd / WT_DS) & 1u);
+          peek_x = peek_d = false;
+          if (z + 2 < D) {
+            const uint32_t g = xbase + (uint32_t)z + 2u;
+            peek_x = mbar_test_wait(smem_u32(&full_x[g % WT_XS]), (g / WT_XS) & 1u);
+          }
+          if (z + 1 < D) {
+            const uint32_t g = gd + 1u;
+            peek_d = mbar_test_wait(smem_u32(&full_d[g % WT_DS]), (g / WT_DS) & 1u);
+          }
           tc_fence_after();
           const uint32_t da = smem_u32(ds + (gd % WT_DS) * WT_D_BYTES);
 #pragma unroll
