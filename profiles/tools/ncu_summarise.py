@@ -2,6 +2,8 @@
 
     python profiles/tools/ncu_summarise.py gpurun_out/prof_r2_wave.ncu-rep profiles/r02_wave_ncu_full_summary.csv \
         [--skip N]   (N leading launches are the warm-up call of profiles/tools/ncu_wave.py)
+        [--no-traffic]   (a capture of something else than the predict wave, e.g. ncu_train.py:
+                          leave profiles/roofline_traffic.json alone)
 
 Writes the CSV (one row per kernel launch: duration, DRAM bytes, tensor-pipe / shared-memory /
 L2 / SM utilisation, registers, dynamic shared memory, cluster size, achieved occupancy) and
@@ -54,7 +56,7 @@ def main():
 
     per = [num(r, "dram__bytes_read.sum") + num(r, "dram__bytes_write.sum") for r in body[skip:]
            if "conv3x3_zfold2_kernel" in r[col["Kernel Name"]]]
-    if per:
+    if per and "--no-traffic" not in sys.argv:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json"), "w") as f:
             json.dump({"kernel": "conv3x3_zfold2_kernel",
                        "source": f"{os.path.relpath(out_csv, ROOT)} (ncu --set full --clock-control none, "

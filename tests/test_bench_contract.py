@@ -31,6 +31,17 @@ def test_flop_accounting_matches_survey_figures():
     assert bench.volume_shape(1) == (512, 512, 512) and bench.volume_shape(8) == (1024, 1024, 1024)
 
 
+def test_training_step_flop_accounting():
+    """`bench.py --workload train`: forward convs on full patches (nothing trimmed), data gradients
+    for all layers but the stem, weight gradients for all."""
+    import bench
+
+    fl = bench.train_flops(16, 96)
+    head = 2 * 96 ** 3 * 3 * 32
+    assert fl["fprop"] == 16 * (bench.F_PATCH_96 - head) == fl["wgrad"]
+    assert fl["dgrad"] == fl["fprop"] - 16 * bench.F_STEM_96
+
+
 def test_reference_arm_prints_one_contract_line():
     res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference",
                           "--steps", "1", "--warmup", "0"], capture_output=True, text=True,

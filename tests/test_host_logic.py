@@ -187,6 +187,31 @@ def test_input_checks_raise_instead_of_altering_the_image():
         inference._as_volume_u16(vol.astype(np.float64), 1000)
 
 
+def test_trainer_fails_loudly_without_gpu():
+    """The training step has no CPU fallback either: exa_train_create fails without a device, and a
+    train()-mode forward on CPU tensors raises instead of running torch modules."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = _native.lib()
+    h = ctypes.c_void_p()
+    code = lib.exa_train_create(0, 0, ctypes.byref(h))
+    assert code < 0 and not h.value
+    assert b"no CPU fallback" in lib.exa_train_last_error(None)
+    assert lib.exa_train_forward(None, None, 1, (ctypes.c_int32 * 3)(16, 16, 16), None, None) < 0
+    from aind_exaspim_neuron_segmentation_b200 import UNet3D
+
+    m = UNet3D(3).train()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(2, 1, 16, 16, 16))
+    # the variants the Trainer never builds are refused in train() mode before any kernel runs
+    for kw in (dict(trilinear=False), dict(width_multiplier=2)):
+        wide = UNet3D(3, **kw).train()
+        with pytest.raises((NotImplementedError, RuntimeError)):
+            wide(torch.zeros(2, 1, 16, 16, 16))
+
+
 def test_model_copies_and_training_mode():
     """Engines live outside the module: models deep-copy / pickle, and a model put back into
     training mode never silently runs the folded eval-mode engine."""
