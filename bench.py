@@ -656,10 +656,7 @@ def run_train(args):
         "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": f"one training step (forward with batch-statistics BatchNorm, "
-                               f"BCEWithLogitsLoss, backward to all 74 parameter gradients) on "
-                               f"{B} patches of {P}^3, UNet3D(output_channels=3)",
-                   "batch": B, "patch": [P, P, P],
+        "config": {"workload": train_workload_text(B, P), "batch": B, "patch": [P, P, P],
                    "l2": f"activations of one step ({eng.workspace_bytes / 2**30:.1f} GiB workspace) "
                          "are far larger than the L2",
                    "workspace_gib": eng.workspace_bytes / 2 ** 30},
@@ -693,6 +690,49 @@ def run_train(args):
                                 "sample": f"oracle/train_ref.py (torch autograd, fp32) on 2 patches of "
                                           f"{P}^3, {cpu_s:.2f} s"}
     emit(line)
+
+
+def train_workload_text(B, P):
+    return (f"one training step (forward with batch-statistics BatchNorm, BCEWithLogitsLoss, "
+            f"backward to all 74 parameter gradients) on {B} patches of {P}^3, "
+            "UNet3D(output_channels=3)")
+
+
+def run_train_reference(args):
+    """`--workload train --impl reference`: the oracle's torch-autograd step (oracle/train_ref.py,
+    the reference's own CPU arithmetic) on the host cores, each step a bounded sample of the
+    workload (2 of the B patches)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    from oracle.train_ref import train_inputs_structured, train_step_ref
+    from oracle.unet_ref import rescaled_state_dict
+
+    B, P = args.train_batch, args.patch
+    torch.set_num_threads(os.cpu_count())
+    sd = rescaled_state_dict(0)
+    x, y = train_inputs_structured(1, 2, (P, P, P))
+    for _ in range(min(args.warmup, 1)):
+        train_step_ref(x, y, sd)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        train_step_ref(x, y, sd)
+    sec = (time.perf_counter() - t0) / args.steps
+    value = 2 * P ** 3 / sec
+    base = {"value": value, "unit": "voxels/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"oracle/train_ref.py (torch autograd, fp32) on 2 of the {B} patches, "
+                      f"{sec:.2f} s/step"}
+    emit({"impl": "reference", "metric": "training patch voxels/sec", "value": value,
+          "unit": "voxels/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+          "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+          "dtype": "f32", "data": "synthetic",
+          "config": {"workload": train_workload_text(B, P), "batch": B, "patch": [P, P, P]},
+          "cpu_baseline": base,
+          "e2e": {"value": value, "unit": "voxels/s", "h2d_bytes_per_step": 0,
+                  "d2h_bytes_per_step": 0},
+          "gpu_launches": 0})
 
 
 def run_train_library(args):
@@ -1057,7 +1097,7 @@ def main():
     if args.workload == "segment":
         run_segment(args)
     elif args.workload == "train":
-        run_train_library(args) if args.impl == "library" else run_train(args)
+        {"library": run_train_library, "reference": run_train_reference}.get(args.impl, run_train)(args)
     elif args.impl == "reference":
         run_reference(args)
     elif args.impl == "library":

@@ -60,6 +60,19 @@ def test_reference_arm_prints_one_contract_line():
     assert "sample" in base and line["config"]["workload"].startswith("predict() on a synthetic 512x512x512")
 
 
+def test_train_reference_arm_prints_one_contract_line():
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "train",
+                          "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, res.stdout[-2000:]
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["metric"] == "training patch voxels/sec"
+    assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["gpu_launches"] == 0
+    assert line["config"]["batch"] == 16 and line["config"]["patch"] == [96, 96, 96]
+
+
 def test_adapted_rand_on_device_equals_the_oracle_form():
     """bench.py --workload segment scores 1024^3 label volumes with a torch implementation of the
     oracle's adapted-Rand agreement; both must agree (here on CPU tensors)."""
