@@ -1084,6 +1084,11 @@ def main():
     ap.add_argument("--patch", type=int, default=96, choices=[96, 128],
                     help="patch edge: 96 = the headline workload; 128 = BASELINE config 4 (not a bench line)")
     args = ap.parse_args()
+    if args.workload == "train" and args.gpus != 1 and args.impl == "b200":
+        # the reference trains on one GPU (train.py:77); data-parallel replicas would need a
+        # gradient all-reduce that is not built, and N unsynchronised copies measure nothing
+        raise SystemExit("bench.py --workload train runs on one GPU (the reference's Trainer is "
+                         "single-GPU, train.py:77); use --gpus 1")
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
         # convenience: launched without torchrun -> start one process per GPU ourselves
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
