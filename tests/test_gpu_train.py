@@ -107,6 +107,22 @@ def test_train_step_fp32_mode_matches_oracle(batch, patch):
             assert int(v) == 1, key
 
 
+def test_train_step_foreground_mode_single_output_channel():
+    """Trainer(affinity_mode=False) builds UNet3D(output_channels=1) (train.py:75-77): the head and
+    its backward with one channel, fp32 validation mode against the oracle."""
+    from oracle.train_ref import train_inputs, train_step_ref
+
+    sd = state_dict_for("rescaled", 16, out_channels=1)
+    x, y = train_inputs(26, 2, (32, 32, 32), out_channels=1)
+    ref = train_step_ref(x, y, sd)
+    model = _model(sd, "fp32")
+    logits, loss = _step(model, x, y)
+    assert logits.shape == (2, 1, 32, 32, 32)
+    assert (logits - ref["logits"]).abs().max().item() <= FP32_LOGIT_TOL
+    assert abs(loss - ref["loss"]) <= 1e-5
+    _compare_grads(model, ref, FP32_GRAD_REL)
+
+
 @pytest.mark.parametrize("batch,patch", [(2, (32, 32, 32)), (3, (16, 32, 48)), (1, (64, 64, 64))])
 def test_train_step_bf16_mode_matches_oracle(batch, patch):
     from oracle.train_ref import train_inputs_structured, train_step_ref
