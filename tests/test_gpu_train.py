@@ -344,3 +344,20 @@ def test_bce_with_logits_kernel_matches_torch():
     loss, grad = bce_with_logits(logits.detach(), target, grad_scale=64.0)
     assert abs(float(loss) - float(ref)) <= 1e-6
     assert (grad - logits.grad).abs().max().item() <= 1e-9 + 1e-5 * logits.grad.abs().max().item()
+
+
+def test_weight_grad_mma_sync_fallback_matches_torch():
+    """EXA_WGRAD=mma selects the warp-level mma.sync weight-gradient kernel (the first version of
+    the step, kept as the A/B arm of the tcgen05 kernel): the bf16 operator cases again, in a fresh
+    process because the knob is read once."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_train.py"),
+                          "-q", "-x", "-k", "conv_weight_grad_operator and bf16"],
+                         capture_output=True, text=True, timeout=600, cwd=root,
+                         env={**os.environ, "EXA_WGRAD": "mma"})
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert " passed" in res.stdout and "failed" not in res.stdout, res.stdout[-500:]
