@@ -7,6 +7,11 @@
  * (reference src/aind_exaspim_neuron_segmentation/inference.py:29-126) and the model it
  * drives (machine_learning/unet3d.py:16-336, loaded by inference.py:400-424).
  *
+ * Widened, one row of SURVEY.md section 8f at a time, to the callers either side of that path:
+ * affinities_to_segmentation (inference.py:196-237; exa_affinities_to_segmentation*), streaming
+ * and float inputs, the model variants of unet3d.py:37, and the Trainer's training step
+ * (machine_learning/train.py:123-157, 200-223; exa_train_*).
+ *
  * The reference is pure Python and has no FFI of its own; its boundary for this path is
  * two Python functions plus the nn.Module call convention.  The
  * entry points below are what a ctypes binding of those functions needs -- see
