@@ -38,8 +38,8 @@ def test_training_step_flop_accounting():
 
     fl = bench.train_flops(16, 96)
     head = 2 * 96 ** 3 * 3 * 32
-    assert fl["fprop"] == 16 * (bench.F_PATCH_96 - head) == fl["wgrad"]
-    assert fl["dgrad"] == fl["fprop"] - 16 * bench.F_STEM_96
+    assert fl["fprop"] == 16 * (bench.F_PATCH_96 - head) == fl["wgrad"] + fl["wgrad_stem"]
+    assert fl["dgrad"] == fl["wgrad"] == fl["fprop"] - 16 * bench.F_STEM_96
 
 
 def test_reference_arm_prints_one_contract_line():
