@@ -10,7 +10,8 @@ so the reference's ``Trainer`` (optimizer, GradScaler, scheduler) runs unchanged
 What runs natively: the convolutions and their data gradients on the tcgen05 kernels of the
 inference path, BatchNorm3d with batch statistics (running statistics are updated in place like
 ``nn.BatchNorm3d`` does), the backward of BatchNorm/LeakyReLU/MaxPool3d/Upsample/head and the
-weight gradients (warp-level tensor-core MMA).  Nothing here falls back to torch operators.
+weight gradients (a tcgen05 kernel, csrc/train_wgrad.cu; ``EXA_WGRAD=mma`` selects the earlier
+warp-level MMA kernel).  Nothing here falls back to torch operators.
 """
 
 import ctypes
